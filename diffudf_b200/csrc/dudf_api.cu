@@ -1,0 +1,316 @@
+// C-ABI layer of libdudf_b200.so (declared in include/dudf_b200.h): context, workspaces and the
+// orchestration of the kernels.  No torch types; pointers + sizes only.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "dudf_common.cuh"
+#include "dudf_kernels.h"
+
+static thread_local std::string g_err;
+void dudf_set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+namespace dudf {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      dudf_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      return 1;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace dudf
+
+struct dudf_ctx {
+  int n_hidden = 0, n_lin = 0, device = 0, sms = 148;
+  float w0 = 30.f, ww = 30.f;
+  bool weights_set = false;
+  float* Wd[DUDF_MAX_LAYERS] = {};
+  float* bd[DUDF_MAX_LAYERS] = {};
+  float* Wtd[DUDF_MAX_LAYERS] = {};
+  void* tc_packed = nullptr;
+  dudf::DevBuf ws_out, ws_x64;
+  NetView view() const {
+    NetView v;
+    memset(&v, 0, sizeof(v));
+    for (int i = 0; i < n_lin; ++i) { v.W[i] = Wd[i]; v.b[i] = bd[i]; v.Wt[i] = Wtd[i]; }
+    v.n_lin = n_lin;
+    v.w0 = w0;
+    v.ww = ww;
+    return v;
+  }
+};
+
+using namespace dudf;
+
+extern "C" {
+
+int dudf_version(void) { return 100; }
+const char* dudf_last_error(void) { return g_err.c_str(); }
+
+int dudf_create(int n_hidden, float w0, float ww, dudf_ctx** out) {
+  DUDF_REQUIRE(out != nullptr, "dudf_create: null output pointer");
+  DUDF_REQUIRE(n_hidden >= 1 && n_hidden + 1 <= DUDF_MAX_LAYERS, "dudf_create: n_hidden=%d unsupported (1..%d)", n_hidden,
+               DUDF_MAX_LAYERS - 1);
+  int dev = 0;
+  DUDF_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DUDF_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  DUDF_REQUIRE(prop.major == 10, "dudf_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev,
+               prop.major, prop.minor);
+  dudf_ctx* c = new dudf_ctx();
+  c->n_hidden = n_hidden;
+  c->n_lin = n_hidden + 1;
+  c->device = dev;
+  c->sms = prop.multiProcessorCount;
+  c->w0 = w0;
+  c->ww = ww;
+  for (int i = 0; i < c->n_lin; ++i) {
+    const size_t in = (i == 0) ? 3 : 256, outn = (i == c->n_lin - 1) ? 1 : 256;
+    DUDF_CUDA_OK(cudaMalloc(&c->Wd[i], in * outn * sizeof(float)));
+    DUDF_CUDA_OK(cudaMalloc(&c->bd[i], outn * sizeof(float)));
+    if (i > 0 && i < c->n_lin - 1) DUDF_CUDA_OK(cudaMalloc(&c->Wtd[i], 256 * 256 * sizeof(float)));
+  }
+  DUDF_CUDA_OK(cudaMalloc(&c->tc_packed, tc_packed_bytes(c->n_lin)));
+  *out = c;
+  return 0;
+}
+
+int dudf_destroy(dudf_ctx* c) {
+  if (!c) return 0;
+  for (int i = 0; i < c->n_lin; ++i) {
+    cudaFree(c->Wd[i]);
+    cudaFree(c->bd[i]);
+    if (c->Wtd[i]) cudaFree(c->Wtd[i]);
+  }
+  cudaFree(c->tc_packed);
+  c->ws_out.release();
+  c->ws_x64.release();
+  delete c;
+  return 0;
+}
+
+int dudf_set_weights(dudf_ctx* c, const float* const* W, const float* const* b, void* stream) {
+  DUDF_REQUIRE(c && W && b, "dudf_set_weights: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < c->n_lin; ++i) {
+    const size_t in = (i == 0) ? 3 : 256, outn = (i == c->n_lin - 1) ? 1 : 256;
+    DUDF_REQUIRE(W[i] && b[i], "dudf_set_weights: null pointer for layer %d", i);
+    DUDF_CUDA_OK(cudaMemcpyAsync(c->Wd[i], W[i], in * outn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DUDF_CUDA_OK(cudaMemcpyAsync(c->bd[i], b[i], outn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (c->Wtd[i]) {
+      int rc = transpose256(c->Wd[i], c->Wtd[i], st);
+      if (rc) return rc;
+    }
+  }
+  int rc = tc_pack(c->view(), c->tc_packed, st);
+  if (rc) return rc;
+  c->weights_set = true;
+  return 0;
+}
+
+static int order_to_nch(int order) { return order == 0 ? 1 : order == 1 ? 4 : order == 2 ? 10 : order == 3 ? 20 : -1; }
+
+static int run_forward(dudf_ctx* c, int nch, const float* x, int64_t P, int gridN, int64_t first, const QueryOut& out,
+                       int precision, cudaStream_t st) {
+  if (precision == DUDF_PRECISION_TC16) {
+    DUDF_REQUIRE(nch != 20, "third-order jets are only available with DUDF_PRECISION_FP32");
+    return tc_forward(c->tc_packed, c->view(), nch, x, P, gridN, first, out, c->sms, st);
+  }
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "unknown precision %d", precision);
+  return simt_forward(c->view(), nch, x, P, gridN, first, out, nullptr, nullptr, 0, 0, c->sms, st);
+}
+
+int dudf_query_points(dudf_ctx* c, const float* x, int64_t P, int order, int flags, float alpha, float* f, float* g,
+                      float* H, float* T, int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_query_points: weights not set");
+  DUDF_REQUIRE(x != nullptr || P == 0, "dudf_query_points: null coordinates");
+  const int nch = order_to_nch(order);
+  DUDF_REQUIRE(nch > 0, "dudf_query_points: order %d unsupported (0..3)", order);
+  if (P <= 0) return 0;
+  QueryOut o{f, g, H, T, nullptr, flags, alpha};
+  return run_forward(c, nch, x, P, 0, 0, o, precision, (cudaStream_t)stream);
+}
+
+int dudf_query_grid(dudf_ctx* c, int N, int64_t first, int64_t count, int flags, float alpha, float* df, float* vecs,
+                    float* H, int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_query_grid: weights not set");
+  DUDF_REQUIRE(N >= 2, "dudf_query_grid: N=%d", N);
+  DUDF_REQUIRE(first >= 0 && count >= 0 && first + count <= (int64_t)N * N * N, "dudf_query_grid: range out of bounds");
+  if (count == 0) return 0;
+  const int nch = H ? 10 : (vecs ? 4 : 1);
+  QueryOut o{df, vecs, H, nullptr, nullptr, flags, alpha};
+  return run_forward(c, nch, nullptr, count, N, first, o, precision, (cudaStream_t)stream);
+}
+
+int dudf_eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,
+                     void* stream) {
+  DUDF_REQUIRE(H && n, "dudf_eig_normals: null argument");
+  return eig_normals(H, ref_dir, ref_mode, P, n, dirs, lam, (cudaStream_t)stream);
+}
+
+int dudf_curvature(const float* H, const float* T, int64_t P, float* n, float* mean, float* gauss, float* J, void* stream) {
+  DUDF_REQUIRE(H && T, "dudf_curvature: null argument");
+  return curvature(H, T, P, n, mean, gauss, J, (cudaStream_t)stream);
+}
+
+int dudf_field_vectors(const float* g, const float* H, int64_t P, float* vecs, void* stream) {
+  DUDF_REQUIRE(g && H && vecs, "dudf_field_vectors: null argument");
+  return field_vectors(g, H, P, vecs, (cudaStream_t)stream);
+}
+
+int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
+                       double* H_host, int64_t max_batch, int precision) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_evaluate_host: weights not set");
+  DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_evaluate_host: order %d", order);
+  if (N <= 0) return 0;
+  if (max_batch <= 0) max_batch = 1 << 20;
+  const int64_t B = max_batch < N ? max_batch : N;
+  // layout of the fp32 chunk: x[3B] f[B] g[3B] H[9B]; the fp64 chunk mirrors f,g,H
+  if (c->ws_out.ensure((size_t)B * 16 * sizeof(float))) return 1;
+  if (c->ws_x64.ensure((size_t)B * 13 * sizeof(double))) return 1;
+  float* xd = (float*)c->ws_out.p;
+  float* fd = xd + 3 * B;
+  float* gd = fd + B;
+  float* Hd = gd + 3 * B;
+  double* f64 = (double*)c->ws_x64.p;
+  double* g64 = f64 + B;
+  double* H64 = g64 + 3 * B;
+  const int nch = order_to_nch(order);
+  cudaStream_t st = 0;
+  for (int64_t head = 0; head < N; head += B) {
+    const int64_t n = (N - head < B) ? N - head : B;
+    DUDF_CUDA_OK(cudaMemcpyAsync(xd, x_host + head * 3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    QueryOut o{fd, order >= 1 ? gd : nullptr, order >= 2 ? Hd : nullptr, nullptr, nullptr, 0, 0.f};
+    int rc = run_forward(c, nch, xd, n, 0, 0, o, precision, st);
+    if (rc) return rc;
+    if (f_host) {
+      if ((rc = f32_to_f64(fd, f64, n, st))) return rc;
+      DUDF_CUDA_OK(cudaMemcpyAsync(f_host + head, f64, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (g_host && order >= 1) {
+      if ((rc = f32_to_f64(gd, g64, n * 3, st))) return rc;
+      DUDF_CUDA_OK(cudaMemcpyAsync(g_host + head * 3, g64, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (H_host && order >= 2) {
+      if ((rc = f32_to_f64(Hd, H64, n * 9, st))) return rc;
+      DUDF_CUDA_OK(cudaMemcpyAsync(H_host + head * 9, H64, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    DUDF_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training primitives: jet forward with stash, loss epilogues, reverse sweep, weight gradients.
+// The stashes Z (pre-activations), A (activations) and Zb (pre-activation adjoints) are caller-owned
+// fp32 arrays [n_hidden][256][ld]; a call works on the column range starting at col0.
+// ---------------------------------------------------------------------------------------------
+int64_t dudf_stash_columns(int order, int64_t P) {
+  const int nch = order_to_nch(order);
+  if (nch < 0 || nch > 10 || P < 0) return -1;
+  const int pt = simt_tile_points(nch), nc = simt_tile_cols(nch);
+  return (P + pt - 1) / pt * nc;
+}
+
+int dudf_jet_forward(dudf_ctx* c, const float* x, int64_t P, int order, float* packed, float* Z, float* A, int64_t ld,
+                     int64_t col0, int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_jet_forward: weights not set");
+  DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_jet_forward: order %d (0..2)", order);
+  DUDF_REQUIRE(x && packed && Z && A, "dudf_jet_forward: null argument");
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "dudf_jet_forward: precision %d is not available for training yet", precision);
+  if (P <= 0) return 0;
+  DUDF_REQUIRE(ld % 4 == 0 && col0 % 4 == 0 && col0 + dudf_stash_columns(order, P) <= ld, "dudf_jet_forward: stash too small");
+  QueryOut o{nullptr, nullptr, nullptr, nullptr, packed, 0, 0.f};
+  return simt_forward(c->view(), order_to_nch(order), x, P, 0, 0, o, Z, A, ld, col0, c->sms, (cudaStream_t)stream);
+}
+
+int dudf_jet_backward(dudf_ctx* c, const float* x, int64_t P, int order, const float* seeds, const float* Z, float* Zb,
+                      int64_t ld, int64_t col0, float* const* gW, float* const* gb, int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_jet_backward: weights not set");
+  DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_jet_backward: order %d (0..2)", order);
+  DUDF_REQUIRE(x && seeds && Z && Zb && gW && gb, "dudf_jet_backward: null argument");
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "dudf_jet_backward: precision %d is not available for training yet", precision);
+  if (P <= 0) return 0;
+  GradView gv;
+  memset(&gv, 0, sizeof(gv));
+  for (int i = 0; i < c->n_lin; ++i) {
+    DUDF_REQUIRE(gW[i] && gb[i], "dudf_jet_backward: null gradient pointer for layer %d", i);
+    gv.W[i] = gW[i];
+    gv.b[i] = gb[i];
+  }
+  return simt_backward(c->view(), gv, order_to_nch(order), x, P, seeds, Z, Zb, ld, col0, c->sms, (cudaStream_t)stream);
+}
+
+int dudf_jet_wgrad(dudf_ctx* c, const float* Zb, const float* A, int64_t ld, int64_t ncols, float* const* gW, int precision,
+                   void* stream) {
+  DUDF_REQUIRE(c && Zb && A && gW, "dudf_jet_wgrad: null argument");
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "dudf_jet_wgrad: precision %d is not available for training yet", precision);
+  GradView gv;
+  memset(&gv, 0, sizeof(gv));
+  for (int i = 0; i < c->n_lin; ++i) gv.W[i] = gW[i];
+  return simt_wgrad(c->view(), gv, Zb, A, ld, ncols, c->sms, (cudaStream_t)stream);
+}
+
+int dudf_loss(int mode, const float* packed, int nch, const float* normals, const float* dist, int64_t P, int64_t P_global,
+              const float* w_host, float alpha, const float* upstream, float* seeds, double* terms, double* s2_stats,
+              void* stream) {
+  DUDF_REQUIRE(packed && dist && w_host, "dudf_loss: null argument");
+  DUDF_REQUIRE(mode == DUDF_LOSS_S1 || mode == DUDF_LOSS_S2 || mode == DUDF_LOSS_SIREN, "dudf_loss: unknown mode %d", mode);
+  DUDF_REQUIRE(nch == 1 || nch == 4 || nch == 10, "dudf_loss: nch %d", nch);
+  DUDF_REQUIRE(mode != DUDF_LOSS_SIREN || nch >= 4, "dudf_loss: loss_siren needs gradients");
+  DUDF_REQUIRE(normals || (mode == DUDF_LOSS_S2), "dudf_loss: normals required");
+  LossArgs a;
+  a.mode = mode; a.packed = packed; a.nch = nch; a.normals = normals; a.dist = dist; a.P = P; a.P_global = P_global;
+  for (int k = 0; k < 4; ++k) a.w[k] = w_host[k];
+  a.alpha = alpha; a.upstream = upstream; a.seeds = seeds; a.terms = terms; a.s2_stats = s2_stats;
+  return loss_seeds(a, (cudaStream_t)stream);
+}
+
+int dudf_loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, void* stream) {
+  DUDF_REQUIRE(packed && dist && stats, "dudf_loss_s2_stats: null argument");
+  return loss_s2_stats(packed, dist, P, stats, (cudaStream_t)stream);
+}
+
+int dudf_loss_s2_finish(const double* stats, float w0, float w1, double* terms, void* stream) {
+  DUDF_REQUIRE(stats && terms, "dudf_loss_s2_finish: null argument");
+  return s2_finish(stats, w0, w1, terms, (cudaStream_t)stream);
+}
+
+int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   int64_t t, void* stream) {
+  DUDF_REQUIRE(p && g && m && v, "dudf_adam_step: null argument");
+  DUDF_REQUIRE(t >= 1, "dudf_adam_step: step count must be >= 1");
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream);
+}
+
+int dudf_selftest_umma(int variant, float* max_err_host) {
+  DUDF_REQUIRE(max_err_host != nullptr, "dudf_selftest_umma: null output");
+  return tc_selftest(variant, max_err_host, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// Internal (C++) interface between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "dudf_common.cuh"
+#include "../../include/dudf_b200.h"
+
+namespace dudf {
+
+// where a query writes its per-point results (any pointer may be null)
+struct QueryOut {
+  float* f;        // [P]
+  float* g;        // [P][3]
+  float* H;        // [P][3][3]
+  float* T;        // [P][10] symmetric third derivatives
+  float* packed;   // [P][NCH] raw channels (training path)
+  int flags;       // DUDF_Q_*
+  float alpha;
+};
+
+// ---- fp32 CUDA-core path (dudf_simt.cu) ----
+int simt_forward(const NetView& net, int nch, const float* x, int64_t P, int gridN, int64_t grid_first,
+                 const QueryOut& out, float* Zst, float* Ast, int64_t ctot, int64_t col0, int sms, cudaStream_t st);
+int simt_backward(const NetView& net, const GradView& grad, int nch, const float* x, int64_t P, const float* seeds,
+                  const float* Zst, float* Zbst, int64_t ctot, int64_t col0, int sms, cudaStream_t st);
+int simt_wgrad(const NetView& net, const GradView& grad, const float* Zbst, const float* Ast, int64_t ctot,
+               int64_t ncols, int sms, cudaStream_t st);
+int simt_tile_points(int nch);   // points per tile of the SIMT kernels
+int simt_tile_cols(int nch);
+
+// ---- tcgen05 path (dudf_tc.cu) ----
+struct TcPacked;                 // opaque device image of the fp16 operand tiles
+size_t tc_packed_bytes(int n_lin);
+int tc_pack(const NetView& net, void* packed, cudaStream_t st);
+int tc_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN,
+               int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
+int tc_selftest(int variant, float* max_err, cudaStream_t st);
+
+// ---- loss epilogues, optimiser, utilities (dudf_misc.cu) ----
+struct LossArgs {
+  int mode;                 // DUDF_LOSS_*
+  const float* packed;      // [P][NCH] forward outputs
+  int nch;
+  const float* normals;     // [P][3]
+  const float* dist;        // [P]
+  int64_t P;                // rows of this call
+  int64_t P_global;         // divisor of the means
+  float w[4];
+  float alpha;
+  const float* upstream;    // [4] dL/d(term) or null (ones)
+  float* seeds;             // [P][NCH] out
+  double* terms;            // [4] accumulated (atomicAdd)
+  double* s2_stats;         // [3] n, sum, sumsq (mode S2)
+};
+int loss_seeds(const LossArgs& a, cudaStream_t st);
+int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st);
+int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+              int64_t t, cudaStream_t st);
+int transpose256(const float* W, float* Wt, cudaStream_t st);
+int eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,
+                cudaStream_t st);
+int curvature(const float* H, const float* T, int64_t P, float* n, float* mean, float* gauss, float* J, cudaStream_t st);
+int field_vectors(const float* g, const float* H, int64_t P, float* vecs, cudaStream_t st);
+int f32_to_f64(const float* src, double* dst, int64_t n, cudaStream_t st);
+
+}  // namespace dudf

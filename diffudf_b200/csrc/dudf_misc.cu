@@ -1,0 +1,371 @@
+// Per-row epilogues of the DUDF hot path: loss terms and their adjoint seeds, Adam, eigen-normals,
+// curvature, the extract_fields fallback and small utilities.  All HBM-bound, one thread per row.
+#include "dudf_common.cuh"
+#include "dudf_kernels.h"
+
+namespace dudf {
+
+__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+__device__ __forceinline__ double sgnd(double x) { return (double)((x > 0.0) - (x < 0.0)); }
+
+template <int N>
+__device__ __forceinline__ void block_reduce_add(double (&v)[N], double* dst) {
+  __shared__ double sh[N][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double x = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += sh[threadIdx.x][w];
+    if (x != 0.0) atomicAdd(&dst[threadIdx.x], x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss_s1 / loss_siren terms + seeds (src/loss_functions.py:123-155, :82-104); loss_s2 seeds (:106-121)
+// seeds use the stored-variable convention: off-diagonal Hessian channels carry Hbar_ij + Hbar_ji.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_seed_kernel(LossArgs a) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  if (p < a.P) {
+    const int nch = a.nch;
+    const float* v = a.packed + p * nch;
+    const float f = v[0];
+    const float d = a.dist[p];
+    const bool on = (d == 0.f);
+    const float up0 = a.upstream ? a.upstream[0] : 1.f, up1 = a.upstream ? a.upstream[1] : 1.f;
+    const float up2 = a.upstream ? a.upstream[2] : 1.f, up3 = a.upstream ? a.upstream[3] : 1.f;
+    const float invP = 1.0f / (float)a.P_global;
+    float sd[10];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) sd[c] = 0.f;
+    if (a.mode == DUDF_LOSS_S1) {
+      const float th = tanhf(a.alpha * d);
+      const float tdf = d * th;
+      if (on) {
+        t[0] = fabsf(f);
+        sd[0] = up0 * a.w[0] * invP * sgnf(f);
+      } else {
+        t[1] = fabsf(tdf - f);
+        sd[0] = -up1 * a.w[1] * invP * sgnf(tdf - f);
+      }
+      if (a.w[3] != 0.f && nch >= 4) {
+        const float gx = v[1], gy = v[2], gz = v[3];
+        const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+        const float tgt = fabsf(th + d * a.alpha * (1.f - th * th));
+        t[3] = fabsf(gn - tgt);
+        if (gn > 0.f) {
+          const float k = up3 * a.w[3] * invP * sgnf(gn - tgt) / gn;
+          sd[1] = k * gx; sd[2] = k * gy; sd[3] = k * gz;
+        }
+      }
+      if (a.w[2] != 0.f && nch >= 10 && on) {
+        double H[3][3], lam[3], V[3][3];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) H[i][j] = (double)v[4 + sym2(i, j)];
+        eigh3<double>(H, lam, V);
+        const double n0 = a.normals[p * 3], n1 = a.normals[p * 3 + 1], n2 = a.normals[p * 3 + 2];
+        const double nn = fmax(sqrt(n0 * n0 + n1 * n1 + n2 * n2), 1e-8);
+        const double vx = V[0][2], vy = V[1][2], vz = V[2][2];
+        const double vn = fmax(sqrt(vx * vx + vy * vy + vz * vz), 1e-8);
+        const double cs = (n0 * vx + n1 * vy + n2 * vz) / (nn * vn);
+        t[2] = 1.0 - fabs(cs);
+        const double coef = -(double)up2 * a.w[2] * invP * sgnd(cs);
+        const double nb[3] = {coef * (n0 / (nn * vn) - cs * vx / (vn * vn)), coef * (n1 / (nn * vn) - cs * vy / (vn * vn)),
+                              coef * (n2 / (nn * vn) - cs * vz / (vn * vn))};
+        double Hb[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        const double vv[3] = {vx, vy, vz};
+        for (int j = 0; j < 2; ++j) {
+          const double cj = (V[0][j] * nb[0] + V[1][j] * nb[1] + V[2][j] * nb[2]) / (lam[2] - lam[j]);
+          for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) Hb[r][q] += cj * 0.5 * (V[r][j] * vv[q] + vv[r] * V[q][j]);
+        }
+        for (int i = 0; i < 3; ++i)
+          for (int j = i; j < 3; ++j) sd[4 + sym2(i, j)] = (float)((i == j) ? Hb[i][i] : Hb[i][j] + Hb[j][i]);
+      }
+      t[0] *= a.w[0] * (double)invP; t[1] *= a.w[1] * (double)invP;
+      t[2] *= a.w[2] * (double)invP; t[3] *= a.w[3] * (double)invP;
+    } else if (a.mode == DUDF_LOSS_SIREN) {
+      if (on) {
+        t[0] = fabsf(f);
+        sd[0] = up0 * a.w[0] * invP * sgnf(f);
+      } else {
+        const float e = expf(-1e2f * fabsf(f));
+        t[1] = e;
+        sd[0] = up1 * a.w[1] * invP * (-1e2f) * sgnf(f) * e;
+      }
+      const float gx = v[1], gy = v[2], gz = v[3];
+      const float gr = sqrtf(gx * gx + gy * gy + gz * gz);
+      const float gn = fmaxf(gr, 1e-8f);
+      if (on) {
+        const float n0 = a.normals[p * 3], n1 = a.normals[p * 3 + 1], n2 = a.normals[p * 3 + 2];
+        const float nn = fmaxf(sqrtf(n0 * n0 + n1 * n1 + n2 * n2), 1e-8f);
+        const float cs = (gx * n0 + gy * n1 + gz * n2) / (gn * nn);
+        t[2] = 1.f - cs;
+        const float k = -up2 * a.w[2] * invP;
+        sd[1] = k * (n0 / (gn * nn) - cs * gx / (gn * gn));
+        sd[2] = k * (n1 / (gn * nn) - cs * gy / (gn * gn));
+        sd[3] = k * (n2 / (gn * nn) - cs * gz / (gn * gn));
+      }
+      t[3] = (double)(gr - 1.f) * (double)(gr - 1.f);
+      if (gr > 0.f) {
+        const float k = up3 * a.w[3] * invP * 2.f * (gr - 1.f) / gr;
+        sd[1] += k * gx; sd[2] += k * gy; sd[3] += k * gz;
+      }
+      t[0] *= a.w[0] * (double)invP; t[1] *= a.w[1] * (double)invP;
+      t[2] *= a.w[2] * (double)invP; t[3] *= a.w[3] * (double)invP;
+    } else {  // S2: seeds from the global statistics
+      if (on && a.s2_stats) {
+        const double n = a.s2_stats[0], s1 = a.s2_stats[1], s2 = a.s2_stats[2];
+        const double mean = s1 / n;
+        const double var = (s2 - n * mean * mean) / (n - 1.0);
+        const double sdv = sqrt(var);
+        sd[0] = (float)(up0 * a.w[0] * sgnd(mean) / n + up1 * a.w[1] * ((double)f - mean) / ((n - 1.0) * sdv));
+      }
+    }
+    if (a.seeds) {
+      float* dst = a.seeds + p * nch;
+      for (int c = 0; c < nch; ++c) dst[c] = sd[c];
+    }
+  }
+  if (a.terms && a.mode != DUDF_LOSS_S2) block_reduce_add<4>(t, a.terms);
+}
+
+int loss_seeds(const LossArgs& a, cudaStream_t st) {
+  if (a.P <= 0) return 0;
+  const int64_t blocks = (a.P + 255) / 256;
+  loss_seed_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) s2_stats_kernel(const float* packed, const float* dist, int64_t P, double* stats) {
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    if (dist[p] == 0.f) {
+      const double f = packed[p];
+      t[0] += 1.0; t[1] += f; t[2] += f * f;
+    }
+  }
+  block_reduce_add<3>(t, stats);
+}
+
+int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st) {
+  if (P <= 0) return 0;
+  const int blocks = (int)std::min<int64_t>((P + 255) / 256, 1024);
+  s2_stats_kernel<<<blocks, 256, 0, st>>>(packed, dist, P, stats);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void s2_finish_kernel(const double* stats, float w0, float w1, double* terms) {
+  const double n = stats[0], mean = stats[1] / n;
+  const double var = (stats[2] - n * mean * mean) / (n - 1.0);
+  terms[0] = fabs(mean) * w0;
+  terms[1] = sqrt(var) * w1;
+  terms[2] = 0.0;
+  terms[3] = 0.0;
+}
+int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st) {
+  s2_finish_kernel<<<1, 1, 0, st>>>(stats, w0, w1, terms);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam defaults used by train.py:334-337)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float step_size, float bc2_sqrt,
+                                                   float b1, float b2, float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
+              cudaStream_t st) {
+  if (n <= 0) return 0;
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)sqrt(bc2), b1, b2, eps);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose256_kernel(const float* __restrict__ W, float* __restrict__ Wt) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = W[(by + r) * 256 + bx + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) Wt[(bx + r) * 256 + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+int transpose256(const float* W, float* Wt, cudaStream_t st) {
+  transpose256_kernel<<<dim3(8, 8), dim3(32, 8), 0, st>>>(W, Wt);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// eigen-normal / principal directions of a batch of Hessians
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void canon_sign(double V[3][3], int k) {
+  int im = 0;
+  double am = fabs(V[0][k]);
+  for (int i = 1; i < 3; ++i)
+    if (fabs(V[i][k]) > am) { am = fabs(V[i][k]); im = i; }
+  if (V[im][k] < 0.0)
+    for (int i = 0; i < 3; ++i) V[i][k] = -V[i][k];
+}
+
+__global__ void __launch_bounds__(256) eig_normals_kernel(const float* __restrict__ Hm, const float* __restrict__ ref,
+                                                          int ref_mode, int64_t P, float* n, float* dirs, float* lamo) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double H[3][3], lam[3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) H[i][j] = (double)Hm[p * 9 + i * 3 + j];
+  eigh3<double>(H, lam, V);
+  for (int k = 0; k < 3; ++k) canon_sign(V, k);
+  if (ref_mode != 0 && ref) {
+    const double dt = V[0][2] * ref[p * 3] + V[1][2] * ref[p * 3 + 1] + V[2][2] * ref[p * 3 + 2];
+    const bool flip = (ref_mode == 1) ? (dt < 0.0) : (dt > 0.0);
+    if (flip)
+      for (int i = 0; i < 3; ++i) V[i][2] = -V[i][2];
+  }
+  for (int i = 0; i < 3; ++i) n[p * 3 + i] = (float)V[i][2];
+  if (dirs)
+    for (int i = 0; i < 3; ++i) { dirs[p * 6 + i * 2] = (float)V[i][0]; dirs[p * 6 + i * 2 + 1] = (float)V[i][1]; }
+  if (lamo)
+    for (int k = 0; k < 3; ++k) lamo[p * 3 + k] = (float)lam[k];
+}
+
+int eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,
+                cudaStream_t st) {
+  if (P <= 0) return 0;
+  eig_normals_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(H, ref_dir, ref_mode, P, n, dirs, lam);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// mean / gaussian curvature from H and the symmetric third derivatives (src/render_st.py:42-55):
+// dn_i/dx_k = sum_{j<2} v_j[i] (v_j^T T[:,:,k] n) / (lam_2 - lam_j)      (SURVEY.md §8 a-M)
+__global__ void __launch_bounds__(256) curvature_kernel(const float* __restrict__ Hm, const float* __restrict__ Tm, int64_t P,
+                                                        float* n, float* meanc, float* gauss, float* Jout) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double H[3][3], lam[3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) H[i][j] = (double)Hm[p * 9 + i * 3 + j];
+  eigh3<double>(H, lam, V);
+  for (int k = 0; k < 3; ++k) canon_sign(V, k);
+  double T[3][3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 3; ++c) T[a][b][c] = (double)Tm[p * 10 + sym3(a, b, c)];
+  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < 2; ++j) {
+    const double inv = 1.0 / (lam[2] - lam[j]);
+    for (int k = 0; k < 3; ++k) {
+      double c = 0.0;
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) c += V[a][j] * T[a][b][k] * V[b][2];
+      c *= inv;
+      for (int i = 0; i < 3; ++i) J[i][k] += V[i][j] * c;
+    }
+  }
+  if (n)
+    for (int i = 0; i < 3; ++i) n[p * 3 + i] = (float)V[i][2];
+  if (Jout)
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) Jout[p * 9 + i * 3 + k] = (float)J[i][k];
+  if (meanc) meanc[p] = (float)(0.5 * (J[0][0] + J[1][1] + J[2][2]));
+  if (gauss) {
+    // -det [[J, n], [n^T, 0]] by cofactor expansion along the last row
+    const double nv[3] = {V[0][2], V[1][2], V[2][2]};
+    double M[4][4];
+    for (int i = 0; i < 3; ++i) {
+      for (int k = 0; k < 3; ++k) M[i][k] = J[i][k];
+      M[i][3] = nv[i];
+      M[3][i] = nv[i];
+    }
+    M[3][3] = 0.0;
+    double det = 0.0;
+    for (int c = 0; c < 4; ++c) {
+      double m3[3][3];
+      for (int i = 0; i < 3; ++i) {
+        int cc = 0;
+        for (int k = 0; k < 4; ++k) {
+          if (k == c) continue;
+          m3[i][cc++] = M[i][k];
+        }
+      }
+      const double d3 = m3[0][0] * (m3[1][1] * m3[2][2] - m3[1][2] * m3[2][1]) -
+                        m3[0][1] * (m3[1][0] * m3[2][2] - m3[1][2] * m3[2][0]) +
+                        m3[0][2] * (m3[1][0] * m3[2][1] - m3[1][1] * m3[2][0]);
+      det += (((3 + c) & 1) ? -1.0 : 1.0) * M[3][c] * d3;
+    }
+    gauss[p] = (float)(-det);
+  }
+}
+
+int curvature(const float* H, const float* T, int64_t P, float* n, float* mean, float* gauss, float* J, cudaStream_t st) {
+  if (P <= 0) return 0;
+  curvature_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(H, T, P, n, mean, gauss, J);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// extract_fields fallback (src/render_mc.py:77-93): where the normalised gradient has norm < 0.04
+// (only possible when grad f == 0 exactly) use the sign-aligned top eigenvector of the Hessian.
+__global__ void __launch_bounds__(256) field_vectors_kernel(const float* __restrict__ g, const float* __restrict__ Hm, int64_t P,
+                                                            float* vecs) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float gx = g[p * 3], gy = g[p * 3 + 1], gz = g[p * 3 + 2];
+  if (sqrtf(gx * gx + gy * gy + gz * gz) < 0.04f) {
+    double H[3][3], lam[3], V[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) H[i][j] = (double)Hm[p * 9 + i * 3 + j];
+    eigh3<double>(H, lam, V);
+    canon_sign(V, 2);
+    const double dt = gx * V[0][2] + gy * V[1][2] + gz * V[2][2];
+    const double sg = dt < 0.0 ? -1.0 : 1.0;
+    gx = (float)(sg * V[0][2]); gy = (float)(sg * V[1][2]); gz = (float)(sg * V[2][2]);
+  }
+  vecs[p * 3] = gx; vecs[p * 3 + 1] = gy; vecs[p * 3 + 2] = gz;
+}
+
+int field_vectors(const float* g, const float* H, int64_t P, float* vecs, cudaStream_t st) {
+  if (P <= 0) return 0;
+  field_vectors_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(g, H, P, vecs);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) f32_to_f64_kernel(const float* __restrict__ s, double* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
+}
+int f32_to_f64(const float* src, double* dst, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  f32_to_f64_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(src, dst, n);
+  DUDF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dudf

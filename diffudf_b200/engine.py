@@ -1,0 +1,173 @@
+"""Thin Python layer over the C ABI (include/dudf_b200.h): one `Engine` per SIREN module holds the
+native context, keeps its weight images in sync with the torch parameters and exposes the query /
+training primitives on torch CUDA tensors.  torch is used for device memory and streams only.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PRECISIONS = {"fp32": 0, "tc16": 1}
+LOSS_MODES = {"s1": 0, "s2": 1, "siren": 2}
+Q_ABS_INV_TANH = 1
+Q_NEG_NORMALIZE = 2
+NCH = {0: 1, 1: 4, 2: 10, 3: 20}
+# packed channel index of H[i][j]
+SYM6 = [[4, 5, 6], [5, 7, 8], [6, 8, 9]]
+
+
+def _f32c(t, device):
+    """float32 contiguous CUDA view/copy of a tensor or numpy array."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class Engine:
+    def __init__(self, n_hidden, w0, ww, device):
+        self.L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("diffudf_b200 runs on CUDA devices only (no CPU fallback); move the model with .to('cuda')")
+        self.n_hidden = n_hidden
+        self.h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dudf_create(n_hidden, float(w0), float(ww), ctypes.byref(self.h)), "dudf_create")
+        self._sig = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.dudf_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- weights ----
+    def sync_weights(self, weights, biases):
+        """Re-pack when any parameter changed (version counters / storage pointers)."""
+        sig = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+        if sig == self._sig:
+            return
+        ws = [w.detach() for w in weights]
+        bs = [b.detach() for b in biases]
+        for t in ws + bs:
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise RuntimeError("SIREN parameters must be contiguous float32 CUDA tensors")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dudf_set_weights(self.h, _ptr_array(ws), _ptr_array(bs), _lib.current_stream()), "dudf_set_weights")
+        self._sig = sig
+
+    # ---- queries ----
+    def query(self, x, order, precision="fp32", flags=0, alpha=0.0):
+        """x: (P,3) float32 CUDA.  Returns (f (P,), g (P,3)|None, H (P,3,3)|None, T (P,10)|None)."""
+        P = x.shape[0]
+        dev = x.device
+        f = torch.empty(P, device=dev, dtype=torch.float32)
+        g = torch.empty(P, 3, device=dev, dtype=torch.float32) if order >= 1 else None
+        H = torch.empty(P, 3, 3, device=dev, dtype=torch.float32) if order >= 2 else None
+        T = torch.empty(P, 10, device=dev, dtype=torch.float32) if order >= 3 else None
+        with torch.cuda.device(dev):
+            _lib.check(self.L.dudf_query_points(self.h, x.data_ptr(), P, order, flags, float(alpha), _lib.ptr(f), _lib.ptr(g),
+                                                _lib.ptr(H), _lib.ptr(T), PRECISIONS[precision], _lib.current_stream()),
+                       "dudf_query_points")
+        return f, g, H, T
+
+    def query_grid(self, N, first, count, precision="fp32", flags=0, alpha=0.0, want_vecs=True, want_hess=False, out=None):
+        dev = self.device
+        if out is None:
+            df = torch.empty(count, device=dev, dtype=torch.float32)
+            vecs = torch.empty(count, 3, device=dev, dtype=torch.float32) if want_vecs else None
+        else:
+            df, vecs = out
+        H = torch.empty(count, 3, 3, device=dev, dtype=torch.float32) if want_hess else None
+        with torch.cuda.device(dev):
+            _lib.check(self.L.dudf_query_grid(self.h, N, first, count, flags, float(alpha), _lib.ptr(df), _lib.ptr(vecs), _lib.ptr(H),
+                                              PRECISIONS[precision], _lib.current_stream()), "dudf_query_grid")
+        return df, vecs, H
+
+    def eig_normals(self, H, ref_dir=None, ref_mode=0, want_dirs=False, want_lam=False):
+        P = H.shape[0]
+        n = torch.empty(P, 3, device=H.device, dtype=torch.float32)
+        dirs = torch.empty(P, 3, 2, device=H.device, dtype=torch.float32) if want_dirs else None
+        lam = torch.empty(P, 3, device=H.device, dtype=torch.float32) if want_lam else None
+        with torch.cuda.device(H.device):
+            _lib.check(self.L.dudf_eig_normals(H.data_ptr(), _lib.ptr(ref_dir), ref_mode, P, n.data_ptr(), _lib.ptr(dirs), _lib.ptr(lam),
+                                               _lib.current_stream()), "dudf_eig_normals")
+        return n, dirs, lam
+
+    def curvature(self, H, T):
+        P = H.shape[0]
+        n = torch.empty(P, 3, device=H.device, dtype=torch.float32)
+        mean = torch.empty(P, device=H.device, dtype=torch.float32)
+        gauss = torch.empty(P, device=H.device, dtype=torch.float32)
+        J = torch.empty(P, 3, 3, device=H.device, dtype=torch.float32)
+        with torch.cuda.device(H.device):
+            _lib.check(self.L.dudf_curvature(H.data_ptr(), T.data_ptr(), P, n.data_ptr(), mean.data_ptr(), gauss.data_ptr(),
+                                             J.data_ptr(), _lib.current_stream()), "dudf_curvature")
+        return n, mean, gauss, J
+
+    def field_vectors(self, g, H):
+        vecs = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            _lib.check(self.L.dudf_field_vectors(g.data_ptr(), H.data_ptr(), g.shape[0], vecs.data_ptr(), _lib.current_stream()),
+                       "dudf_field_vectors")
+        return vecs
+
+    def evaluate_host(self, x_host, order, f_host, g_host, H_host, max_batch, precision="fp32"):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dudf_evaluate_host(self.h, x_host.ctypes.data, x_host.shape[0], order, _lib.ptr(f_host), _lib.ptr(g_host),
+                                                 _lib.ptr(H_host), max_batch, PRECISIONS[precision]), "dudf_evaluate_host")
+
+    # ---- training primitives ----
+    def stash_columns(self, order, P):
+        return int(self.L.dudf_stash_columns(order, P))
+
+    def jet_forward(self, x, order, packed, Z, A, ld, col0, precision="fp32"):
+        with torch.cuda.device(x.device):
+            _lib.check(self.L.dudf_jet_forward(self.h, x.data_ptr(), x.shape[0], order, packed.data_ptr(), Z.data_ptr(), A.data_ptr(), ld,
+                                               col0, PRECISIONS[precision], _lib.current_stream()), "dudf_jet_forward")
+
+    def jet_backward(self, x, order, seeds, Z, Zb, ld, col0, gW, gb, precision="fp32"):
+        with torch.cuda.device(x.device):
+            _lib.check(self.L.dudf_jet_backward(self.h, x.data_ptr(), x.shape[0], order, seeds.data_ptr(), Z.data_ptr(), Zb.data_ptr(), ld,
+                                                col0, _ptr_array(gW), _ptr_array(gb), PRECISIONS[precision], _lib.current_stream()),
+                       "dudf_jet_backward")
+
+    def jet_wgrad(self, Zb, A, ld, ncols, gW, precision="fp32"):
+        with torch.cuda.device(Zb.device):
+            _lib.check(self.L.dudf_jet_wgrad(self.h, Zb.data_ptr(), A.data_ptr(), ld, ncols, _ptr_array(gW), PRECISIONS[precision],
+                                             _lib.current_stream()), "dudf_jet_wgrad")
+
+    def loss(self, mode, packed, nch, normals, dist, P, P_global, w, alpha, upstream=None, seeds=None, terms=None, s2_stats=None):
+        w4 = (ctypes.c_float * 4)(*([float(v) for v in w] + [0.0] * (4 - len(w))))
+        with torch.cuda.device(packed.device):
+            _lib.check(self.L.dudf_loss(LOSS_MODES[mode], packed.data_ptr(), nch, _lib.ptr(normals), dist.data_ptr(), P, P_global, w4,
+                                        float(alpha), _lib.ptr(upstream), _lib.ptr(seeds), _lib.ptr(terms), _lib.ptr(s2_stats),
+                                        _lib.current_stream()), "dudf_loss")
+
+    def loss_s2_stats(self, packed, dist, P, stats):
+        with torch.cuda.device(packed.device):
+            _lib.check(self.L.dudf_loss_s2_stats(packed.data_ptr(), dist.data_ptr(), P, stats.data_ptr(), _lib.current_stream()),
+                       "dudf_loss_s2_stats")
+
+    def loss_s2_finish(self, stats, w0, w1, terms):
+        with torch.cuda.device(stats.device):
+            _lib.check(self.L.dudf_loss_s2_finish(stats.data_ptr(), float(w0), float(w1), terms.data_ptr(), _lib.current_stream()),
+                       "dudf_loss_s2_finish")
+
+
+def adam_step(p, g, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place Adam on flat fp32 CUDA tensors (train.py:334-337 semantics)."""
+    L = _lib.lib()
+    with torch.cuda.device(p.device):
+        _lib.check(L.dudf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
+                                    float(beta2), float(eps), int(t), _lib.current_stream()), "dudf_adam_step")

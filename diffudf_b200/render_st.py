@@ -1,0 +1,137 @@
+"""Sphere tracing field queries: drop-in for the query side of /root/reference/src/render_st.py
+(evaluate :13-36, compute_curvature :42-55, compute_normals_and_cd :57-62, compute_grad :64-65,
+propagate_rays :136-161, grad_descent :163-172).  The march keeps rays on the device (one active-count
+read-back per iteration instead of a full D2H of the values); shading / colour maps are host glue and
+out of scope."""
+import numpy as np
+import torch
+
+from .diff_operators import gradient, hessian, jacobian
+from .inverses import inverse_torch
+
+
+def grid_points(N, idx, device):
+    """Coordinates of flat grid indices as render_mc.py:36-49 computes them (fp32)."""
+    idx = idx.to(device=device, dtype=torch.int64)
+    vs = torch.tensor(2.0 / (N - 1), dtype=torch.float32, device=device)
+    i2 = (idx % N).to(torch.float32)
+    i1 = ((idx // N) % N).to(torch.float32)
+    i0 = ((idx // N // N) % N).to(torch.float32)
+    return torch.stack([i0 * vs - 1, i1 * vs - 1, i2 * vs - 1], dim=1).contiguous()
+
+
+def evaluate(model, samples, max_batch=64 ** 2, device=torch.device(0)):
+    """Returns ([model_in], [model_out]) like the reference's chunk lists (one chunk: the kernels tile internally)."""
+    if not torch.is_tensor(samples):
+        samples = torch.from_numpy(np.asarray(samples)).float()
+    x, y = model(samples.to(device).float().unsqueeze(0)).values()
+    return [x], [y]
+
+
+def batched_op(inputs, outputs, op, *args, **kwargs):
+    return [op(x, y, *args, **kwargs) for x, y in zip(inputs, outputs)]
+
+
+def compute_grad(inputs, outputs):
+    return gradient(outputs, inputs)
+
+
+def compute_normals_and_cd(inputs, outputs):
+    """Eigen-normal (1,P,3) and principal directions (1,P,3,2) (on CPU like the reference)."""
+    H = hessian(outputs, inputs)
+    eng = inputs._dudf.model._engine
+    n, dirs, _ = eng.eig_normals(H.reshape(-1, 3, 3).contiguous(), want_dirs=True)
+    return n.unsqueeze(0), dirs.unsqueeze(0).detach().cpu()
+
+
+def compute_curvature(inputs, normals, curvature="mean", device=torch.device(0)):
+    """Mean: tr(dn/dx)/2, Gaussian: -det [[dn/dx, n],[n^T, 0]] — shapes (1,P,1) on CPU as in the reference."""
+    shape_op, status = jacobian(normals, inputs)
+    if curvature == "mean":
+        return (torch.sum(torch.diagonal(shape_op[0], dim1=1, dim2=2), dim=-1) / 2).detach().cpu()[None, ..., None]
+    if curvature == "gaussian":
+        n = normals.reshape(-1, 3)
+        ext = torch.zeros((shape_op.shape[1], 4, 4), device=shape_op.device)
+        ext[:, :3, :3] = shape_op[0]
+        ext[:, :3, 3] = n
+        ext[:, 3, :3] = n
+        return (-1 * torch.linalg.det(ext)[None, ..., None]).detach().cpu()
+    return None
+
+
+def _march(model, rays_d, t0_d, idx, gt_mode, alpha, thr, max_it):
+    eng = model._engine_synced()
+    hits = torch.zeros(t0_d.shape[0], dtype=torch.bool, device=t0_d.device)
+    it = 0
+    nq = 0
+    while idx.numel() > 0 and it < max_it:
+        x = t0_d[idx].to(torch.float32).contiguous()
+        f, _, _, _ = eng.query(x, 0, model.precision)
+        nq += x.shape[0]
+        steps = inverse_torch(gt_mode, f.abs(), alpha)
+        pos = t0_d[idx] + rays_d[idx] * steps.to(torch.float64)[:, None]
+        t0_d[idx] = pos
+        below = (f < thr) if gt_mode == "siren" else (steps.abs() < thr)
+        inside = ((pos > -1).all(dim=1)) & ((pos < 1).all(dim=1))
+        hits[idx] |= below & inside
+        idx = idx[(~below) & inside]
+        it += 1
+    return hits, idx, nq
+
+
+def propagate_rays(model, rays, t0, mask_rays, network_config, rendering_config, device):
+    """Same contract as the reference: t0 (R,3) float64 and mask_rays (R,) bool numpy arrays are updated
+    in place, the hit mask is returned; raises ValueError when nothing is hit."""
+    dev = torch.device(device)
+    rays_d = torch.from_numpy(np.ascontiguousarray(rays, dtype=np.float64)).to(dev)
+    t0_d = torch.from_numpy(np.ascontiguousarray(t0, dtype=np.float64)).to(dev)
+    idx = torch.nonzero(torch.from_numpy(np.asarray(mask_rays, dtype=bool)).to(dev)).reshape(-1)
+    hits, idx, _ = _march(model, rays_d, t0_d, idx, network_config["gt_mode"], network_config["alpha"],
+                          rendering_config["surface_threshold"], rendering_config["max_iterations"])
+    t0[...] = t0_d.cpu().numpy()
+    still = np.zeros(mask_rays.shape, dtype=bool)
+    still[idx.cpu().numpy()] = True
+    mask_rays[...] = still
+    hits_np = hits.cpu().numpy()
+    if hits_np.sum() == 0:
+        raise ValueError(f"Ray tracing did not converge in {rendering_config['max_iterations']} iterations to any point at "
+                         f"distance {rendering_config['surface_threshold']} or lower from surface.")
+    return hits_np
+
+
+def grad_descent(model, t0, mask_rays, network_config, rendering_config, device):
+    dev = torch.device(device)
+    eng = model._engine_synced()
+    sel = np.asarray(mask_rays, dtype=bool)
+    pos = torch.from_numpy(np.ascontiguousarray(t0[sel], dtype=np.float64)).to(dev)
+    for _ in range(rendering_config["gd_steps"]):
+        f, g, _, _ = eng.query(pos.to(torch.float32).contiguous(), 1, model.precision)
+        gn = g / torch.linalg.norm(g, dim=1, keepdim=True)
+        steps = inverse_torch(network_config["gt_mode"], f.abs(), network_config["alpha"])
+        pos = pos - (gn * steps[:, None]).to(torch.float64)
+    t0[sel] = pos.cpu().numpy()
+
+
+def hit_attributes(model, points, ray_dirs=None, curvature="mean"):
+    """Device-side replacement of the per-hit block of create_projectional_image (render_st.py:92-108):
+    eigen-normals, principal directions and (optionally) curvature at `points` (P,3), sign-fixed
+    against the ray directions.  Returns dict of CUDA tensors."""
+    eng = model._engine_synced()
+    x = points.to(torch.float32).contiguous()
+    out = {}
+    if curvature in ("mean", "gaussian"):
+        _, _, H, T = eng.query(x, 3, "fp32")
+        n, mean, gauss, _ = eng.curvature(H, T)
+        out["mean"], out["gauss"] = mean, gauss
+        _, dirs, _ = eng.eig_normals(H, want_dirs=True)
+    else:
+        _, _, H, _ = eng.query(x, 2, model.precision)
+        n, dirs, _ = eng.eig_normals(H, want_dirs=True)
+    out["dirs"] = dirs
+    if ray_dirs is not None:
+        align = -torch.sign((n * ray_dirs.to(n.dtype)).sum(-1, keepdim=True))
+        n = n * align
+        if "mean" in out:
+            out["mean"] = out["mean"] * align[:, 0]
+    out["normals"] = n
+    return out

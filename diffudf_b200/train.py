@@ -1,0 +1,125 @@
+"""Training loop: drop-in for the step / schedule semantics of /root/reference/train.py
+(train_model_tanh :146-283, train_model_siren :23-143, Adam as built at :334-337,365-368).
+
+`FusedTrainer.step` is the fast path: no autograd graph, no host synchronisation — jet forward,
+loss epilogue, reverse sweep, weight gradients, (all-reduce), Adam, all enqueued on the current
+stream.  The reference's per-step `.item()` calls become one read-back per epoch.
+File IO (TensorBoard, checkpoints every epoch, plots, meshing) is host glue and is left to the caller.
+"""
+import copy
+import time
+
+import numpy as np
+import torch
+
+from .engine import adam_step
+from .loss_functions import S1_KEYS, S2_KEYS, SIREN_KEYS, TrainCore
+
+
+def lr_for_epoch(epoch, epochs, s1_epochs, warmup_epochs, warmup_lr, lr_s1, lr_s2):
+    """Learning rate in effect during `epoch` (train.py:167-191)."""
+    if epoch >= s1_epochs:
+        return 0.5 * (np.cos(epoch / (epochs - s1_epochs) * np.pi) + 1) * lr_s2
+    if epoch >= warmup_epochs:
+        return lr_s1
+    return warmup_lr
+
+
+class FusedTrainer:
+    """Owns flat fp32 parameter / gradient / Adam-moment buffers; the module's parameters become views
+    of the flat buffer so that state_dict()/load_state_dict() keep working."""
+
+    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None):
+        self.model = model
+        self.betas, self.eps, self.dp = betas, eps, dp
+        ws, bs = model._weights_biases()
+        dev = ws[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedTrainer needs the model on a CUDA (sm_100) device")
+        tensors = []
+        for w, b in zip(ws, bs):
+            tensors += [w, b]
+        n = sum(t.numel() for t in tensors)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        self.gW, self.gB = [], []
+        for i, t in enumerate(tensors):
+            k = t.numel()
+            self.flat[off:off + k].copy_(t.detach().reshape(-1))
+            t.data = self.flat[off:off + k].view_as(t)
+            gv = self.grad[off:off + k].view_as(t)
+            (self.gW if i % 2 == 0 else self.gB).append(gv)
+            off += k
+        self.core = TrainCore(model)
+        self.t = 0
+
+    def step(self, mode, x, normals, d, n_on, weights, alpha, lr):
+        """One optimisation step on a device-resident batch (x (P,3), normals (P,3), d (P,), fp32).
+        Returns the (4,) float64 device tensor of this rank's loss-term shares (no sync)."""
+        dp = self.dp
+        P_global = dp.global_rows(x.shape[0]) if dp is not None else None
+        terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None)
+        self.grad.zero_()
+        self.core.backward(None, self.gW, self.gB)
+        if dp is not None:
+            dp.reduce_grads(self.grad)
+        self.t += 1
+        adam_step(self.flat, self.grad, self.m, self.v, lr, self.t, self.betas[0], self.betas[1], self.eps)
+        # parameters changed in place behind torch's back: make the engine re-pack on next use
+        if self.model._engine is not None:
+            self.model._engine._sig = None
+        return terms
+
+
+def _epoch_loop(dataset, model, device, config, stage_fn):
+    epochs = config["epochs"]
+    trainer = FusedTrainer(model.to(device), dp=config.get("dp"))
+    losses, best_loss, best_weights = {}, np.inf, None
+    torch.cuda.synchronize(device)
+    start = time.time()
+    for epoch in range(epochs):
+        mode, keys, weights, lr = stage_fn(epoch)
+        running = torch.zeros(4, device=device, dtype=torch.float64)
+        for input_data, normals, sdf in iter(dataset):
+            x = input_data.to(device).reshape(-1, 3).float().contiguous()
+            n = normals.to(device).reshape(-1, 3).float().contiguous()
+            d = sdf.to(device).reshape(-1).float().contiguous()
+            n_on = getattr(dataset, "samplesOnSurface", None)
+            if n_on is None and mode == "s1" and weights[2] != 0:
+                from .loss_functions import on_surface_prefix
+                n_on = on_surface_prefix(d)
+                if n_on is None:
+                    raise RuntimeError("batches must be ordered [on-surface | off-surface] for the fused step")
+            running += trainer.step(mode, x, n, d, n_on or 0, weights, config.get("alpha", 0.0), lr)
+        vals = running.cpu().numpy()                        # one read-back per epoch
+        epoch_loss = 0.0
+        for i, k in enumerate(keys):
+            losses.setdefault(k, [0.0] * epochs)[epoch] = float(vals[i])
+            epoch_loss += float(vals[i])
+        epoch_loss /= getattr(dataset, "batchesPerEpoch", 1)
+        if epoch_loss < best_loss:
+            best_loss = epoch_loss
+            best_weights = copy.deepcopy(model.state_dict())
+    torch.cuda.synchronize(device)
+    return losses, best_weights, time.time() - start
+
+
+def train_model_tanh(dataset, model, device, config):
+    """Two-stage hyperbolic training (train.py:146-283): loss_s1 with warm-up lr, then loss_s2 with cosine lr."""
+    def stage(epoch):
+        lr = lr_for_epoch(epoch, config["epochs"], config["s1_epochs"], config["warmup_epochs"], config["warmup_lr"],
+                          config["lr_s1"], config["lr_s2"])
+        if epoch >= config["s1_epochs"]:
+            return "s2", S2_KEYS, list(config["loss_s2_weights"]), lr
+        return "s1", S1_KEYS, list(config["loss_s1_weights"]), lr
+    return _epoch_loop(dataset, model, device, config, stage)
+
+
+def train_model_siren(dataset, model, device, config):
+    """SDF baseline (train.py:23-143): loss_siren, constant lr."""
+    def stage(epoch):
+        return "siren", SIREN_KEYS, list(config["loss_weights"]), config["lr"]
+    return _epoch_loop(dataset, model, device, config, stage)

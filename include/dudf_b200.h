@@ -1,0 +1,127 @@
+/* dudf_b200.h — C ABI of the B200-native DUDF hot path (libdudf_b200.so).
+ *
+ * The reference (LIA-DiTella/DiffUDF) has no FFI: its boundary is the Python call surface of
+ * src/model.py, src/diff_operators.py, src/loss_functions.py, src/evaluate.py and the field queries
+ * of src/render_mc.py / render_st.py / render_pc.py.  Each entry point below names the reference
+ * interface it replaces; diffudf_b200/*.py binds them with ctypes and mirrors the reference
+ * signatures (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions: every pointer is a DEVICE pointer unless its name ends in _host; tensors are dense
+ * fp32 row-major; `stream` is a cudaStream_t passed as void* (NULL = default stream); the caller
+ * owns all buffers; functions return 0 on success, non-zero on failure with the message available
+ * from dudf_last_error().  There is no CPU fallback: calls fail when no sm_100 device is present.
+ */
+#ifndef DUDF_B200_H
+#define DUDF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dudf_ctx dudf_ctx;
+
+/* arithmetic of the hidden-layer contractions */
+#define DUDF_PRECISION_FP32 0  /* fp32 FFMA on CUDA cores; tolerance 1e-5 vs the fp64 oracle          */
+#define DUDF_PRECISION_TC16 1  /* tcgen05 MMA, fp16 operands, fp32 TMEM accumulation; tolerance 1e-3  */
+
+/* post-processing flags of the field queries */
+#define DUDF_Q_ABS_INV_TANH 1  /* f <- inv_tanh(|f|, alpha)            src/inverses.py:18-19, render_mc.py:71 */
+#define DUDF_Q_NEG_NORMALIZE 2 /* g <- -g / max(|g|, 1e-12)            src/render_mc.py:74-75                 */
+
+/* loss selectors */
+#define DUDF_LOSS_S1 0    /* src/loss_functions.py:123-155 */
+#define DUDF_LOSS_S2 1    /* src/loss_functions.py:106-121 */
+#define DUDF_LOSS_SIREN 2 /* src/loss_functions.py:82-104  */
+
+int dudf_version(void);
+const char* dudf_last_error(void);
+
+/* Network container: replaces SIREN.__init__ / load_state_dict / .to(device) (src/model.py:85-113).
+ * n_hidden sine layers of width 256 (anything else is rejected), w0 = first-layer omega, ww = others. */
+int dudf_create(int n_hidden, float w0, float ww, dudf_ctx** out);
+int dudf_destroy(dudf_ctx* ctx);
+/* W_host[i] / b_host[i] (HOST arrays of n_hidden+1 DEVICE pointers) use the nn.Linear layout of the
+ * state_dict keys net.{i}.0.weight / net.{i}.0.bias.  Copies and re-packs the operand images. */
+int dudf_set_weights(dudf_ctx* ctx, const float* const* W_host, const float* const* b_host, void* stream);
+
+/* Field query at arbitrary points: SIREN.forward + diff_operators.gradient / hessian
+ * (src/model.py:116-135, src/diff_operators.py:187-212) and the third derivatives that
+ * render_st.compute_curvature obtains through jacobian() (src/render_st.py:42-55).
+ * order 0: f | 1: f, grad | 2: + Hessian | 3: + third derivatives (10 symmetric components, fp32 path only).
+ * Any output pointer may be NULL.  x: [P][3]; f: [P]; g: [P][3]; H: [P][3][3]; T: [P][10]. */
+int dudf_query_points(dudf_ctx* ctx, const float* x, int64_t P, int order, int flags, float alpha, float* f,
+                      float* g, float* H, float* T, int precision, void* stream);
+
+/* Dense grid query: the coordinate generation and evaluate() call of extract_fields
+ * (src/render_mc.py:36-49,69-75).  Flat index i -> (i0,i1,i2), i2 fastest, coord = idx*2/(N-1) - 1.
+ * Evaluates indices [first, first+count).  df: [count] = inv_tanh(|f|); vecs: [count][3] = -normalize(grad f)
+ * (flags select the post-processing; with flags = 0 raw f and grad are written). */
+int dudf_query_grid(dudf_ctx* ctx, int N, int64_t first, int64_t count, int flags, float alpha, float* df,
+                    float* vecs, float* H, int precision, void* stream);
+
+/* Top eigenvector of the Hessian ("eigen-normal") and the two principal directions:
+ * torch.linalg.eigh call sites src/loss_functions.py:142-143, src/render_st.py:59-62, src/render_mc.py:77-84,
+ * src/render_pc.py:65.  ref_mode 0: LAPACK-free canonical sign (largest |component| positive);
+ * 1: flip so that dot(n, ref_dir) >= 0 (render_mc.py:80-84); 2: flip so that dot(n, ref_dir) <= 0
+ * (render_st.py:104-105).  n: [P][3]; dirs: [P][3][2] (may be NULL); lam: [P][3] ascending (may be NULL). */
+int dudf_eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs,
+                     float* lam, void* stream);
+
+/* Mean and Gaussian curvature of the level set from H and the third derivatives T
+ * (src/render_st.py:42-55: jacobian of the eigen-normal, src/diff_operators.py:214-227).  n: [P][3] canonical
+ * sign; mean, gauss: [P]; J: [P][3][3] = d n_i / d x_k.  Any output may be NULL. */
+int dudf_curvature(const float* H, const float* T, int64_t P, float* n, float* mean, float* gauss, float* J,
+                   void* stream);
+
+/* vecs <- where(|g| == 0, eigen-normal sign-aligned, g) : the fallback branch of extract_fields
+ * (src/render_mc.py:77-93); g is the already normalised, negated gradient. */
+int dudf_field_vectors(const float* g, const float* H, int64_t P, float* vecs, void* stream);
+
+/* evaluate() of src/evaluate.py:5-37 with HOST buffers: chunks of max_batch points, fp32 compute, results
+ * widened to float64 on the device and copied into the caller's arrays (any of them may be NULL). */
+int dudf_evaluate_host(dudf_ctx* ctx, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
+                       double* H_host, int64_t max_batch, int precision);
+
+/* Training primitives.  loss_s1 / loss_s2 / loss_siren (src/loss_functions.py:82-155) followed by
+ * train_loss.backward() (train.py:221) decompose into
+ *   1. dudf_jet_forward : model(x) + gradient/hessian as forward jets, stashing what the reverse sweep needs;
+ *   2. dudf_loss        : the loss terms (values) and, given dL/d(term), the per-row adjoint seeds;
+ *   3. dudf_jet_backward: reverse sweep through the jet network (bias / first / last layer gradients);
+ *   4. dudf_jet_wgrad   : weight gradients of the hidden 256x256 layers (contraction over all columns).
+ * `packed` / `seeds` are [P][NCH] with NCH = 1, 4, 10 for order 0, 1, 2: channels f, d_x, d_y, d_z, d_xx, d_xy,
+ * d_xz, d_yy, d_yz, d_zz (a seed of an off-diagonal channel is dL/dH_ij + dL/dH_ji).  The stashes Z, A, Zb are
+ * caller-owned fp32 arrays [n_hidden][256][ld]; dudf_stash_columns gives the padded number of columns a call
+ * uses starting at col0 (ld and col0 multiples of 4).  Gradients ACCUMULATE into gW / gb (HOST arrays of
+ * n_hidden+1 DEVICE pointers, nn.Linear layouts). */
+int64_t dudf_stash_columns(int order, int64_t P);
+int dudf_jet_forward(dudf_ctx* ctx, const float* x, int64_t P, int order, float* packed, float* Z, float* A, int64_t ld,
+                     int64_t col0, int precision, void* stream);
+int dudf_jet_backward(dudf_ctx* ctx, const float* x, int64_t P, int order, const float* seeds, const float* Z, float* Zb,
+                      int64_t ld, int64_t col0, float* const* gW_host, float* const* gb_host, int precision, void* stream);
+int dudf_jet_wgrad(dudf_ctx* ctx, const float* Zb, const float* A, int64_t ld, int64_t ncols, float* const* gW_host,
+                   int precision, void* stream);
+/* Loss epilogue over P rows.  w_host: 4 host floats (loss weights); P_global: divisor of the means (sum of rows over
+ * data-parallel ranks).  terms (4 device doubles, may be NULL) is ACCUMULATED with this call's share of each term in
+ * the order of the reference dicts: S1 {sdf_on_surf, sdf_off_surf, hessian_constraint, grad_constraint}, SIREN
+ * {sdf_on_surf, sdf_off_surf, normal_constraint, grad_constraint}.  seeds (may be NULL) receives
+ * d(sum_k upstream[k] term_k)/d(packed); upstream: 4 device floats or NULL (ones).  For S2 the seeds need the
+ * (all-reduced) statistics n, sum, sum of squares of the on-surface predictions: dudf_loss_s2_stats accumulates them
+ * into 3 device doubles, dudf_loss_s2_finish turns them into the two S2 terms. */
+int dudf_loss(int mode, const float* packed, int nch, const float* normals, const float* dist, int64_t P, int64_t P_global,
+              const float* w_host, float alpha, const float* upstream, float* seeds, double* terms, double* s2_stats,
+              void* stream);
+int dudf_loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, void* stream);
+int dudf_loss_s2_finish(const double* stats, float w0, float w1, double* terms, void* stream);
+/* torch.optim.Adam.step as configured in train.py:334-337 (betas, eps given explicitly, no weight decay);
+ * t is the 1-based step count.  Flat fp32 arrays of n elements. */
+int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int64_t t, void* stream);
+
+/* bring-up / regression tests of the tcgen05 building blocks (tests/test_gpu_umma.py) */
+int dudf_selftest_umma(int variant, float* max_err_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
