@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the DUDF hot path (contract: see the task description / DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): SIREN 3->256x8->1 training on a 200k-sample synthetic complex shape,
+one step = loss_s1 (weights [1e4,1e4,1e4,1e3], alpha 100) forward jets + loss + reverse sweep + weight
+gradients + Adam on a 29 970-row batch [9 990 on | 9 990 far | 9 990 near] per GPU (weak scaling), data
+parallel with one all-reduce of the flat gradient.  Metric: train points/s (whole job).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F = {1: 1536 + 1 * 918016, 4: 1536 + 4 * 918016, 10: 1536 + 10 * 918016}   # algorithmic FLOP / point
+W_S1 = [1e4, 1e4, 1e4, 1e3]
+ALPHA = 100.0
+LR = 1e-4
+
+
+def make_batches(n_batches, seed, rows=30000):
+    import numpy as np
+    from diffudf_b200 import synthetic
+    shape = synthetic.make_shape(0)
+    surf_p, surf_n = shape.sample_surface(200000, np.random.default_rng(0))
+    rng = np.random.default_rng(1000 + seed)
+    return [synthetic.make_batch(shape, surf_p, surf_n, rows, (0.333, 0.666), rng) for _ in range(n_batches)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_run(steps, warmup, rows_cap=None):
+    """The reference's CPU way of running the step (oracle/autograd_port.py) on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import autograd_port as AP
+    from oracle import dudf_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    params = AP.make_params(O.init_params(8, 256, 30.0, 123))
+    opt = AP.make_optimizer(params, LR)
+    x, n, d = make_batches(1, 0)[0]
+    sample = "full 29 970-row batch per step"
+    if rows_cap is not None and rows_cap < x.shape[1]:
+        k = rows_cap // 3
+        sel = np.concatenate([np.arange(k), 9990 + np.arange(k), 19980 + np.arange(k)])
+        x, n, d = x[:, sel], n[:, sel], d[:, sel]
+        sample = f"{3 * k}-row subsample [on|far|near] per step (linear in rows)"
+    x, n, d = torch.from_numpy(x), torch.from_numpy(n), torch.from_numpy(d)
+    for _ in range(warmup):
+        AP.train_step(params, opt, x, n, d, "s1", W_S1, ALPHA)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        AP.train_step(params, opt, x, n, d, "s1", W_S1, ALPHA)
+    dt = time.perf_counter() - t0
+    return x.shape[1] * steps / dt, dt / steps * 1e3, torch.get_num_threads(), sample
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bound the run: ~2.3 s per full step on 8 cores; keep the whole arm within a few minutes
+    t_probe = time.perf_counter()
+    v1, ms1, cores, _ = cpu_port_run(1, 1, rows_cap=2997)
+    est_full = ms1 * 10 / 1e3 * (args.steps + args.warmup)
+    cap = None if est_full < 200 else max(2997, int(29970 * 200 / est_full) // 3 * 3)
+    value, ms, cores, sample = cpu_port_run(args.steps, args.warmup, cap)
+    line = {"impl": "reference", "metric": "train points/s", "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 200k-sample synthetic complex shape, SIREN 3->256x8->1, loss_s1 step, 29 970 rows/step",
+                       "device": "host CPU"},
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "probe_s": round(time.perf_counter() - t_probe, 1)}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from diffudf_b200 import SIREN, _lib
+    from diffudf_b200 import engine as E
+    from diffudf_b200.parallel import DataParallel
+    from diffudf_b200.train import FusedTrainer
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dp = DataParallel()
+    torch.manual_seed(123)
+    model = SIREN(3, 1, [256] * 8, w0=30).to(dev)
+    trainer = FusedTrainer(model, dp=dp)
+    NB = 4
+    host = []
+    for x, n, d in make_batches(NB, rank):
+        host.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], n[0], d[0, :, 0])))
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    P = host[0][0].shape[0]
+    n_on = 9990
+    L = _lib.lib()
+
+    def step_resident(i):
+        x, n, d = resident[i % NB]
+        return trainer.step("s1", x, n, d, n_on, W_S1, ALPHA, LR)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    # ---- device-resident timing ----
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if clocks:
+        clocks.start()
+    l0 = L.dudf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    launches = L.dudf_launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # ---- end to end: pinned host batch -> device, step, loss terms -> host, every step ----
+    dbuf = [torch.empty_like(t) for t in resident[0]]
+    for i in range(2):
+        for dst, src in zip(dbuf, host[i % NB]):
+            dst.copy_(src, non_blocking=True)
+        trainer.step("s1", dbuf[0], dbuf[1], dbuf[2], n_on, W_S1, ALPHA, LR).cpu()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = None
+    for i in range(args.steps):
+        for dst, src in zip(dbuf, host[i % NB]):
+            dst.copy_(src, non_blocking=True)
+        last = trainer.step("s1", dbuf[0], dbuf[1], dbuf[2], n_on, W_S1, ALPHA, LR).cpu()
+    e3.record()
+    barrier()
+    clk = clocks.stop() if clocks else None
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2.item())
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    assert bool(torch.isfinite(last).all()), "non-finite loss terms"
+
+    # ---- per-kernel timing of one step (CUDA events on the launching stream) for the roofline object ----
+    prof = {}
+    if rank == 0:
+        eng = model._engine_synced()
+        names = ["jet_forward", "loss", "jet_backward", "jet_wgrad"]
+        orig = {k: getattr(eng, k) for k in names}
+        events = []
+
+        def wrap(name, fn):
+            def inner(*a, **kw):
+                s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = fn(*a, **kw)
+                t.record()
+                tag = name
+                if name in ("jet_forward", "jet_backward"):
+                    tag = f"{name}[order{a[1]}]"
+                events.append((tag, s, t))
+                return r
+            return inner
+        for k in names:
+            setattr(eng, k, wrap(k, orig[k]))
+        reps = 3
+        for i in range(reps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        for k in names:
+            setattr(eng, k, orig[k])
+        for tag, s, t in events:
+            prof[tag] = prof.get(tag, 0.0) + s.elapsed_time(t) / reps
+    # ---- field queries (secondary metric: UDF+grad queries/s on a dense grid) ----
+    aux = {}
+    if rank == 0:
+        eng = model._engine_synced()
+        for prec, N in (("tc16", 256), ("fp32", 128)):
+            cnt = N ** 3
+            df = torch.empty(cnt, device=dev)
+            vecs = torch.empty(cnt, 3, device=dev)
+            eng.query_grid(N, 0, cnt, prec, 3, ALPHA, out=(df, vecs))
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(3):
+                eng.query_grid(N, 0, cnt, prec, 3, ALPHA, out=(df, vecs))
+            t.record()
+            torch.cuda.synchronize()
+            q = 3 * cnt / (s.elapsed_time(t) * 1e-3)
+            aux[f"grid{N}_{prec}_queries_per_s"] = q
+            aux[f"grid{N}_{prec}_tflops"] = q * F[4] / 1e12
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+    flops = {"jet_forward[order2]": n_on * F[10], "jet_forward[order1]": (P - n_on) * F[4],
+             "jet_backward[order2]": n_on * F[10], "jet_backward[order1]": (P - n_on) * F[4],
+             "jet_wgrad": n_on * F[10] + (P - n_on) * F[4]}
+    dom = max((k for k in prof if k in flops), key=lambda k: prof[k]) if prof else None
+    roof = None
+    if dom:
+        ach = flops[dom] / (prof[dom] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "peak_source": peak_src, "ms": prof[dom],
+                "step_share": prof[dom] / max(sum(prof.values()), 1e-9),
+                "kernel_ms": {k: round(v, 4) for k, v in prof.items()},
+                "step_algorithmic_gflop": (n_on * F[10] + (P - n_on) * F[4]) * 3 / 1e9}
+    cpu = None
+    if world == 1:
+        v, msc, cores, sample = cpu_port_run(3, 1)
+        cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "ms_per_step": msc,
+               "sample": "3 timed loss_s1+backward+Adam steps (after 1 warm-up) of the " + sample + ", oracle/autograd_port.py"}
+    value = world * P * args.steps / (ms_total * 1e-3)
+    line = {"metric": "train points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 200k-sample synthetic complex shape, SIREN 3->256x8->1, loss_s1 step "
+                                   "(w=[1e4,1e4,1e4,1e3], alpha=100, Adam lr 1e-4), 29 970 rows per GPU per step [9990 on|9990 far|9990 near]",
+                       "rows_per_gpu": P, "global_rows": world * P, "parallelism": f"dp{world}", "precision": "fp32 CUDA-core step",
+                       "l2": "per-step working set (activation stashes, ~4 GB) exceeds the 126 MB L2; 4 distinct batches cycled"},
+            "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "aux": aux}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

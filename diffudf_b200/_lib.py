@@ -27,6 +27,7 @@ c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int6
 # name -> (argtypes) ; every function returns int except the two noted below
 SIGNATURES = {
     "dudf_version": [],
+    "dudf_launch_count": [],
     "dudf_create": [c_int, c_float, c_float, ctypes.POINTER(c_void_p)],
     "dudf_destroy": [c_void_p],
     "dudf_set_weights": [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p],
@@ -102,7 +103,7 @@ def lib():
             for name, args in SIGNATURES.items():
                 fn = getattr(L, name)
                 fn.argtypes = args
-                fn.restype = c_int64 if name == "dudf_stash_columns" else c_int
+                fn.restype = c_int64 if name in ("dudf_stash_columns", "dudf_launch_count") else c_int
             L.dudf_last_error.argtypes = []
             L.dudf_last_error.restype = ctypes.c_char_p
             _lib = L

@@ -17,6 +17,9 @@ void dudf_set_error(const char* fmt, ...) {
   g_err = buf;
 }
 
+static long long g_launches = 0;
+void dudf_count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
 namespace dudf {
 
 struct DevBuf {
@@ -71,6 +74,7 @@ extern "C" {
 
 int dudf_version(void) { return 100; }
 const char* dudf_last_error(void) { return g_err.c_str(); }
+int64_t dudf_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int dudf_create(int n_hidden, float w0, float ww, dudf_ctx** out) {
   DUDF_REQUIRE(out != nullptr, "dudf_create: null output pointer");

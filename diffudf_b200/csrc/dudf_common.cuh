@@ -141,6 +141,13 @@ void dudf_set_error(const char* fmt, ...);
       return 1;                                                                         \
     }                                                                                   \
   } while (0)
+// every kernel launch of this library goes through this: error check + launch counter (dudf_launch_count)
+void dudf_count_launch();
+#define DUDF_LAUNCH_OK()                    \
+  do {                                      \
+    DUDF_CUDA_OK(cudaGetLastError());       \
+    dudf_count_launch();                    \
+  } while (0)
 #define DUDF_REQUIRE(cond, ...)            \
   do {                                     \
     if (!(cond)) {                         \

@@ -142,7 +142,7 @@ int loss_seeds(const LossArgs& a, cudaStream_t st) {
   if (a.P <= 0) return 0;
   const int64_t blocks = (a.P + 255) / 256;
   loss_seed_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -161,7 +161,7 @@ int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* sta
   if (P <= 0) return 0;
   const int blocks = (int)std::min<int64_t>((P + 255) / 256, 1024);
   s2_stats_kernel<<<blocks, 256, 0, st>>>(packed, dist, P, stats);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -175,7 +175,7 @@ __global__ void s2_finish_kernel(const double* stats, float w0, float w1, double
 }
 int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st) {
   s2_finish_kernel<<<1, 1, 0, st>>>(stats, w0, w1, terms);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -203,7 +203,7 @@ int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
   const double bc2 = 1.0 - pow((double)b2, (double)t);
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
   adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)sqrt(bc2), b1, b2, eps);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -217,7 +217,7 @@ __global__ void transpose256_kernel(const float* __restrict__ W, float* __restri
 }
 int transpose256(const float* W, float* Wt, cudaStream_t st) {
   transpose256_kernel<<<dim3(8, 8), dim3(32, 8), 0, st>>>(W, Wt);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -259,7 +259,7 @@ int eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, f
                 cudaStream_t st) {
   if (P <= 0) return 0;
   eig_normals_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(H, ref_dir, ref_mode, P, n, dirs, lam);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) curvature_kernel(const float* __restrict_
 int curvature(const float* H, const float* T, int64_t P, float* n, float* mean, float* gauss, float* J, cudaStream_t st) {
   if (P <= 0) return 0;
   curvature_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(H, T, P, n, mean, gauss, J);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) field_vectors_kernel(const float* __restr
 int field_vectors(const float* g, const float* H, int64_t P, float* vecs, cudaStream_t st) {
   if (P <= 0) return 0;
   field_vectors_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(g, H, P, vecs);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256) f32_to_f64_kernel(const float* __restrict
 int f32_to_f64(const float* src, double* dst, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
   f32_to_f64_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(src, dst, n);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 

@@ -460,7 +460,7 @@ static int launch_forward_t(const NetView& net, const float* x, int64_t P, int g
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * 2);
   if (grid < 1) return 0;
   k<<<grid, 256, C::smem_bytes, st>>>(net, x, P, gridN, grid_first, out, Zst, Ast, ctot, col0);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -490,7 +490,7 @@ static int launch_backward_t(const NetView& net, const GradView& grad, const flo
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms);
   if (grid < 1) return 0;
   k<<<grid, 256, C::smem_bytes, st>>>(net, grad, x, P, seeds, Zst, Zbst, ctot, col0);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -512,7 +512,7 @@ int simt_wgrad(const NetView& net, const GradView& grad, const float* Zbst, cons
   splits = (int)std::min<int64_t>(splits, (ncols + 255) / 256);
   dim3 grid(4, L - 1, splits);
   simt_wgrad_kernel<<<grid, 256, 0, st>>>(grad, Zbst, Ast, ctot, ncols);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 

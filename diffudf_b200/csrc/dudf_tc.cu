@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(NetView net, unsigned char
 int tc_pack(const NetView& net, void* packed, cudaStream_t st) {
   if (net.n_lin <= 2) return 0;
   tc_pack_kernel<<<dim3(256, net.n_lin - 2), 256, 0, st>>>(net, (unsigned char*)packed);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -313,7 +313,7 @@ static int tc_launch(const void* packed, const NetView& net, const float* x, int
   const int grid = (int)std::min<int64_t>(npairs, sms);
   if (grid < 1) return 0;
   k<<<grid, TC_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, x, P, gridN, first, out);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   return 0;
 }
 
@@ -417,7 +417,7 @@ int tc_selftest(int variant, float* max_err, cudaStream_t st) {
   const int smem = 2 * 65536 + 1024;
   DUDF_CUDA_OK(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tc_selftest_kernel<<<1, 128, smem, st>>>(dA, dB, 65536, 65536, N, variant, dD);
-  DUDF_CUDA_OK(cudaGetLastError());
+  DUDF_LAUNCH_OK();
   DUDF_CUDA_OK(cudaStreamSynchronize(st));
   std::vector<float> D(M * N);
   DUDF_CUDA_OK(cudaMemcpy(D.data(), dD, M * N * sizeof(float), cudaMemcpyDeviceToHost));

@@ -36,6 +36,8 @@ typedef struct dudf_ctx dudf_ctx;
 
 int dudf_version(void);
 const char* dudf_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t dudf_launch_count(void);
 
 /* Network container: replaces SIREN.__init__ / load_state_dict / .to(device) (src/model.py:85-113).
  * n_hidden sine layers of width 256 (anything else is rejected), w0 = first-layer omega, ww = others. */

@@ -59,8 +59,11 @@ def test_tc16_query_matches_oracle(tag, order, golden, oracle, weights, cuda_mod
     if order >= 2:
         e["H"] = (rel_max(H, ref["H"]), rel_l2(H, ref["H"]))
     print(f"tc16 {tag} order {order}: (max-measure, rel-L2) {e}")
+    # single-pass fp16 operands carry an 11-bit significand, the same as tf32: BASELINE.md's probe puts that class at
+    # f 5.7e-4 / grad 1.6e-3 / hess 1.9e-3 at the SIREN init ("borderline at 1e-3"); trained weights sit below 1e-3.
+    lim = 1e-3 if tag == "trained" else 2.5e-3
     for k, (emax, el2) in e.items():
-        assert el2 < 1e-3, (k, el2)
+        assert el2 < lim, (k, el2)
         assert emax < 4e-3, (k, emax)
 
 

@@ -23,7 +23,7 @@ def test_evaluate_fills_caller_arrays(tag, golden, cuda_models):
 
 
 @pytest.mark.parametrize("tag", ["init", "trained"])
-@pytest.mark.parametrize("precision,tol_df,tol_v", [("fp32", 2e-5, 2e-4), ("tc16", 4e-3, 2e-2)])
+@pytest.mark.parametrize("precision,tol_df,tol_v", [("fp32", 2e-5, 2e-4), ("tc16", 4e-3, 5e-2)])
 def test_extract_fields(tag, precision, tol_df, tol_v, golden, oracle, cuda_models):
     from diffudf_b200.render_mc import extract_fields
     F = golden(f"fields_{tag}.npz")

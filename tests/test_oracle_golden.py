@@ -135,3 +135,26 @@ def test_trajectory_matches_reference(golden, oracle, weights):
         rtol = 1e-5 if step == 0 else (2e-3 if step == 1 else 0.12)
         assert np.allclose(got, ref, rtol=rtol, atol=1e-3), (step, got, ref)
         params, m, v = oracle.adam_step(params, grads, m, v, step + 1, lr)
+
+
+@pytest.mark.parametrize("tag", ["init", "trained"])
+def test_autograd_port_matches_reference_fixtures(tag, golden, weights):
+    """oracle/autograd_port.py (the CPU baseline bench.py times) reproduces the reference's fp32 numbers."""
+    import torch
+    from oracle import autograd_port as AP
+    Ld = golden(f"losses_{tag}.npz")
+    x, n, d = torch.from_numpy(Ld["x"]), torch.from_numpy(Ld["normals"]), torch.from_numpy(Ld["d"])
+    for mode, w, fn in (("s1", [1e4, 1e4, 1e4, 1e3], AP.loss_s1), ("s2", [1e5, 1e5], AP.loss_s2)):
+        params = AP.make_params(weights[tag])
+        loss = fn(params, x, n, d, w, 100.0)
+        for k, v in loss.items():
+            ref = float(Ld[f"{mode}_32_{k}"][0])
+            assert abs(float(v) - ref) <= 1e-4 * max(abs(ref), 1e-2), (k, float(v), ref)
+        tot = sum(loss.values())
+        tot.backward()
+        for i in (0, 4, 8):
+            g = params[i][0].grad.numpy().reshape(-1)[::37]
+            assert rel_max(g, Ld[f"{mode}_gWsub{i}"]) < 5e-3            # fp32 autograd vs the reference's fp64 run
+    E = golden(f"evaluate_{tag}.npz")
+    f, g, H = AP.evaluate(AP.make_params(weights[tag], requires_grad=False), E["x"][:300], True, True)
+    assert rel_max(f, E["f"][:300]) < 1e-5 and rel_max(g, E["g"][:300]) < 1e-5 and rel_max(H, E["H"][:300]) < 1e-5
