@@ -141,7 +141,7 @@ def run_ours(args, rank, local_rank, world):
         dp = DataParallel()
     torch.manual_seed(123)
     model = SIREN(3, 1, [256] * 8, w0=30).to(dev)
-    trainer = FusedTrainer(model, dp=dp)
+    trainer = FusedTrainer(model, dp=dp, precision=args.precision)
     NB = 4
     host = []
     for x, n, d in make_batches(NB, rank):
@@ -282,10 +282,11 @@ def run_ours(args, rank, local_rank, world):
     value = world * P * args.steps / (ms_total * 1e-3)
     line = {"metric": "train points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f16 operands / f32 accumulate" if args.precision == "tc16" else "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: 200k-sample synthetic complex shape, SIREN 3->256x8->1, loss_s1 step "
                                    "(w=[1e4,1e4,1e4,1e3], alpha=100, Adam lr 1e-4), 29 970 rows per GPU per step [9990 on|9990 far|9990 near]",
-                       "rows_per_gpu": P, "global_rows": world * P, "parallelism": f"dp{world}", "precision": "fp32 CUDA-core step",
+                       "rows_per_gpu": P, "global_rows": world * P, "parallelism": f"dp{world}",
+                       "precision": "tcgen05 fp16-operand step (tc16)" if args.precision == "tc16" else "fp32 CUDA-core step",
                        "l2": "per-step working set (activation stashes, ~4 GB) exceeds the 126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / args.steps},
@@ -301,6 +302,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tc16", choices=["tc16", "fp32"],
+                    help="arithmetic of the training step: tcgen05 fp16-operand MMAs (default) or fp32 CUDA cores")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -234,55 +234,71 @@ int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, d
 // The stashes Z (pre-activations), A (activations) and Zb (pre-activation adjoints) are caller-owned
 // fp32 arrays [n_hidden][256][ld]; a call works on the column range starting at col0.
 // ---------------------------------------------------------------------------------------------
-int64_t dudf_stash_columns(int order, int64_t P) {
+int64_t dudf_stash_columns(int order, int64_t P, int precision) {
   const int nch = order_to_nch(order);
   if (nch < 0 || nch > 10 || P < 0) return -1;
+  if (precision == DUDF_PRECISION_TC16) {
+    const int pp = tc_train_pair_points(nch), pc = tc_train_pair_cols(nch);
+    return (P + pp - 1) / pp * pc;
+  }
   const int pt = simt_tile_points(nch), nc = simt_tile_cols(nch);
   return (P + pt - 1) / pt * nc;
 }
 
-int dudf_jet_forward(dudf_ctx* c, const float* x, int64_t P, int order, float* packed, float* Z, float* A, int64_t ld,
+static int fill_grad_view(dudf_ctx* c, float* const* gW, float* const* gb, GradView& gv, const char* who) {
+  memset(&gv, 0, sizeof(gv));
+  for (int i = 0; i < c->n_lin; ++i) {
+    DUDF_REQUIRE(gW[i] && (!gb || gb[i]), "%s: null gradient pointer for layer %d", who, i);
+    gv.W[i] = gW[i];
+    gv.b[i] = gb ? gb[i] : nullptr;
+  }
+  return 0;
+}
+
+int dudf_jet_forward(dudf_ctx* c, const float* x, int64_t P, int order, float* packed, void* Z, void* A, int64_t ld,
                      int64_t col0, int precision, void* stream) {
   DUDF_REQUIRE(c && c->weights_set, "dudf_jet_forward: weights not set");
   DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_jet_forward: order %d (0..2)", order);
   DUDF_REQUIRE(x && packed && Z && A, "dudf_jet_forward: null argument");
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "dudf_jet_forward: precision %d is not available for training yet", precision);
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "dudf_jet_forward: unknown precision %d", precision);
   if (P <= 0) return 0;
-  DUDF_REQUIRE(ld % 4 == 0 && col0 % 4 == 0 && col0 + dudf_stash_columns(order, P) <= ld, "dudf_jet_forward: stash too small");
+  DUDF_REQUIRE(ld % 4 == 0 && col0 % 4 == 0 && col0 + dudf_stash_columns(order, P, precision) <= ld, "dudf_jet_forward: stash too small");
+  if (precision == DUDF_PRECISION_TC16)
+    return tc_train_forward(c->tc_packed, c->view(), order_to_nch(order), x, P, packed, (float*)Z, A, ld, col0, c->sms, (cudaStream_t)stream);
   QueryOut o{nullptr, nullptr, nullptr, nullptr, packed, 0, 0.f};
-  return simt_forward(c->view(), order_to_nch(order), x, P, 0, 0, o, Z, A, ld, col0, c->sms, (cudaStream_t)stream);
+  return simt_forward(c->view(), order_to_nch(order), x, P, 0, 0, o, (float*)Z, (float*)A, ld, col0, c->sms, (cudaStream_t)stream);
 }
 
-int dudf_jet_backward(dudf_ctx* c, const float* x, int64_t P, int order, const float* seeds, const float* Z, float* Zb,
-                      int64_t ld, int64_t col0, float* const* gW, float* const* gb, int precision, void* stream) {
+int dudf_jet_backward(dudf_ctx* c, const float* x, int64_t P, int order, const float* seeds, const float* seed_absmax, const void* Z,
+                      void* Zb, int64_t ld, int64_t col0, float* const* gW, float* const* gb, int precision, void* stream) {
   DUDF_REQUIRE(c && c->weights_set, "dudf_jet_backward: weights not set");
   DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_jet_backward: order %d (0..2)", order);
   DUDF_REQUIRE(x && seeds && Z && Zb && gW && gb, "dudf_jet_backward: null argument");
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "dudf_jet_backward: precision %d is not available for training yet", precision);
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "dudf_jet_backward: unknown precision %d", precision);
   if (P <= 0) return 0;
   GradView gv;
-  memset(&gv, 0, sizeof(gv));
-  for (int i = 0; i < c->n_lin; ++i) {
-    DUDF_REQUIRE(gW[i] && gb[i], "dudf_jet_backward: null gradient pointer for layer %d", i);
-    gv.W[i] = gW[i];
-    gv.b[i] = gb[i];
-  }
-  return simt_backward(c->view(), gv, order_to_nch(order), x, P, seeds, Z, Zb, ld, col0, c->sms, (cudaStream_t)stream);
+  int rc = fill_grad_view(c, gW, gb, gv, "dudf_jet_backward");
+  if (rc) return rc;
+  if (precision == DUDF_PRECISION_TC16)
+    return tc_train_backward(c->tc_packed, c->view(), gv, order_to_nch(order), x, P, seeds, seed_absmax, (const float*)Z, Zb, ld, col0,
+                             c->sms, (cudaStream_t)stream);
+  return simt_backward(c->view(), gv, order_to_nch(order), x, P, seeds, (const float*)Z, (float*)Zb, ld, col0, c->sms, (cudaStream_t)stream);
 }
 
-int dudf_jet_wgrad(dudf_ctx* c, const float* Zb, const float* A, int64_t ld, int64_t ncols, float* const* gW, int precision,
-                   void* stream) {
+int dudf_jet_wgrad(dudf_ctx* c, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax, float* const* gW,
+                   int precision, void* stream) {
   DUDF_REQUIRE(c && Zb && A && gW, "dudf_jet_wgrad: null argument");
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "dudf_jet_wgrad: precision %d is not available for training yet", precision);
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "dudf_jet_wgrad: unknown precision %d", precision);
   GradView gv;
-  memset(&gv, 0, sizeof(gv));
-  for (int i = 0; i < c->n_lin; ++i) gv.W[i] = gW[i];
-  return simt_wgrad(c->view(), gv, Zb, A, ld, ncols, c->sms, (cudaStream_t)stream);
+  int rc = fill_grad_view(c, gW, nullptr, gv, "dudf_jet_wgrad");
+  if (rc) return rc;
+  if (precision == DUDF_PRECISION_TC16) return tc_train_wgrad(c->view(), gv, Zb, A, ld, seed_absmax, c->sms, (cudaStream_t)stream);
+  return simt_wgrad(c->view(), gv, (const float*)Zb, (const float*)A, ld, ncols, c->sms, (cudaStream_t)stream);
 }
 
 int dudf_loss(int mode, const float* packed, int nch, const float* normals, const float* dist, int64_t P, int64_t P_global,
-              const float* w_host, float alpha, const float* upstream, float* seeds, double* terms, double* s2_stats,
-              void* stream) {
+              const float* w_host, float alpha, const float* upstream, float* seeds, float* seed_absmax, double* terms,
+              double* s2_stats, void* stream) {
   DUDF_REQUIRE(packed && dist && w_host, "dudf_loss: null argument");
   DUDF_REQUIRE(mode == DUDF_LOSS_S1 || mode == DUDF_LOSS_S2 || mode == DUDF_LOSS_SIREN, "dudf_loss: unknown mode %d", mode);
   DUDF_REQUIRE(nch == 1 || nch == 4 || nch == 10, "dudf_loss: nch %d", nch);
@@ -291,7 +307,7 @@ int dudf_loss(int mode, const float* packed, int nch, const float* normals, cons
   LossArgs a;
   a.mode = mode; a.packed = packed; a.nch = nch; a.normals = normals; a.dist = dist; a.P = P; a.P_global = P_global;
   for (int k = 0; k < 4; ++k) a.w[k] = w_host[k];
-  a.alpha = alpha; a.upstream = upstream; a.seeds = seeds; a.terms = terms; a.s2_stats = s2_stats;
+  a.alpha = alpha; a.upstream = upstream; a.seeds = seeds; a.terms = terms; a.s2_stats = s2_stats; a.seed_absmax = seed_absmax;
   return loss_seeds(a, (cudaStream_t)stream);
 }
 

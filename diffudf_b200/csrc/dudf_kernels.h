@@ -51,7 +51,17 @@ struct LossArgs {
   float* seeds;             // [P][NCH] out
   double* terms;            // [4] accumulated (atomicAdd)
   double* s2_stats;         // [3] n, sum, sumsq (mode S2)
+  float* seed_absmax;       // [1] running max of |stored seed| (atomicMax), may be null
 };
+// ---- tcgen05 training path (dudf_tc_train.cu) ----
+int tc_train_pair_cols(int nch);
+int tc_train_pair_points(int nch);
+int tc_train_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, float* outp, float* Ust, void* Aimg,
+                     int64_t ld, int64_t col0, int sms, cudaStream_t st);
+int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, int nch, const float* x, int64_t P, const float* seeds,
+                      const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st);
+int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,
+                   int sms, cudaStream_t st);
 int loss_seeds(const LossArgs& a, cudaStream_t st);
 int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st);
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);

@@ -34,6 +34,7 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[N], double* dst) {
 __global__ void __launch_bounds__(256) loss_seed_kernel(LossArgs a) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double t[4] = {0.0, 0.0, 0.0, 0.0};
+  float smax = 0.f;
   if (p < a.P) {
     const int nch = a.nch;
     const float* v = a.packed + p * nch;
@@ -134,6 +135,15 @@ __global__ void __launch_bounds__(256) loss_seed_kernel(LossArgs a) {
       float* dst = a.seeds + p * nch;
       for (int c = 0; c < nch; ++c) dst[c] = sd[c];
     }
+    if (a.seed_absmax) {
+      // magnitude of the stored seeds of the tensor-core reverse sweep (second-order channels carry 1/KAPPA = 8)
+      for (int c = 0; c < nch; ++c) smax = fmaxf(smax, fabsf(sd[c]) * (c >= 4 ? 8.f : 1.f));
+    }
+  }
+  if (a.seed_absmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    if ((threadIdx.x & 31) == 0 && smax > 0.f && isfinite(smax)) atomicMax(reinterpret_cast<int*>(a.seed_absmax), __float_as_int(smax));
   }
   if (a.terms && a.mode != DUDF_LOSS_S2) block_reduce_add<4>(t, a.terms);
 }

@@ -48,17 +48,25 @@ struct TcCfg {
   static constexpr int SMEM = OFF_BAR + 256 + 1024;                   // + alignment slack
 };
 
-size_t tc_packed_bytes(int n_lin) { return (size_t)((n_lin > 2) ? (n_lin - 2) : 1) * 8 * TC_CHUNK_BYTES; }
+size_t tc_packed_bytes(int n_lin) { return (size_t)((n_lin > 2) ? (n_lin - 2) : 1) * 2 * 8 * TC_CHUNK_BYTES; }
 
-// ---- weight packing: fp16(ww * W) in ready-to-copy swizzled chunks [layer][half][kblock] ----
+// ---- weight packing: fp16(ww * W) in ready-to-copy swizzled chunks [layer][half][kblock]; the images of
+// ---- the transposed matrices (A operand of the reverse sweep) follow the forward ones ----
 __global__ void __launch_bounds__(256) tc_pack_kernel(NetView net, unsigned char* packed) {
   const int l = blockIdx.y + 1;                       // linear layer index 1 .. n_lin-2
   const int n = blockIdx.x;                           // output neuron
   const int k = threadIdx.x;                          // input neuron
-  const float v = net.ww * net.W[l][n * 256 + k];
-  const int h = n >> 7, r = n & 127, kb = k >> 6, kk = k & 63;
-  unsigned char* chunk = packed + ((size_t)(l - 1) * 8 + h * 4 + kb) * TC_CHUNK_BYTES;
-  *reinterpret_cast<__half*>(chunk + sw128_offset(r, kk)) = __float2half_rn(v);
+  const __half v = __float2half_rn(net.ww * net.W[l][n * 256 + k]);
+  {
+    const int h = n >> 7, r = n & 127, kb = k >> 6, kk = k & 63;
+    unsigned char* chunk = packed + ((size_t)(l - 1) * 8 + h * 4 + kb) * TC_CHUNK_BYTES;
+    *reinterpret_cast<__half*>(chunk + sw128_offset(r, kk)) = v;
+  }
+  {
+    const int h = k >> 7, r = k & 127, kb = n >> 6, kk = n & 63;
+    unsigned char* chunk = packed + ((size_t)(net.n_lin - 2 + l - 1) * 8 + h * 4 + kb) * TC_CHUNK_BYTES;
+    *reinterpret_cast<__half*>(chunk + sw128_offset(r, kk)) = v;
+  }
 }
 
 int tc_pack(const NetView& net, void* packed, cudaStream_t st) {

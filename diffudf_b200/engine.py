@@ -128,31 +128,32 @@ class Engine:
                                                  _lib.ptr(H_host), max_batch, PRECISIONS[precision]), "dudf_evaluate_host")
 
     # ---- training primitives ----
-    def stash_columns(self, order, P):
-        return int(self.L.dudf_stash_columns(order, P))
+    def stash_columns(self, order, P, precision="fp32"):
+        return int(self.L.dudf_stash_columns(order, P, PRECISIONS[precision]))
 
     def jet_forward(self, x, order, packed, Z, A, ld, col0, precision="fp32"):
         with torch.cuda.device(x.device):
             _lib.check(self.L.dudf_jet_forward(self.h, x.data_ptr(), x.shape[0], order, packed.data_ptr(), Z.data_ptr(), A.data_ptr(), ld,
                                                col0, PRECISIONS[precision], _lib.current_stream()), "dudf_jet_forward")
 
-    def jet_backward(self, x, order, seeds, Z, Zb, ld, col0, gW, gb, precision="fp32"):
+    def jet_backward(self, x, order, seeds, Z, Zb, ld, col0, gW, gb, precision="fp32", seed_absmax=None):
         with torch.cuda.device(x.device):
-            _lib.check(self.L.dudf_jet_backward(self.h, x.data_ptr(), x.shape[0], order, seeds.data_ptr(), Z.data_ptr(), Zb.data_ptr(), ld,
-                                                col0, _ptr_array(gW), _ptr_array(gb), PRECISIONS[precision], _lib.current_stream()),
-                       "dudf_jet_backward")
+            _lib.check(self.L.dudf_jet_backward(self.h, x.data_ptr(), x.shape[0], order, seeds.data_ptr(), _lib.ptr(seed_absmax),
+                                                Z.data_ptr(), Zb.data_ptr(), ld, col0, _ptr_array(gW), _ptr_array(gb),
+                                                PRECISIONS[precision], _lib.current_stream()), "dudf_jet_backward")
 
-    def jet_wgrad(self, Zb, A, ld, ncols, gW, precision="fp32"):
+    def jet_wgrad(self, Zb, A, ld, ncols, gW, precision="fp32", seed_absmax=None):
         with torch.cuda.device(Zb.device):
-            _lib.check(self.L.dudf_jet_wgrad(self.h, Zb.data_ptr(), A.data_ptr(), ld, ncols, _ptr_array(gW), PRECISIONS[precision],
-                                             _lib.current_stream()), "dudf_jet_wgrad")
+            _lib.check(self.L.dudf_jet_wgrad(self.h, Zb.data_ptr(), A.data_ptr(), ld, ncols, _lib.ptr(seed_absmax), _ptr_array(gW),
+                                             PRECISIONS[precision], _lib.current_stream()), "dudf_jet_wgrad")
 
-    def loss(self, mode, packed, nch, normals, dist, P, P_global, w, alpha, upstream=None, seeds=None, terms=None, s2_stats=None):
+    def loss(self, mode, packed, nch, normals, dist, P, P_global, w, alpha, upstream=None, seeds=None, terms=None, s2_stats=None,
+             seed_absmax=None):
         w4 = (ctypes.c_float * 4)(*([float(v) for v in w] + [0.0] * (4 - len(w))))
         with torch.cuda.device(packed.device):
             _lib.check(self.L.dudf_loss(LOSS_MODES[mode], packed.data_ptr(), nch, _lib.ptr(normals), dist.data_ptr(), P, P_global, w4,
-                                        float(alpha), _lib.ptr(upstream), _lib.ptr(seeds), _lib.ptr(terms), _lib.ptr(s2_stats),
-                                        _lib.current_stream()), "dudf_loss")
+                                        float(alpha), _lib.ptr(upstream), _lib.ptr(seeds), _lib.ptr(seed_absmax), _lib.ptr(terms),
+                                        _lib.ptr(s2_stats), _lib.current_stream()), "dudf_loss")
 
     def loss_s2_stats(self, packed, dist, P, stats):
         with torch.cuda.device(packed.device):

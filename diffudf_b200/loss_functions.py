@@ -19,22 +19,27 @@ SIREN_KEYS = ("sdf_on_surf", "sdf_off_surf", "normal_constraint", "grad_constrai
 class TrainCore:
     """Forward/backward of one batch on the native primitives, with cached workspaces."""
 
-    def __init__(self, model):
+    def __init__(self, model, precision=None):
         self.model = model
         self.ws = {}
         self.pending = None
+        self.precision = precision          # None -> model.train_precision (default 'fp32')
 
-    def _buf(self, name, shape, dtype=torch.float32):
+    def _prec(self):
+        return self.precision or getattr(self.model, "train_precision", "fp32")
+
+    def _buf(self, name, shape, dtype=torch.float32, zero=False):
         key = (name, tuple(shape), dtype)
         t = self.ws.get(key)
         if t is None:
             for k in [k for k in self.ws if k[0] == name]:
                 del self.ws[k]
-            t = torch.empty(*shape, device=self.model._weights_biases()[0][0].device, dtype=dtype)
+            alloc = torch.zeros if zero else torch.empty
+            t = alloc(*shape, device=self.model._weights_biases()[0][0].device, dtype=dtype)
             self.ws[key] = t
         return t
 
-    def plan(self, mode, P, n_on, w):
+    def plan(self, mode, P, n_on, w, prec):
         eng = self.model._engine_synced()
         if mode == "s1":
             base = 1 if (w[3] != 0 or w[2] != 0) else 0
@@ -47,29 +52,39 @@ class TrainCore:
         for row0, rows, order in ((0, nh, 2), (nh, P - nh, base)):
             if rows <= 0:
                 continue
-            cols = eng.stash_columns(order, rows)
+            cols = eng.stash_columns(order, rows, prec)
             segs.append(dict(row0=row0, rows=rows, order=order, col0=col, cols=cols, off=off))
             col += cols
             off += rows * NCH[order]
-        return segs, (col + 3) // 4 * 4, off
+        ld = (col + 63) // 64 * 64 if prec == "tc16" else (col + 3) // 4 * 4
+        return segs, ld, off
+
+    def _stashes(self, L, ld, prec):
+        Z = self._buf("Z", (L, 256, ld))
+        if prec == "tc16":       # fp16 operand images [layer][ld/64][256][64]; zero tails are part of the contract
+            A = self._buf("A", (L, ld // 64, 256, 64), torch.float16, zero=True)
+            Zb = self._buf("Zb", (L, ld // 64, 256, 64), torch.float16, zero=True)
+        else:
+            A = self._buf("A", (L, 256, ld))
+            Zb = self._buf("Zb", (L, 256, ld))
+        return Z, A, Zb
 
     def forward(self, mode, x, normals, d, n_on, w, alpha, P_global=None, stats_reduce=None):
         """Returns a (4,) float64 device tensor with this rank's share of the loss terms."""
         m = self.model
         eng = m._engine_synced()
+        prec = self._prec()
         P = x.shape[0]
         P_global = P if P_global is None else P_global
-        segs, ld, nout = self.plan(mode, P, n_on, w)
-        L = m.n_hidden
-        Z = self._buf("Z", (L, 256, ld))
-        A = self._buf("A", (L, 256, ld))
+        segs, ld, nout = self.plan(mode, P, n_on, w, prec)
+        Z, A, Zb = self._stashes(m.n_hidden, ld, prec)
         packed = self._buf("packed", (nout,))
         terms = torch.zeros(4, device=x.device, dtype=torch.float64)
         stats = torch.zeros(3, device=x.device, dtype=torch.float64) if mode == "s2" else None
         for s in segs:
             xs = x[s["row0"]:s["row0"] + s["rows"]]
             pk = packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]
-            eng.jet_forward(xs, s["order"], pk, Z, A, ld, s["col0"], "fp32")
+            eng.jet_forward(xs, s["order"], pk, Z, A, ld, s["col0"], prec)
             ds = d[s["row0"]:s["row0"] + s["rows"]]
             if mode == "s2":
                 eng.loss_s2_stats(pk, ds, s["rows"], stats)
@@ -81,7 +96,7 @@ class TrainCore:
                 stats_reduce(stats)
             eng.loss_s2_finish(stats, w[0], w[1], terms)
         self.pending = dict(mode=mode, x=x, normals=normals, d=d, w=list(w), alpha=alpha, P_global=P_global, segs=segs,
-                            ld=ld, Z=Z, A=A, packed=packed, stats=stats, sig=eng._sig)
+                            ld=ld, Z=Z, A=A, Zb=Zb, packed=packed, stats=stats, sig=eng._sig, prec=prec)
         return terms
 
     def backward(self, upstream, gW, gB):
@@ -93,19 +108,24 @@ class TrainCore:
         eng = m._engine_synced()
         if eng._sig != p["sig"]:
             raise RuntimeError("SIREN parameters changed between the loss forward and backward")
-        Zb = self._buf("Zb", tuple(p["Z"].shape))
+        prec = p["prec"]
         seeds = self._buf("seeds", tuple(p["packed"].shape))
-        ncols = 0
-        for s in p["segs"]:
+        absmax = torch.zeros(1, device=p["x"].device, dtype=torch.float32) if prec == "tc16" else None
+        for s in p["segs"]:                 # all seeds (and their magnitude) before the first reverse sweep
             r0, r1 = s["row0"], s["row0"] + s["rows"]
             nch = NCH[s["order"]]
             pk = p["packed"][s["off"]:s["off"] + s["rows"] * nch]
             sd = seeds[s["off"]:s["off"] + s["rows"] * nch]
             eng.loss(p["mode"], pk, nch, p["normals"][r0:r1] if p["normals"] is not None else None, p["d"][r0:r1], s["rows"],
-                     p["P_global"], p["w"], p["alpha"], upstream=upstream, seeds=sd, s2_stats=p["stats"])
-            eng.jet_backward(p["x"][r0:r1], s["order"], sd, p["Z"], Zb, p["ld"], s["col0"], gW, gB, "fp32")
+                     p["P_global"], p["w"], p["alpha"], upstream=upstream, seeds=sd, s2_stats=p["stats"], seed_absmax=absmax)
+        ncols = 0
+        for s in p["segs"]:
+            r0, r1 = s["row0"], s["row0"] + s["rows"]
+            nch = NCH[s["order"]]
+            sd = seeds[s["off"]:s["off"] + s["rows"] * nch]
+            eng.jet_backward(p["x"][r0:r1], s["order"], sd, p["Z"], p["Zb"], p["ld"], s["col0"], gW, gB, prec, seed_absmax=absmax)
             ncols = s["col0"] + s["cols"]
-        eng.jet_wgrad(Zb, p["A"], p["ld"], ncols, gW, "fp32")
+        eng.jet_wgrad(p["Zb"], p["A"], p["ld"], ncols, gW, prec, seed_absmax=absmax)
 
 
 def _core(model):

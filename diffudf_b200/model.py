@@ -190,7 +190,8 @@ class SIREN(nn.Module):
             self.net[0].apply(first_layer_sine_init)
             self.net[1:].apply(lambda module: sine_init(module, self.ww))
         self.n_hidden = len(hidden_layer_config)
-        self.precision = "fp32"
+        self.precision = "fp32"           # arithmetic of field queries: 'fp32' | 'tc16'
+        self.train_precision = "fp32"     # arithmetic of the fused losses / trainer
         self.jet_order = 0
         self._engine = None
 

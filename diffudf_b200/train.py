@@ -29,7 +29,7 @@ class FusedTrainer:
     """Owns flat fp32 parameter / gradient / Adam-moment buffers; the module's parameters become views
     of the flat buffer so that state_dict()/load_state_dict() keep working."""
 
-    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None):
+    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None, precision=None):
         self.model = model
         self.betas, self.eps, self.dp = betas, eps, dp
         ws, bs = model._weights_biases()
@@ -53,7 +53,7 @@ class FusedTrainer:
             gv = self.grad[off:off + k].view_as(t)
             (self.gW if i % 2 == 0 else self.gB).append(gv)
             off += k
-        self.core = TrainCore(model)
+        self.core = TrainCore(model, precision)
         self.t = 0
 
     def step(self, mode, x, normals, d, n_on, weights, alpha, lr):

@@ -96,13 +96,18 @@ int dudf_evaluate_host(dudf_ctx* ctx, const float* x_host, int64_t N, int order,
  * caller-owned fp32 arrays [n_hidden][256][ld]; dudf_stash_columns gives the padded number of columns a call
  * uses starting at col0 (ld and col0 multiples of 4).  Gradients ACCUMULATE into gW / gb (HOST arrays of
  * n_hidden+1 DEVICE pointers, nn.Linear layouts). */
-int64_t dudf_stash_columns(int order, int64_t P);
-int dudf_jet_forward(dudf_ctx* ctx, const float* x, int64_t P, int order, float* packed, float* Z, float* A, int64_t ld,
+int64_t dudf_stash_columns(int order, int64_t P, int precision);
+int dudf_jet_forward(dudf_ctx* ctx, const float* x, int64_t P, int order, float* packed, void* Z, void* A, int64_t ld,
                      int64_t col0, int precision, void* stream);
-int dudf_jet_backward(dudf_ctx* ctx, const float* x, int64_t P, int order, const float* seeds, const float* Z, float* Zb,
-                      int64_t ld, int64_t col0, float* const* gW_host, float* const* gb_host, int precision, void* stream);
-int dudf_jet_wgrad(dudf_ctx* ctx, const float* Zb, const float* A, int64_t ld, int64_t ncols, float* const* gW_host,
-                   int precision, void* stream);
+int dudf_jet_backward(dudf_ctx* ctx, const float* x, int64_t P, int order, const float* seeds, const float* seed_absmax,
+                      const void* Z, void* Zb, int64_t ld, int64_t col0, float* const* gW_host, float* const* gb_host,
+                      int precision, void* stream);
+int dudf_jet_wgrad(dudf_ctx* ctx, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax,
+                   float* const* gW_host, int precision, void* stream);
+/* With DUDF_PRECISION_TC16 the stashes change type: Z stays fp32 [n_hidden][256][ld] (ld a multiple of 64), A and Zb are
+ * fp16 images [n_hidden][ld/64][256][64] (128-byte swizzled, zero-initialised by the caller), and the reverse sweep runs
+ * under a power-of-two loss scale derived from seed_absmax (1 device float, zeroed by the caller before the dudf_loss
+ * calls of a step, which raise it with atomicMax; all dudf_loss calls of a step must precede its first backward). */
 /* Loss epilogue over P rows.  w_host: 4 host floats (loss weights); P_global: divisor of the means (sum of rows over
  * data-parallel ranks).  terms (4 device doubles, may be NULL) is ACCUMULATED with this call's share of each term in
  * the order of the reference dicts: S1 {sdf_on_surf, sdf_off_surf, hessian_constraint, grad_constraint}, SIREN
@@ -111,8 +116,8 @@ int dudf_jet_wgrad(dudf_ctx* ctx, const float* Zb, const float* A, int64_t ld, i
  * (all-reduced) statistics n, sum, sum of squares of the on-surface predictions: dudf_loss_s2_stats accumulates them
  * into 3 device doubles, dudf_loss_s2_finish turns them into the two S2 terms. */
 int dudf_loss(int mode, const float* packed, int nch, const float* normals, const float* dist, int64_t P, int64_t P_global,
-              const float* w_host, float alpha, const float* upstream, float* seeds, double* terms, double* s2_stats,
-              void* stream);
+              const float* w_host, float alpha, const float* upstream, float* seeds, float* seed_absmax, double* terms,
+              double* s2_stats, void* stream);
 int dudf_loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, void* stream);
 int dudf_loss_s2_finish(const double* stats, float w0, float w1, double* terms, void* stream);
 /* torch.optim.Adam.step as configured in train.py:334-337 (betas, eps given explicitly, no weight decay);

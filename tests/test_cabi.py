@@ -28,10 +28,12 @@ def test_library_builds_and_exports_header_symbols():
 def test_stash_geometry_is_host_side():
     from diffudf_b200 import _lib
     L = _lib.lib()
-    assert L.dudf_stash_columns(0, 64) == 64
-    assert L.dudf_stash_columns(1, 17) == 2 * 64          # 16 points x 4 channels per tile
-    assert L.dudf_stash_columns(2, 9990) == 1249 * 80     # 8 points x 10 channels per tile
-    assert L.dudf_stash_columns(5, 10) == -1
+    assert L.dudf_stash_columns(0, 64, 0) == 64
+    assert L.dudf_stash_columns(1, 17, 0) == 2 * 64          # fp32 path: 16 points x 4 channels per tile
+    assert L.dudf_stash_columns(2, 9990, 0) == 1249 * 80     # 8 points x 10 channels per tile
+    assert L.dudf_stash_columns(1, 65, 1) == 2 * 256         # tcgen05 path: pairs of 32-point sub-tiles, 4 channels
+    assert L.dudf_stash_columns(2, 9990, 1) == 625 * 160     # pairs of 8-point sub-tiles, 10 channels
+    assert L.dudf_stash_columns(5, 10, 0) == -1
 
 
 def test_sass_uses_tcgen05_and_bulk_copies():

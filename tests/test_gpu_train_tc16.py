@@ -1,0 +1,85 @@
+"""Parity of the tensor-core (tcgen05, fp16 operands) training step against the fp64 oracle.
+
+Tolerances: the forward is the same fp16-operand jet as the TC16 queries (tf32-class significand), so loss
+terms are held to 2e-3 relative (they average per-row errors); parameter gradients to 1e-2 in the max measure
+per tensor and 5e-3 in relative L2 (operand rounding of both the activations and the adjoints, 8 layers deep).
+The fp32 CUDA-core path (tests/test_gpu_losses.py) is the 1e-5-class reference on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+MODES = [("s1", [1e4, 1e4, 1e4, 1e3]), ("s1_nohess", [1e4, 1e4, 0, 1e3]), ("s2", [1e5, 1e5]), ("siren", [3e3, 1e2, 1e2, 5e1])]
+
+
+def _loss(model, mode, x, n, d, w, alpha=100.0):
+    import diffudf_b200 as D
+    gt = {"normals": torch.from_numpy(n).cuda(), "sdf": torch.from_numpy(d).cuda()}
+    xi = torch.from_numpy(x).cuda()
+    if mode.startswith("s1"):
+        return D.loss_s1(model, xi, gt, w, alpha)
+    if mode == "s2":
+        return D.loss_s2(model, xi, gt, w, alpha)
+    return D.loss_siren(model, xi, gt, w)
+
+
+@pytest.mark.parametrize("tag", ["init", "trained"])
+@pytest.mark.parametrize("mode,w", MODES)
+def test_tc16_loss_terms_and_gradients(tag, mode, w, golden, oracle, weights, cuda_models):
+    Ld = golden(f"losses_{tag}.npz")
+    m = cuda_models[tag]
+    m.train_precision = "tc16"
+    try:
+        for p in m.parameters():
+            p.requires_grad_(True)
+            p.grad = None
+        loss = _loss(m, mode, Ld["x"], Ld["normals"], Ld["d"], w)
+        terms_ref, grads_ref = oracle.train_grads(weights[tag], Ld["x"], Ld["normals"], Ld["d"], mode.split("_")[0], w, 100.0)
+        errs = {}
+        for k, v in loss.items():
+            ref = float(terms_ref[k])
+            errs[k] = abs(float(v) - ref) / max(abs(ref), 1e-2)
+        total = 0
+        for v in loss.values():
+            total = total + v
+        total.backward()
+        gmax, gl2 = {}, {}
+        for i in range(len(grads_ref)):
+            gW = m.net[i][0].weight.grad.cpu().numpy()
+            gb = m.net[i][0].bias.grad.cpu().numpy()
+            gmax[f"W{i}"] = rel_max(gW, grads_ref[i][0].reshape(gW.shape))
+            gmax[f"b{i}"] = rel_max(gb, grads_ref[i][1].reshape(gb.shape))
+            gl2[f"W{i}"] = rel_l2(gW, grads_ref[i][0].reshape(gW.shape))
+        print(f"tc16 {tag} {mode}: term errs {errs}\n   grad max-measure {gmax}\n   grad rel-L2 {gl2}")
+        assert max(errs.values()) < 2e-3, errs
+        assert max(gmax.values()) < 1e-2, gmax
+        assert max(gl2.values()) < 5e-3, gl2
+    finally:
+        m.train_precision = "fp32"
+
+
+def test_tc16_trainer_matches_fp32_trainer_for_a_few_steps(weights):
+    """Same batches through FusedTrainer in both arithmetics: loss terms stay within 1 % for the first steps."""
+    from diffudf_b200 import SIREN, synthetic
+    from diffudf_b200.train import FusedTrainer
+    shape = synthetic.make_shape(0)
+    sp, sn = shape.sample_surface(20000, np.random.default_rng(0))
+    batches = [synthetic.make_batch(shape, sp, sn, 3000, (0.333, 0.666), np.random.default_rng(5 + i)) for i in range(3)]
+    out = {}
+    for prec in ("fp32", "tc16"):
+        m = SIREN(3, 1, [256] * 8, w0=30, delay_init=True)
+        m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(v) for i, (W, b) in enumerate(weights["trained"])
+                           for k, v in (("weight", W), ("bias", b))})
+        tr = FusedTrainer(m.cuda(), precision=prec)
+        res = []
+        for x, n, d in batches:
+            t = tr.step("s1", torch.from_numpy(x[0]).cuda(), torch.from_numpy(n[0]).cuda(), torch.from_numpy(d[0, :, 0]).cuda(), 999,
+                        [1e4, 1e4, 1e4, 1e3], 100.0, 1e-5)
+            res.append(t.cpu().numpy())
+        out[prec] = np.array(res)
+        assert all(torch.isfinite(v).all() for v in m.state_dict().values())
+    print(out)
+    assert np.allclose(out["fp32"], out["tc16"], rtol=1e-2, atol=1e-2)

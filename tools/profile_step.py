@@ -1,5 +1,6 @@
 """Short driver for ncu captures: a few fused training steps and one grid query per precision.
-    ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 3 -o gpurun_out/prof python tools/profile_step.py
+    ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 3 -o gpurun_out/prof \
+        python tools/profile_step.py [steps] [gridN] [train precision: tc16|fp32]
 """
 import os
 import sys
@@ -14,15 +15,17 @@ from diffudf_b200.train import FusedTrainer  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 gridN = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+prec = sys.argv[3] if len(sys.argv) > 3 else "tc16"
 torch.manual_seed(123)
 model = SIREN(3, 1, [256] * 8, w0=30).cuda()
-tr = FusedTrainer(model)
+tr = FusedTrainer(model, precision=prec)
 x, n, d = make_batches(1, 0)[0]
 x, n, d = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x[0], n[0], d[0, :, 0]))
 for _ in range(steps):
     tr.step("s1", x, n, d, 9990, W_S1, ALPHA, LR)
-eng = model._engine_synced()
-for prec in ("tc16", "fp32"):
-    eng.query_grid(gridN, 0, gridN ** 3, prec, 3, ALPHA)
+if gridN > 0:
+    eng = model._engine_synced()
+    for p in ("tc16", "fp32"):
+        eng.query_grid(gridN, 0, gridN ** 3, p, 3, ALPHA)
 torch.cuda.synchronize()
 print("profile_step done")
