@@ -6,8 +6,10 @@
 // epilogue warps.  Differences:
 //   * stored variables: u0 = w z0, u_i = w z_i, v_ij = KAPPA w z_ij and a0 = sin u0, a_i = cos(u0) u_i,
 //     b_ij = KAPPA a_ij (KAPPA = 1/8 keeps second-order channels inside fp16 range);
-//   * the forward stashes the stored pre-activations (fp32, [layer][neuron][column]) and the stored
-//     activations as fp16 swizzled 256x64 images ready to be bulk-copied as weight-gradient operands;
+//   * the forward stashes the stored pre-activations in fp32, thread-major ([layer][column group][4-vector][neuron])
+//     so that every warp store is one contiguous 512-byte line, and the stored activations as fp16: the MMA
+//     thread bulk-copies (TMA engine, smem -> global) the finished B-operand tile into per-k-block planes
+//     [layer][kblock][column][64 neurons], which are exactly the MN-major operands of the weight gradient;
 //   * the backward runs the chain in reverse with the transposed weight images, reads the stash,
 //     applies the sine-jet adjoint per thread and emits the adjoints both as the next B operand and
 //     as fp16 images; all adjoints carry a power-of-two loss scale S chosen from max|seed| so that
@@ -61,6 +63,13 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
 
+// bulk copy shared -> global (TMA engine), grouped completion
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- roles shared by the forward and backward chain kernels ------------------------------------
 // image index of MMA phase j (0 .. n_phase-1): forward uses layer j+1, backward layer L-1-j (transposed images)
 __device__ __forceinline__ const unsigned char* tt_image(const unsigned char* packed, int n_phase, int j, bool backward) {
@@ -84,9 +93,12 @@ __device__ __forceinline__ void tt_producer(const unsigned char* packed, unsigne
     }
 }
 
+// `img` (may be null): plane array [layer][4][ld][128 B]; phase j's finished tile of sub-tile s is copied to the rows
+// [col0 + (pair*2+s)*N, +N) of the 4 planes of layer img_layer(j) (forward: j, backward: L-1-j)
 template <int NCH>
 __device__ __forceinline__ void tt_mma(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
-                                       uint64_t* acc_ready, uint32_t tmem_base, int64_t npairs, int n_phase) {
+                                       uint64_t* acc_ready, uint32_t tmem_base, int64_t npairs, int n_phase, unsigned char* img,
+                                       int64_t ld, int64_t col0, bool backward) {
   using C = TtCfg<NCH>;
   constexpr uint32_t idesc = make_idesc_f16(128, C::N, 0, 0, 0);
   uint32_t stage = 0, phase = 0;
@@ -112,6 +124,15 @@ __device__ __forceinline__ void tt_mma(unsigned char* act, unsigned char* ring, 
             mma_commit(&empty[stage]);
             if (++stage == TT_STAGES) { stage = 0; phase ^= 1; }
           }
+        }
+        if (img) {
+          const int layer = backward ? (n_phase - j) : j;
+          const int64_t row0 = col0 + (pair * 2 + s) * C::N;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+            bulk_s2g(img + (((size_t)layer * 4 + kb) * ld + row0) * 128, act + s * C::ACT_BYTES + kb * C::KB_BYTES, C::KB_BYTES);
+          bulk_commit();
+          bulk_wait_read0();          // the tile may be overwritten once acc_ready is published
         }
         mma_commit(&acc_ready[s]);
       }
@@ -168,27 +189,11 @@ __device__ __forceinline__ void adj_point(const float* u, const float* ab, float
   ub[0] = u0;
 }
 
-// write GC values of one thread (its neuron n) into: the smem B-operand tile (2-byte scattered, K-major),
-// and optionally the fp16 image stash (16-byte swizzled chunks of 8 columns)
+// write GC values of one thread (its neuron n) into the smem B-operand tile (2-byte scattered, K-major rows)
 template <int GC>
-__device__ __forceinline__ void emit_group(const float* v, unsigned char* tile_g, const uint32_t* sw, unsigned char* img, int64_t colg,
-                                           int n) {
+__device__ __forceinline__ void emit_group(const float* v, unsigned char* tile_g, const uint32_t* sw) {
 #pragma unroll
   for (int j = 0; j < GC; ++j) *reinterpret_cast<__half*>(tile_g + j * 128 + sw[j & 7]) = __float2half_rn(v[j]);
-  if (img) {
-#pragma unroll
-    for (int j8 = 0; j8 < GC / 8; ++j8) {
-      const int64_t c8 = colg + j8 * 8;
-      const int64_t cb = c8 >> 6;
-      const uint32_t chunk = (uint32_t)(c8 & 63) >> 3;
-      uint4 w;
-      w.x = pack_h2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-      w.y = pack_h2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-      w.z = pack_h2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-      w.w = pack_h2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-      *reinterpret_cast<uint4*>(img + (size_t)cb * TT_IMG + n * 128 + ((chunk ^ (uint32_t)(n & 7)) << 4)) = w;
-    }
-  }
 }
 
 // =============================================================================================
@@ -228,7 +233,7 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   if (warp == 8) {
     if (lane == 0) tt_producer(packed, ring, full, empty, npairs, L - 1, false);
   } else if (warp == 9) {
-    if (lane == 0) tt_mma<NCH>(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1);
+    if (lane == 0) tt_mma<NCH>(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Aimg, ld, col0, false);
   } else {
     const int q = warp & 3, h = warp >> 2;
     const int n = h * 128 + q * 32 + lane;
@@ -256,8 +261,7 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
         for (int s = 0; s < 2; ++s) {
           unsigned char* tile = act + s * C::ACT_BYTES + tile_off;
           const int64_t colt = col0 + (pair * 2 + s) * C::N;           // first stash column of this sub-tile
-          float* urow = Ust + ((size_t)l * 256 + n) * ld + colt;
-          unsigned char* img = (l < L - 1) ? (Aimg + (size_t)l * ncb * TT_IMG) : nullptr;
+          float* ust = Ust + ((size_t)l * ld + colt) * 256 + n * 4;     // thread-major: [column group][4-vector][neuron]
           if (l > 0) {
             mbar_wait(&acc_ready[s], acc_phase[s], 0x400 + s);
             acc_phase[s] ^= 1;
@@ -295,8 +299,9 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
             }
 #pragma unroll
             for (int j4 = 0; j4 < C::GC / 4; ++j4)
-              *reinterpret_cast<float4*>(urow + g * C::GC + j4 * 4) = make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
-            emit_group<C::GC>(a, tile + g * C::GC * 128, sw, img, colt + g * C::GC, n);
+              *reinterpret_cast<float4*>(ust + (size_t)g * C::GC * 256 + j4 * 1024) =
+                  make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
+            emit_group<C::GC>(a, tile + g * C::GC * 128, sw);
           }
           if (l < L - 1) {
             tc_fence_before();
@@ -379,7 +384,7 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
   if (warp == 8) {
     if (lane == 0) tt_producer(packed, ring, full, empty, npairs, L - 1, true);
   } else if (warp == 9) {
-    if (lane == 0) tt_mma<NCH>(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1);
+    if (lane == 0) tt_mma<NCH>(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Zimg, ld, col0, true);
   } else {
     const int q = warp & 3, h = warp >> 2;
     const int n = h * 128 + q * 32 + lane;
@@ -419,8 +424,7 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
         for (int s = 0; s < 2; ++s) {
           unsigned char* tile = act + s * C::ACT_BYTES + tile_off;
           const int64_t colt = col0 + (pair * 2 + s) * C::N;
-          const float* urow = Ust + ((size_t)l * 256 + n) * ld + colt;
-          unsigned char* img = (l > 0) ? (Zimg + (size_t)l * ncb * TT_IMG) : nullptr;
+          const float* ust = Ust + ((size_t)l * ld + colt) * 256 + n * 4;
           if (l < L - 1) {
             mbar_wait(&acc_ready[s], acc_phase[s], 0x400 + s);
             acc_phase[s] ^= 1;
@@ -432,7 +436,7 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
             float u[C::GC], ab[C::GC], ub[C::GC];
 #pragma unroll
             for (int j4 = 0; j4 < C::GC / 4; ++j4) {
-              const float4 t = *reinterpret_cast<const float4*>(urow + g * C::GC + j4 * 4);
+              const float4 t = *reinterpret_cast<const float4*>(ust + (size_t)g * C::GC * 256 + j4 * 1024);
               u[j4 * 4] = t.x; u[j4 * 4 + 1] = t.y; u[j4 * 4 + 2] = t.z; u[j4 * 4 + 3] = t.w;
             }
             if (l == L - 1) {
@@ -472,7 +476,7 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
             if (l > 0) {
 #pragma unroll
               for (int j = 0; j < C::GC; ++j) ub[j] = clamp_h(ub[j]);
-              emit_group<C::GC>(ub, tile + g * C::GC * 128, sw, img, colt + g * C::GC, n);
+              emit_group<C::GC>(ub, tile + g * C::GC * 128, sw);
             }
           }
           atomicAdd(&grad.b[l][n], bsum * wl_cur * invS);
@@ -586,6 +590,101 @@ tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const uns
   if (warp == 5) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- v2: operands are the per-k-block planes [layer][4][ld rows = columns][64 neurons] written by the chain
+// kernels' bulk stores, i.e. MN-major tiles (neuron contiguous, reduction index = row).  One stage = 64 rows of all
+// 4 planes of both operands (8 bulk copies of 8 KB).
+constexpr int TW2_STAGES = 3;
+constexpr int TW2_ROWS = 64;
+constexpr int TW2_PLANE = TW2_ROWS * 128;                        // 8 KB
+constexpr int TW2_STAGE_BYTES = 8 * TW2_PLANE;                   // Z planes 0..3 | A planes 0..3
+constexpr int TW2_SMEM = TW2_STAGES * TW2_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 1)
+tt_wgrad2_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const unsigned char* __restrict__ Aimg, int64_t ld, int splits,
+                 float ww, const float* __restrict__ seed_absmax) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TW2_STAGES * TW2_STAGE_BYTES);
+  uint64_t *full = bars, *empty = bars + TW2_STAGES, *done = bars + 2 * TW2_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TW2_STAGES + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int l = 1 + blockIdx.x / splits;
+  const int split = blockIdx.x % splits;
+  const int64_t nrb = ld / TW2_ROWS;                              // row blocks
+  const int64_t per = (nrb + splits - 1) / splits;
+  const int64_t rb0 = split * per, rb1 = min(nrb, rb0 + per);
+  if (tid == 0) {
+    for (int i = 0; i < TW2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t rb = rb0; rb < rb1; ++rb) {
+        mbar_wait(&empty[stage], phase ^ 1, 0x500 + stage);
+        mbar_arrive_expect_tx(&full[stage], TW2_STAGE_BYTES);
+        unsigned char* dst = smem + stage * TW2_STAGE_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          bulk_g2s(dst + kb * TW2_PLANE, Zimg + (((size_t)l * 4 + kb) * ld + rb * TW2_ROWS) * 128, TW2_PLANE, &full[stage]);
+          bulk_g2s(dst + (4 + kb) * TW2_PLANE, Aimg + (((size_t)(l - 1) * 4 + kb) * ld + rb * TW2_ROWS) * 128, TW2_PLANE, &full[stage]);
+        }
+        if (++stage == TW2_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, /*A MN-major*/ 1, /*B MN-major*/ 1);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t rb = rb0; rb < rb1; ++rb) {
+        mbar_wait(&full[stage], phase, 0x600 + stage);
+        tc_fence_after();
+        const uint32_t z_addr = smem_u32(smem + stage * TW2_STAGE_BYTES);
+        const uint32_t a_addr = z_addr + 4 * TW2_PLANE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int ks = 0; ks < TW2_ROWS / 16; ++ks)
+            mma_f16_ss(tmem_base + h * 256, make_desc_sw128(z_addr + 2 * h * TW2_PLANE + ks * 2048, TW2_PLANE, 1024),
+                       make_desc_sw128(a_addr + ks * 2048, TW2_PLANE, 1024), idesc, (rb > rb0) || (ks != 0));
+        mma_commit(&empty[stage]);
+        if (++stage == TW2_STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(done);
+    }
+  } else if (rb1 > rb0) {
+    mbar_wait(done, 0, 0x700);
+    tc_fence_after();
+    const float factor = ww / loss_scale_from(seed_absmax);
+    float* dst = grad.W[l];
+    for (int h = 0; h < 2; ++h) {
+      const int n = h * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 256 + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float* p = dst + (size_t)n * 256 + c0 + j;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(r[j]) * factor),
+                       "f"(__uint_as_float(r[j + 1]) * factor), "f"(__uint_as_float(r[j + 2]) * factor),
+                       "f"(__uint_as_float(r[j + 3]) * factor)
+                       : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem_base);
+}
+
 // =============================================================================================
 // launchers
 // =============================================================================================
@@ -645,12 +744,12 @@ int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, c
   if (L < 2 || ld <= 0) return 0;
   DUDF_REQUIRE(ld % 64 == 0, "tensor-core stash: ld must be a multiple of 64");
   DUDF_REQUIRE(seed_absmax != nullptr, "tensor-core weight gradient needs the seed magnitude (loss scale)");
-  const int64_t ncb = ld / 64;
+  const int64_t nrb = ld / TW2_ROWS;
   int splits = std::max(1, sms / (L - 1));
-  splits = (int)std::min<int64_t>(splits, ncb);
-  DUDF_CUDA_OK(cudaFuncSetAttribute(tt_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
-  tt_wgrad_kernel<<<(L - 1) * splits, 192, TW_SMEM, st>>>(grad, (const unsigned char*)Zimg, (const unsigned char*)Aimg, ncb, splits, net.ww,
-                                                         seed_absmax);
+  splits = (int)std::min<int64_t>(splits, nrb);
+  DUDF_CUDA_OK(cudaFuncSetAttribute(tt_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW2_SMEM));
+  tt_wgrad2_kernel<<<(L - 1) * splits, 192, TW2_SMEM, st>>>(grad, (const unsigned char*)Zimg, (const unsigned char*)Aimg, ld, splits, net.ww,
+                                                           seed_absmax);
   DUDF_LAUNCH_OK();
   return 0;
 }

@@ -61,9 +61,9 @@ class TrainCore:
 
     def _stashes(self, L, ld, prec):
         Z = self._buf("Z", (L, 256, ld))
-        if prec == "tc16":       # fp16 operand images [layer][ld/64][256][64]; zero tails are part of the contract
-            A = self._buf("A", (L, ld // 64, 256, 64), torch.float16, zero=True)
-            Zb = self._buf("Zb", (L, ld // 64, 256, 64), torch.float16, zero=True)
+        if prec == "tc16":       # fp16 operand planes [layer][k-block][column][64 neurons]; zero tails are part of the contract
+            A = self._buf("A", (L, 4, ld, 64), torch.float16, zero=True)
+            Zb = self._buf("Zb", (L, 4, ld, 64), torch.float16, zero=True)
         else:
             A = self._buf("A", (L, 256, ld))
             Zb = self._buf("Zb", (L, 256, ld))

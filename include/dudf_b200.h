@@ -104,8 +104,9 @@ int dudf_jet_backward(dudf_ctx* ctx, const float* x, int64_t P, int order, const
                       int precision, void* stream);
 int dudf_jet_wgrad(dudf_ctx* ctx, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax,
                    float* const* gW_host, int precision, void* stream);
-/* With DUDF_PRECISION_TC16 the stashes change type: Z stays fp32 [n_hidden][256][ld] (ld a multiple of 64), A and Zb are
- * fp16 images [n_hidden][ld/64][256][64] (128-byte swizzled, zero-initialised by the caller), and the reverse sweep runs
+/* With DUDF_PRECISION_TC16 the stashes change type: Z is fp32 [n_hidden][ld][256] (column-group / thread-major, private
+ * to the kernel pair; ld a multiple of 64), A and Zb are fp16 operand planes [n_hidden][4 k-blocks][ld][64 neurons]
+ * (128-byte swizzled rows, zero-initialised by the caller), and the reverse sweep runs
  * under a power-of-two loss scale derived from seed_absmax (1 device float, zeroed by the caller before the dudf_loss
  * calls of a step, which raise it with atomicMax; all dudf_loss calls of a step must precede its first backward). */
 /* Loss epilogue over P rows.  w_host: 4 host floats (loss weights); P_global: divisor of the means (sum of rows over
