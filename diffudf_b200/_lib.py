@@ -15,7 +15,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
 SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_misc.cu"]
-HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", os.path.join(ROOT, "include", "dudf_b200.h")]
+HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh",
+           os.path.join(ROOT, "include", "dudf_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

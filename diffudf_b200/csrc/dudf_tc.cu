@@ -1,52 +1,33 @@
-// Tensor-core ("TC16") path: the fused SIREN chain on tcgen05.mma with TMEM accumulators.
+// Tensor-core ("TC16") field queries: the fused SIREN chain on tcgen05.mma with TMEM accumulators.
 //
 // Orientation.  For every hidden layer the kernel computes  D[neuron][column] = (w W)[neuron][k] * A[k][column]
-// where a column is one jet channel of one point.  The weights are the UMMA "A" operand (M = 128
-// neurons per instruction, two halves per layer), the activations the "B" operand (N = columns of
-// a sub-tile), both K-major fp16 in shared memory with 128-byte swizzle.  The accumulator lives
-// in TMEM with lane = neuron, so one epilogue thread owns ALL channels of ALL points of its neuron
-// and the sine-jet (which mixes the channels of a point) is thread-local.  The epilogue writes the
-// next layer's B operand straight back into shared memory: activations never leave the SM.
+// where a column is one jet channel of one point.  The weights are the UMMA "A" operand (K-major, M = 128
+// neurons per instruction, two halves per layer), the activations the "B" operand, stored MN-major
+// (column-contiguous rows of one input neuron each) in 128-byte-swizzled shared memory.  The accumulator
+// lives in TMEM with lane = neuron, so one epilogue thread owns ALL channels of ALL points of its neuron:
+// the sine-jet (which mixes the channels of a point) is thread-local, and the thread writes its row of the
+// next layer's B operand with 16-byte stores of eight packed halves.  Activations never leave the SM.
+//
+// A sub-tile is 128 columns: 128 points (value only), 32 points x 4 channels, or 12 points x 10 channels
+// (+ 8 idle columns).  Second-order channels are carried scaled by KAPPA = 1/8 (fp16 range head-room).
 //
 // Pipeline per CTA (persistent, one CTA per SM, 320 threads):
 //   warps 0-7  epilogue: TMEM -> registers -> sin/cos jet -> fp16 -> swizzled smem (+ first and last layer)
 //   warp  8    producer: streams 16 KB weight chunks (128 neurons x 64 k) global/L2 -> smem ring with
 //              cp.async.bulk (TMA engine) completing on mbarriers
-//   warp  9    MMA issuer: one thread issues tcgen05.mma, tcgen05.commit frees ring slots / publishes accumulators
-// Two sub-tiles of points are in flight so that the MMAs of one overlap the epilogue of the other.
+//   warp  9    MMA issuer: one thread issues tcgen05.mma; tcgen05.commit frees ring slots / publishes accumulators
+// Two sub-tiles are in flight so that the MMAs of one overlap the epilogue of the other.
 #include <cuda_fp16.h>
 #include <vector>
 #include "dudf_common.cuh"
 #include "dudf_kernels.h"
 #include "dudf_device.cuh"
 #include "dudf_umma.cuh"
+#include "dudf_tc_common.cuh"
 
 namespace dudf {
 
 using namespace umma;
-
-constexpr int TC_CHUNK_BYTES = 128 * 64 * 2;   // one weight chunk: 128 neurons x 64 k, fp16
-constexpr int TC_STAGES = 5;
-constexpr int TC_EPI_THREADS = 256;
-constexpr int TC_THREADS = 320;
-
-template <int NCH>
-struct TcCfg {
-  static constexpr int PT = (NCH == 1) ? 128 : (NCH == 4 ? 32 : 8);   // points per sub-tile
-  static constexpr int N = PT * NCH;                                  // columns per sub-tile (UMMA N)
-  static constexpr int GC = (NCH == 10) ? 40 : 32;                    // columns handled per epilogue step
-  static constexpr int KB_BYTES = N * 128;                            // one 64-wide k block of the activation tile
-  static constexpr int ACT_BYTES = 4 * KB_BYTES;
-  static constexpr int OFF_ACT = 0;
-  static constexpr int OFF_RING = 2 * ACT_BYTES;
-  static constexpr int OFF_MISC = OFF_RING + TC_STAGES * TC_CHUNK_BYTES;
-  // misc: wl[256] f32 | xs[2][PT*3] f32 | os[2][N] f32 | barriers
-  static constexpr int OFF_WL = OFF_MISC;
-  static constexpr int OFF_XS = OFF_WL + 256 * 4;
-  static constexpr int OFF_OS = OFF_XS + 2 * PT * 3 * 4;
-  static constexpr int OFF_BAR = (OFF_OS + 2 * N * 4 + 15) / 16 * 16;
-  static constexpr int SMEM = OFF_BAR + 256 + 1024;                   // + alignment slack
-};
 
 size_t tc_packed_bytes(int n_lin) { return (size_t)((n_lin > 2) ? (n_lin - 2) : 1) * 2 * 8 * TC_CHUNK_BYTES; }
 
@@ -76,37 +57,6 @@ int tc_pack(const NetView& net, void* packed, cudaStream_t st) {
   return 0;
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ void st_half(unsigned char* p, float v) { *reinterpret_cast<__half*>(p) = __float2half_rn(v); }
-
-// sine-jet of one point given the accumulator values (already multiplied by omega): writes NCH halves
-// into rows row0.. of the activation tile (k position fixed per thread).  sw[j] = (chunk ^ j) << 4.
-template <int NCH>
-__device__ __forceinline__ void emit_point(const float* u, unsigned char* base, int row0_mod8_is_const, const uint32_t* sw,
-                                           int row0) {
-  float s, c;
-  sincos_fast(u[0], s, c);
-  float a[NCH];
-  a[0] = s;
-  if constexpr (NCH >= 4) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) a[1 + i] = c * u[1 + i];
-  }
-  if constexpr (NCH >= 10) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = i; j < 3; ++j) a[4 + sym2(i, j)] = fmaf(c, u[4 + sym2(i, j)], -s * u[1 + i] * u[1 + j]);
-  }
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    const int row = row0 + ch;
-    st_half(base + row * 128 + sw[row & 7], a[ch]);
-  }
-  (void)row0_mod8_is_const;
-}
-
 template <int NCH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, int gridN,
@@ -114,16 +64,13 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   using C = TcCfg<NCH>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* act = smem + C::OFF_ACT;
+  unsigned char* act = smem;
   unsigned char* ring = smem + C::OFF_RING;
   float* wl_s = (float*)(smem + C::OFF_WL);
   float* xs = (float*)(smem + C::OFF_XS);
   float* os = (float*)(smem + C::OFF_OS);
   uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
-  uint64_t* full = bars;                  // [STAGES]
-  uint64_t* empty = bars + TC_STAGES;     // [STAGES]
-  uint64_t* act_ready = bars + 2 * TC_STAGES;      // [2]
-  uint64_t* acc_ready = bars + 2 * TC_STAGES + 2;  // [2]
+  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,85 +84,34 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
   if (tid < 256) wl_s[tid] = net.W[L][tid];
+  if (C::NV < 128 && tid < 256) {         // idle columns of both tiles stay zero for the whole kernel
+    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(act + s * TC_ACT_BYTES, tid) + tc_chunk_off(15, tid & 7)) = make_uint4(0, 0, 0, 0);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    // ===================== producer: weight chunks through the ring =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        for (int l = 1; l < L; ++l) {
-          const unsigned char* src = packed + (size_t)(l - 1) * 8 * TC_CHUNK_BYTES;
-          for (int s = 0; s < 2; ++s) {
-            for (int ck = 0; ck < 8; ++ck) {
-              mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
-              mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
-              bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            }
-          }
-        }
-      }
-    }
+    if (lane == 0) tc_producer(packed, ring, full, empty, npairs, L - 1, false);
   } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, C::N, /*fp16*/ 0, 0, 0);
-      uint32_t stage = 0, phase = 0;
-      uint32_t act_phase[2] = {0, 0};
-      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        for (int l = 1; l < L; ++l) {
-          for (int s = 0; s < 2; ++s) {
-            mbar_wait(&act_ready[s], act_phase[s], 0x200 + s);
-            act_phase[s] ^= 1;
-            tc_fence_after();
-            const uint32_t act_s = smem_u32(act + s * C::ACT_BYTES);
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
-              for (int kb = 0; kb < 4; ++kb) {
-                mbar_wait(&full[stage], phase, 0x300 + stage);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(ring + stage * TC_CHUNK_BYTES);
-                const uint32_t b_addr = act_s + kb * C::KB_BYTES;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  const uint64_t ad = make_desc_sw128(a_addr + k4 * 32, 16, 1024);
-                  const uint64_t bd = make_desc_sw128(b_addr + k4 * 32, 16, 1024);
-                  mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k4) != 0);
-                }
-                mma_commit(&empty[stage]);
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-              }
-            }
-            mma_commit(&acc_ready[s]);
-          }
-        }
-      }
-    }
+    if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, nullptr, 0, 0, false);
   } else {
     // ===================== epilogue warps (256 threads) =====================
     const int q = warp & 3, h = warp >> 2;
-    const int n = h * 128 + q * 32 + lane;                  // this thread's neuron
-    const uint32_t chunk = (n & 63) >> 3;
-    uint32_t sw[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sw[j] = ((chunk ^ j) << 4);
-    const uint32_t tile_off = (n >> 6) * C::KB_BYTES + (n & 7) * 2;
+    const int n = h * 128 + q * 32 + lane;                  // this thread's neuron = its row of the B operand
+    const uint32_t r7 = n & 7;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
     const float w0 = net.w0, ww = net.ww;
-    const float w0x = w0 * net.W[0][n * 3], w0y = w0 * net.W[0][n * 3 + 1], w0z = w0 * net.W[0][n * 3 + 2];
-    const float b0 = net.b[0][n];
+    const float r0x = net.W[0][n * 3], r0y = net.W[0][n * 3 + 1], r0z = net.W[0][n * 3 + 2], b0 = net.b[0][n];
     const float bL = net.b[L][0];
     const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase = 0;                                 // bit s = parity of acc_ready[s]
 
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       // ---- coordinates of both sub-tiles ----
-      epi_bar_sync();
-      for (int i = tid; i < 2 * C::PT; i += TC_EPI_THREADS) {
+      tc_epi_bar();
+      for (int i = tid; i < 2 * C::PT; i += 256) {
         const int64_t p = pair * 2 * C::PT + i;
         float pt[3] = {0.f, 0.f, 0.f};
         if (p < P) {
@@ -224,47 +120,33 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
         }
         xs[i * 3] = pt[0]; xs[i * 3 + 1] = pt[1]; xs[i * 3 + 2] = pt[2];
       }
-      epi_bar_sync();
+      tc_epi_bar();
 
       for (int l = 0; l < L; ++l) {
         const float bias = (l > 0) ? ww * net.b[l][n] : 0.f;
         for (int s = 0; s < 2; ++s) {
-          unsigned char* tile = act + s * C::ACT_BYTES + tile_off;
+          unsigned char* trow = tc_tile_row(act + s * TC_ACT_BYTES, n);
+          if (l > 0) {
+            mbar_wait(&acc_ready[s], (acc_phase >> s) & 1u, 0x400 + s);
+            acc_phase ^= 1u << s;
+            tc_fence_after();
+          }
           if (l == 0) {
-            // first layer in fp32 on CUDA cores: u = w0 (W0 x + b0); derivative channels are w0 W0[:, i]
+            // first layer in fp32 on CUDA cores: u0 = w0 (W0 x + b0); derivative channels are w0 W0[:, i]
 #pragma unroll 1
-            for (int g = 0; g < C::N / C::GC; ++g) {
-#pragma unroll
-              for (int pp = 0; pp < C::GC / NCH; ++pp) {
-                const int pl = g * (C::GC / NCH) + pp;
-                const float* pt = xs + (s * C::PT + pl) * 3;
-                float u[NCH];
-                u[0] = w0 * fmaf(net.W[0][n * 3 + 2], pt[2], fmaf(net.W[0][n * 3 + 1], pt[1], fmaf(net.W[0][n * 3], pt[0], b0)));
-                if constexpr (NCH >= 4) { u[1] = w0x; u[2] = w0y; u[3] = w0z; }
-#pragma unroll
-                for (int ch = 4; ch < NCH; ++ch) u[ch] = 0.f;
-                emit_point<NCH>(u, tile + g * C::GC * 128, 0, sw, pp * NCH);
-              }
+            for (int g = 0; g < C::NGRP; ++g) {
+              float u[C::GC];
+              tc_first_layer_group<NCH, C::GC>(u, xs + (s * C::PT + g * (C::GC / NCH)) * 3, w0, r0x, r0y, r0z, b0);
+              tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
             }
           } else {
-            mbar_wait(&acc_ready[s], acc_phase[s], 0x400 + s);
-            acc_phase[s] ^= 1;
-            tc_fence_after();
 #pragma unroll 1
-            for (int g = 0; g < C::N / C::GC; ++g) {
-              uint32_t r[C::GC];
-              const uint32_t taddr = tmem_lane + s * 256 + g * C::GC;
-              tmem_ld_x32(taddr, r);
-              if constexpr (C::GC == 40) tmem_ld_x8(taddr + 32, r + 32);
-              tmem_ld_wait();
+            for (int g = 0; g < C::NGRP; ++g) {
+              float u[C::GC];
+              tc_load_group<C::GC>(tmem_lane + s * 256 + g * C::GC, u);
 #pragma unroll
-              for (int pp = 0; pp < C::GC / NCH; ++pp) {
-                float u[NCH];
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) u[ch] = __uint_as_float(r[pp * NCH + ch]);
-                u[0] += bias;
-                emit_point<NCH>(u, tile + g * C::GC * 128, 0, sw, pp * NCH);
-              }
+              for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
+              tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
             }
           }
           if (l < L - 1) {
@@ -275,31 +157,18 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
             if (lane == 0) mbar_arrive(&act_ready[s]);
           } else {
             // ---- output layer (256 -> 1 per channel) from the fp16 tile, then per-point finalisation ----
-            epi_bar_sync();
-            if (tid < C::N) {
-              const unsigned char* rowp = act + s * C::ACT_BYTES + tid * 128;
-              float sum = 0.f;
-#pragma unroll
-              for (int kb = 0; kb < 4; ++kb) {
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                  const uint4 v = *reinterpret_cast<const uint4*>(rowp + kb * C::KB_BYTES + ((c8 ^ (tid & 7)) << 4));
-                  const __half2* hv = reinterpret_cast<const __half2*>(&v);
-                  const float* wv = wl_s + kb * 64 + c8 * 8;
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f2 = __half22float2(hv[e]);
-                    sum = fmaf(wv[2 * e], f2.x, sum);
-                    sum = fmaf(wv[2 * e + 1], f2.y, sum);
-                  }
-                }
-              }
-              os[s * C::N + tid] = sum + ((tid % NCH == 0) ? bL : 0.f);
+            tc_epi_bar();
+            tc_output_dot<C::NV>(act + s * TC_ACT_BYTES, wl_s, os + s * 256, tid);
+            tc_epi_bar();
+            if (tid < C::NV) {
+              const int ch = tid % NCH;
+              const float v = os[s * 256 + tid] + os[s * 256 + 128 + tid];
+              os[s * 256 + tid] = (ch == 0) ? v + bL : (ch >= 4 ? v * TC_KAPPA_INV : v);
             }
-            epi_bar_sync();
+            tc_epi_bar();
             if (tid < C::PT) {
               const int64_t p = (pair * 2 + s) * C::PT + tid;
-              if (p < P) finalize_point<NCH>(out, p, os + s * C::N + tid * NCH);
+              if (p < P) finalize_point<NCH>(out, p, os + s * 256 + tid * NCH);
             }
           }
         }

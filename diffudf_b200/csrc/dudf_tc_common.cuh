@@ -1,0 +1,251 @@
+// Building blocks shared by the tcgen05 kernels (field queries, training forward, reverse sweep).
+//
+// Stored variables of a sine layer (w = omega of the layer):  u0 = w z0 (bias included), u_i = w z_i,
+// v_ij = KAPPA w z_ij;   activations  a0 = sin u0, a_i = cos(u0) u_i, b_ij = cos(u0) v_ij - KAPPA sin(u0) u_i u_j.
+// With the weights packed as fp16(w W) the MMA maps stored activations to stored pre-activations directly.
+//
+// Shared-memory B-operand tile (one sub-tile, 128 columns x 256 input neurons, fp16, 64 KB), MN-major:
+// 8-row x 128-byte swizzle atoms, atom(nb = column/64, kg = k/8) at (nb*32 + kg) KB, inside an atom row k%8 holds
+// 64 consecutive columns with its 16-byte chunks XOR-swizzled by k%8.  Seen from the weight-gradient GEMM
+// (reduction over columns) each 32 KB half nb is a K-major [256 neurons][64 columns] operand image.
+#pragma once
+#include <cuda_fp16.h>
+#include "dudf_common.cuh"
+#include "dudf_umma.cuh"
+
+namespace dudf {
+
+constexpr int TC_CHUNK_BYTES = 128 * 64 * 2;   // one weight chunk: 128 neurons x 64 k, fp16
+constexpr int TC_STAGES = 5;
+constexpr int TC_THREADS = 320;
+constexpr int TC_ACT_BYTES = 65536;
+constexpr int TC_IMG_BYTES = 32768;            // [256][64] fp16 operand image
+constexpr float TC_KAPPA = 0.125f;
+constexpr float TC_KAPPA_INV = 8.0f;
+
+template <int NCH>
+struct TcCfg {
+  static constexpr int PT = (NCH == 1) ? 128 : (NCH == 4 ? 32 : 12);   // points per sub-tile
+  static constexpr int NV = PT * NCH;                                  // columns in use (128, 128, 120)
+  static constexpr int GC = (NCH == 10) ? 40 : 32;                     // columns per epilogue step
+  static constexpr int NGRP = NV / GC;
+  static constexpr int OFF_RING = 2 * TC_ACT_BYTES;
+  static constexpr int OFF_WL = OFF_RING + TC_STAGES * TC_CHUNK_BYTES;
+  static constexpr int OFF_XS = OFF_WL + 256 * 4;
+  static constexpr int OFF_OS = OFF_XS + 2 * PT * 3 * 4;               // [2][256] floats: outputs / seeds
+  static constexpr int OFF_BAR = (OFF_OS + 2 * 256 * 4 + 15) / 16 * 16;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
+};
+
+__device__ __forceinline__ void tc_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tc_pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ unsigned char* tc_tile_row(unsigned char* tile, int k) { return tile + (k >> 3) * 1024 + (k & 7) * 128; }
+// byte offset (relative to the row) of column chunk c (8 columns each, c = 0..15)
+__device__ __forceinline__ uint32_t tc_chunk_off(int c, uint32_t r7) { return (uint32_t)(c >> 3) * 32768u + ((((uint32_t)c & 7u) ^ r7) << 4); }
+
+__device__ __forceinline__ float loss_scale_from(const float* seed_absmax) {
+  const float m = seed_absmax ? *seed_absmax : 0.f;
+  return (m > 0.f && isfinite(m)) ? exp2f(floorf(log2f(2048.f / m))) : 1.f;
+}
+
+// bulk copy shared -> global (TMA engine), grouped completion
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(umma::smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- producer: weight chunks through the ring.  Phase j of a pair uses image j (forward) or the transposed
+// ---- image of layer n_phase-j (reverse sweep); both sub-tiles re-stream the 8 chunks of the layer.
+__device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t npairs,
+                                            int n_phase, bool backward) {
+  using namespace umma;
+  uint32_t stage = 0, phase = 0;
+  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+    for (int j = 0; j < n_phase; ++j) {
+      const int idx = backward ? (n_phase + (n_phase - 1 - j)) : j;
+      const unsigned char* src = packed + (size_t)idx * 8 * TC_CHUNK_BYTES;
+      for (int s = 0; s < 2; ++s)
+        for (int ck = 0; ck < 8; ++ck) {
+          mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
+          mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
+          bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
+// ---- MMA issuer (one thread).  img != null: after issuing the MMAs of a sub-tile, bulk-copy its B tile (two
+// ---- 32 KB operand images) to img[layer][cb0 + 2*subtile + nb] for the weight-gradient GEMM.
+__device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                            uint64_t* acc_ready, uint32_t tmem_base, int64_t npairs, int n_phase, unsigned char* img,
+                                            int64_t ncb, int64_t cb0, bool backward) {
+  using namespace umma;
+  constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
+  uint32_t stage = 0, phase = 0;
+  uint32_t act_phase = 0;                                   // bit s = parity of act_ready[s]
+  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+    for (int j = 0; j < n_phase; ++j)
+      for (int s = 0; s < 2; ++s) {
+        mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
+        act_phase ^= 1u << s;
+        tc_fence_after();
+        const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&full[stage], phase, 0x300 + stage);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + stage * TC_CHUNK_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              mma_f16_ss(d_tmem, make_desc_sw128(a_addr + k4 * 32, 16, 1024), make_desc_sw128(act_s + (kb * 8 + k4 * 2) * 1024, 32768, 1024),
+                         idesc, (kb | k4) != 0);
+            mma_commit(&empty[stage]);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (img) {
+          const int layer = backward ? (n_phase - j) : j;
+          const int64_t cb = cb0 + (pair * 2 + s) * 2;
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+            bulk_s2g(img + ((size_t)layer * ncb + cb + nb) * TC_IMG_BYTES, act + s * TC_ACT_BYTES + nb * TC_IMG_BYTES, TC_IMG_BYTES);
+          bulk_commit();
+          bulk_wait_read0();          // the tile may be overwritten once acc_ready is published
+        }
+        mma_commit(&acc_ready[s]);
+      }
+}
+
+template <int GC>
+__device__ __forceinline__ void tc_load_group(uint32_t taddr, float* u) {
+  uint32_t r[32];
+  umma::tmem_ld_x32(taddr, r);
+  if constexpr (GC == 40) {
+    uint32_t r2[8];
+    umma::tmem_ld_x8(taddr + 32, r2);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[32 + j] = __uint_as_float(r2[j]);
+  } else {
+    umma::tmem_ld_wait();
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(r[j]);
+}
+
+// stored pre-activations u -> stored activations, in place
+template <int NCH>
+__device__ __forceinline__ void tc_act_point(float* u, float s, float c) {
+  // written out channel by channel (xx,xy,xz,yy,yz,zz = 4..9): loops over symmetric index pairs keep the
+  // array in local memory (nvcc 12.9 does not scalarise them)
+  if constexpr (NCH >= 10) {
+    const float ks = TC_KAPPA * s;
+    const float kx = ks * u[1], ky = ks * u[2], kz = ks * u[3];
+    u[4] = fmaf(c, u[4], -kx * u[1]);
+    u[5] = fmaf(c, u[5], -kx * u[2]);
+    u[6] = fmaf(c, u[6], -kx * u[3]);
+    u[7] = fmaf(c, u[7], -ky * u[2]);
+    u[8] = fmaf(c, u[8], -ky * u[3]);
+    u[9] = fmaf(c, u[9], -kz * u[3]);
+  }
+  if constexpr (NCH >= 4) {
+    u[1] = c * u[1];
+    u[2] = c * u[2];
+    u[3] = c * u[3];
+  }
+  u[0] = s;
+}
+
+// stored pre-activations of the first layer for GC/NCH consecutive points (pts: xyz triples)
+template <int NCH, int GC>
+__device__ __forceinline__ void tc_first_layer_group(float* u, const float* pts, float w0, float r0x, float r0y, float r0z, float b0) {
+#pragma unroll
+  for (int pp = 0; pp < GC / NCH; ++pp) {
+    const float* pt = pts + pp * 3;
+    float* up = u + pp * NCH;
+    up[0] = w0 * fmaf(r0z, pt[2], fmaf(r0y, pt[1], fmaf(r0x, pt[0], b0)));
+    if constexpr (NCH >= 4) { up[1] = w0 * r0x; up[2] = w0 * r0y; up[3] = w0 * r0z; }
+#pragma unroll
+    for (int ch = 4; ch < NCH; ++ch) up[ch] = 0.f;
+  }
+}
+
+// pack GC fp32 values of one thread into halves and store them as GC/8 16-byte chunks of its tile row
+template <int GC>
+__device__ __forceinline__ void tc_store_group(const float* v, unsigned char* trow, int chunk0, uint32_t r7) {
+#pragma unroll
+  for (int c8 = 0; c8 < GC / 8; ++c8)
+    *reinterpret_cast<uint4*>(trow + tc_chunk_off(chunk0 + c8, r7)) =
+        make_uint4(tc_pack_h2(v[8 * c8], v[8 * c8 + 1]), tc_pack_h2(v[8 * c8 + 2], v[8 * c8 + 3]), tc_pack_h2(v[8 * c8 + 4], v[8 * c8 + 5]),
+                   tc_pack_h2(v[8 * c8 + 6], v[8 * c8 + 7]));
+}
+
+// sine-jet of GC/NCH points (in place) and store into the B-operand tile.  PRECISE: explicit 2*pi reduction
+// (first layer, arguments up to ~50 rad); otherwise MUFU on the raw argument (hidden layers, |u| of a few rad).
+template <int NCH, int GC, bool PRECISE>
+__device__ __forceinline__ void tc_emit_group(float* u, unsigned char* trow, int chunk0, uint32_t r7) {
+#pragma unroll
+  for (int pp = 0; pp < GC / NCH; ++pp) {
+    float sn, cs;
+    if constexpr (PRECISE) sincos_fast(u[pp * NCH], sn, cs);
+    else { sn = __sinf(u[pp * NCH]); cs = __cosf(u[pp * NCH]); }
+    tc_act_point<NCH>(u + pp * NCH, sn, cs);
+  }
+  tc_store_group<GC>(u, trow, chunk0, r7);
+}
+
+// adjoint of the above: ab = dL/d(stored activations) -> ub = dL/d(stored pre-activations)
+template <int NCH>
+__device__ __forceinline__ void tc_adj_point(const float* u, const float* ab, float* ub, float s, float c) {
+  float u0 = c * ab[0];
+  if constexpr (NCH >= 4) {
+    const float ux = u[1], uy = u[2], uz = u[3];
+    float bx = c * ab[1], by = c * ab[2], bz = c * ab[3];
+    u0 = fmaf(-s, fmaf(ab[1], ux, fmaf(ab[2], uy, ab[3] * uz)), u0);
+    if constexpr (NCH >= 10) {
+      const float ks = TC_KAPPA * s, kc = TC_KAPPA * c;
+      const float axx = ab[4], axy = ab[5], axz = ab[6], ayy = ab[7], ayz = ab[8], azz = ab[9];
+      float acc2 = axx * fmaf(s, u[4], kc * ux * ux);
+      acc2 = fmaf(axy, fmaf(s, u[5], kc * ux * uy), acc2);
+      acc2 = fmaf(axz, fmaf(s, u[6], kc * ux * uz), acc2);
+      acc2 = fmaf(ayy, fmaf(s, u[7], kc * uy * uy), acc2);
+      acc2 = fmaf(ayz, fmaf(s, u[8], kc * uy * uz), acc2);
+      acc2 = fmaf(azz, fmaf(s, u[9], kc * uz * uz), acc2);
+      u0 -= acc2;
+      bx -= ks * fmaf(2.f * axx, ux, fmaf(axy, uy, axz * uz));
+      by -= ks * fmaf(axy, ux, fmaf(2.f * ayy, uy, ayz * uz));
+      bz -= ks * fmaf(axz, ux, fmaf(ayz, uy, 2.f * azz * uz));
+      ub[4] = c * axx; ub[5] = c * axy; ub[6] = c * axz; ub[7] = c * ayy; ub[8] = c * ayz; ub[9] = c * azz;
+    }
+    ub[1] = bx; ub[2] = by; ub[3] = bz;
+  }
+  ub[0] = u0;
+}
+
+// output layer: os[half*128 + j] = sum_{k in half} wl[k] * tile[k][j]  (256 threads, 2 per column)
+template <int NV>
+__device__ __forceinline__ void tc_output_dot(const unsigned char* tile, const float* wl_s, float* os, int tid) {
+  const int j = tid & 127, half = tid >> 7;
+  if (j < NV) {
+    const uint32_t cj = (uint32_t)(j & 63) >> 3;
+    const unsigned char* base = tile + (j >> 6) * 32768 + (j & 7) * 2 + half * 16 * 1024;
+    float sum = 0.f;
+#pragma unroll 4
+    for (int kg = 0; kg < 16; ++kg) {
+#pragma unroll
+      for (uint32_t r = 0; r < 8; ++r) {
+        const __half hv = *reinterpret_cast<const __half*>(base + kg * 1024 + r * 128 + ((cj ^ r) << 4));
+        sum = fmaf(wl_s[half * 128 + kg * 8 + r], __half2float(hv), sum);
+      }
+    }
+    os[half * 128 + j] = sum;
+  }
+}
+
+}  // namespace dudf
