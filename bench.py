@@ -207,7 +207,7 @@ def run_ours(args, rank, local_rank, world):
     prof = {}
     if rank == 0:
         eng = model._engine_synced()
-        names = ["jet_forward", "loss", "jet_backward", "jet_wgrad"]
+        names = ["jet_forward_multi", "loss", "jet_backward_multi", "jet_wgrad"]
         orig = {k: getattr(eng, k) for k in names}
         events = []
 
@@ -217,10 +217,7 @@ def run_ours(args, rank, local_rank, world):
                 s.record()
                 r = fn(*a, **kw)
                 t.record()
-                tag = name
-                if name in ("jet_forward", "jet_backward"):
-                    tag = f"{name}[order{a[1]}]"
-                events.append((tag, s, t))
+                events.append((name, s, t))
                 return r
             return inner
         for k in names:
@@ -262,9 +259,8 @@ def run_ours(args, rank, local_rank, world):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
-    flops = {"jet_forward[order2]": n_on * F[10], "jet_forward[order1]": (P - n_on) * F[4],
-             "jet_backward[order2]": n_on * F[10], "jet_backward[order1]": (P - n_on) * F[4],
-             "jet_wgrad": n_on * F[10] + (P - n_on) * F[4]}
+    third = n_on * F[10] + (P - n_on) * F[4]        # forward = reverse sweep = weight gradient in algorithmic FLOPs
+    flops = {"jet_forward_multi": third, "jet_backward_multi": third, "jet_wgrad": third}
     dom = max((k for k in prof if k in flops), key=lambda k: prof[k]) if prof else None
     roof = None
     if dom:

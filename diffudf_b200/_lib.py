@@ -25,8 +25,16 @@ _lib = None
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
+class Segment(ctypes.Structure):
+    """struct dudf_segment of include/dudf_b200.h"""
+    _fields_ = [("x", c_void_p), ("rows", c_int64), ("order", c_int), ("packed", c_void_p), ("seeds", c_void_p), ("col0", c_int64)]
+
+
 # name -> (argtypes) ; every function returns int except the two noted below
 SIGNATURES = {
+    "dudf_jet_forward_multi": [c_void_p, ctypes.POINTER(Segment), c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "dudf_jet_backward_multi": [c_void_p, ctypes.POINTER(Segment), c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                                ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_void_p],
     "dudf_version": [],
     "dudf_launch_count": [],
     "dudf_create": [c_int, c_float, c_float, ctypes.POINTER(c_void_p)],

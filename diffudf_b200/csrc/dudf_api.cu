@@ -255,34 +255,78 @@ static int fill_grad_view(dudf_ctx* c, float* const* gW, float* const* gb, GradV
   return 0;
 }
 
+// validates a segment list and, for the tensor-core path, that the segments occupy consecutive stash columns
+static int check_segments(const dudf_segment* segs, int nseg, int64_t ld, int precision, bool forward, const char* who) {
+  DUDF_REQUIRE(segs && nseg >= 1 && nseg <= 2, "%s: 1 or 2 segments", who);
+  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "%s: unknown precision %d", who, precision);
+  int64_t next = -1;
+  for (int i = 0; i < nseg; ++i) {
+    const dudf_segment& s = segs[i];
+    DUDF_REQUIRE(s.order >= 0 && s.order <= 2, "%s: order %d (0..2)", who, s.order);
+    DUDF_REQUIRE(s.rows > 0 && s.x && (forward ? (s.packed != nullptr) : (s.seeds != nullptr)), "%s: empty or null segment", who);
+    const int64_t cols = dudf_stash_columns(s.order, s.rows, precision);
+    DUDF_REQUIRE(s.col0 % 4 == 0 && s.col0 + cols <= ld, "%s: stash too small", who);
+    if (precision == DUDF_PRECISION_TC16 && i > 0)
+      DUDF_REQUIRE(s.col0 == next && segs[0].order == 2, "%s: tensor-core segments must be contiguous, Hessian segment first", who);
+    next = s.col0 + cols;
+  }
+  return 0;
+}
+
+int dudf_jet_forward_multi(dudf_ctx* c, const dudf_segment* segs, int nseg, void* Z, void* A, int64_t ld, int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_jet_forward: weights not set");
+  DUDF_REQUIRE(Z && A && ld % 4 == 0, "dudf_jet_forward: null or misaligned stash");
+  int rc = check_segments(segs, nseg, ld, precision, true, "dudf_jet_forward");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DUDF_PRECISION_TC16) {
+    TcSegment ts[2];
+    for (int i = 0; i < nseg; ++i) ts[i] = TcSegment{segs[i].x, segs[i].rows, order_to_nch(segs[i].order), segs[i].packed, nullptr};
+    return tc_train_forward(c->tc_packed, c->view(), ts, nseg, (float*)Z, A, ld, segs[0].col0, c->sms, st);
+  }
+  for (int i = 0; i < nseg; ++i) {
+    QueryOut o{nullptr, nullptr, nullptr, nullptr, segs[i].packed, 0, 0.f};
+    rc = simt_forward(c->view(), order_to_nch(segs[i].order), segs[i].x, segs[i].rows, 0, 0, o, (float*)Z, (float*)A, ld, segs[i].col0, c->sms, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int dudf_jet_backward_multi(dudf_ctx* c, const dudf_segment* segs, int nseg, const float* seed_absmax, const void* Z, void* Zb, int64_t ld,
+                            float* const* gW, float* const* gb, int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_jet_backward: weights not set");
+  DUDF_REQUIRE(Z && Zb && gW && gb, "dudf_jet_backward: null argument");
+  int rc = check_segments(segs, nseg, ld, precision, false, "dudf_jet_backward");
+  if (rc) return rc;
+  GradView gv;
+  rc = fill_grad_view(c, gW, gb, gv, "dudf_jet_backward");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DUDF_PRECISION_TC16) {
+    TcSegment ts[2];
+    for (int i = 0; i < nseg; ++i) ts[i] = TcSegment{segs[i].x, segs[i].rows, order_to_nch(segs[i].order), nullptr, segs[i].seeds};
+    return tc_train_backward(c->tc_packed, c->view(), gv, ts, nseg, seed_absmax, (const float*)Z, Zb, ld, segs[0].col0, c->sms, st);
+  }
+  for (int i = 0; i < nseg; ++i) {
+    rc = simt_backward(c->view(), gv, order_to_nch(segs[i].order), segs[i].x, segs[i].rows, segs[i].seeds, (const float*)Z, (float*)Zb, ld,
+                       segs[i].col0, c->sms, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int dudf_jet_forward(dudf_ctx* c, const float* x, int64_t P, int order, float* packed, void* Z, void* A, int64_t ld,
                      int64_t col0, int precision, void* stream) {
-  DUDF_REQUIRE(c && c->weights_set, "dudf_jet_forward: weights not set");
-  DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_jet_forward: order %d (0..2)", order);
-  DUDF_REQUIRE(x && packed && Z && A, "dudf_jet_forward: null argument");
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "dudf_jet_forward: unknown precision %d", precision);
   if (P <= 0) return 0;
-  DUDF_REQUIRE(ld % 4 == 0 && col0 % 4 == 0 && col0 + dudf_stash_columns(order, P, precision) <= ld, "dudf_jet_forward: stash too small");
-  if (precision == DUDF_PRECISION_TC16)
-    return tc_train_forward(c->tc_packed, c->view(), order_to_nch(order), x, P, packed, (float*)Z, A, ld, col0, c->sms, (cudaStream_t)stream);
-  QueryOut o{nullptr, nullptr, nullptr, nullptr, packed, 0, 0.f};
-  return simt_forward(c->view(), order_to_nch(order), x, P, 0, 0, o, (float*)Z, (float*)A, ld, col0, c->sms, (cudaStream_t)stream);
+  dudf_segment s{x, P, order, packed, nullptr, col0};
+  return dudf_jet_forward_multi(c, &s, 1, Z, A, ld, precision, stream);
 }
 
 int dudf_jet_backward(dudf_ctx* c, const float* x, int64_t P, int order, const float* seeds, const float* seed_absmax, const void* Z,
                       void* Zb, int64_t ld, int64_t col0, float* const* gW, float* const* gb, int precision, void* stream) {
-  DUDF_REQUIRE(c && c->weights_set, "dudf_jet_backward: weights not set");
-  DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_jet_backward: order %d (0..2)", order);
-  DUDF_REQUIRE(x && seeds && Z && Zb && gW && gb, "dudf_jet_backward: null argument");
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "dudf_jet_backward: unknown precision %d", precision);
   if (P <= 0) return 0;
-  GradView gv;
-  int rc = fill_grad_view(c, gW, gb, gv, "dudf_jet_backward");
-  if (rc) return rc;
-  if (precision == DUDF_PRECISION_TC16)
-    return tc_train_backward(c->tc_packed, c->view(), gv, order_to_nch(order), x, P, seeds, seed_absmax, (const float*)Z, Zb, ld, col0,
-                             c->sms, (cudaStream_t)stream);
-  return simt_backward(c->view(), gv, order_to_nch(order), x, P, seeds, (const float*)Z, (float*)Zb, ld, col0, c->sms, (cudaStream_t)stream);
+  dudf_segment s{x, P, order, nullptr, seeds, col0};
+  return dudf_jet_backward_multi(c, &s, 1, seed_absmax, Z, Zb, ld, gW, gb, precision, stream);
 }
 
 int dudf_jet_wgrad(dudf_ctx* c, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax, float* const* gW,

@@ -56,9 +56,16 @@ struct LossArgs {
 // ---- tcgen05 training path (dudf_tc_train.cu) ----
 int tc_train_pair_cols(int nch);
 int tc_train_pair_points(int nch);
-int tc_train_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, float* outp, float* Ust, void* Aimg,
-                     int64_t ld, int64_t col0, int sms, cudaStream_t st);
-int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, int nch, const float* x, int64_t P, const float* seeds,
+struct TcSegment {          // one row segment of a training batch (consecutive stash columns, 256 per sub-tile pair)
+  const float* x;           // [rows][3]
+  int64_t rows;
+  int nch;
+  float* packed;            // forward: [rows][nch] raw channels out
+  const float* seeds;       // backward: [rows][nch]
+};
+int tc_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld,
+                     int64_t col0, int sms, cudaStream_t st);
+int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg,
                       const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st);
 int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,
                    int sms, cudaStream_t st);

@@ -32,7 +32,8 @@ struct TcCfg {
   static constexpr int OFF_RING = 2 * TC_ACT_BYTES;
   static constexpr int OFF_WL = OFF_RING + TC_STAGES * TC_CHUNK_BYTES;
   static constexpr int OFF_XS = OFF_WL + 256 * 4;
-  static constexpr int OFF_OS = OFF_XS + 2 * PT * 3 * 4;               // [2][256] floats: outputs / seeds
+  static constexpr int OFF_OS = OFF_XS + 2 * 128 * 3 * 4;              // xs sized for the largest sub-tile (a launch may mix orders)
+                                                                       // os: [2][256] floats: outputs / seeds
   static constexpr int OFF_BAR = (OFF_OS + 2 * 256 * 4 + 15) / 16 * 16;
   static constexpr int SMEM = OFF_BAR + 256 + 1024;
 };

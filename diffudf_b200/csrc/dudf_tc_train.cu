@@ -1,14 +1,17 @@
 // Tensor-core training path: forward jets with stash, reverse sweep and weight gradients on tcgen05.
 //
 // Same orientation, tile layout and pipeline as the query kernel (dudf_tc.cu / dudf_tc_common.cuh).  Additions:
-//   * the forward stashes the stored pre-activations in fp32, thread-major ([layer][column group][4-vector][neuron]),
-//     so every warp store is one contiguous 512-byte line; the MMA thread bulk-copies (TMA engine, smem -> global)
-//     each finished B-operand tile as two 32 KB [256 neurons][64 columns] images — exactly the K-major operands
-//     of the weight-gradient GEMM;
+//   * one launch serves up to two row segments with different jet orders (loss_s1: on-surface rows carry the Hessian
+//     jet, the others the gradient jet): the MMA / producer roles only see 128-column sub-tiles, the epilogue picks
+//     the per-point math by segment, so the persistent grid is balanced over ALL sub-tile pairs of the step;
+//   * the forward stashes the stored pre-activations thread-major (every warp store is one contiguous 512-byte
+//     line): the sine argument u0 in fp32, the derivative channels in fp16; the MMA thread bulk-copies (TMA engine,
+//     smem -> global) each finished B-operand tile as two 32 KB [256 neurons][64 columns] images — exactly the
+//     K-major operands of the weight-gradient GEMM;
 //   * the reverse sweep runs the chain backwards with the transposed weight images, reads the stash, applies the
-//     sine-jet adjoint per thread and emits the pre-activation adjoints as its B operand (and, through the same
-//     bulk copies, as operand images); all adjoints carry a power-of-two loss scale S chosen from max|seed| so that
-//     fp16 keeps its full significand over the observed 1e6 dynamic range of the adjoints;
+//     sine-jet adjoint per thread and emits the pre-activation adjoints as its B operand (and, through the same bulk
+//     copies, as operand images); all adjoints carry a power-of-two loss scale S chosen from max|seed| so that fp16
+//     keeps its full significand over the observed 1e6 dynamic range of the adjoints;
 //   * the weight gradient of every hidden layer is one split-K GEMM over all columns (M = N = 256, K = columns).
 #include <cuda_fp16.h>
 #include "dudf_common.cuh"
@@ -26,29 +29,235 @@ int tc_train_pair_points(int nch) { return nch == 1 ? 2 * TcCfg<1>::PT : nch == 
 
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
 
-// thread-major stash of GC stored pre-activations: 4-vectors of all 256 neurons are contiguous
-template <int GC>
+// ---- thread-major stash of one column group: chunk j of the group lives at dst + j*1024 floats (+ 4*neuron) -------
+// value channels (u0) in fp32 first, then the derivative channels packed as halves (in column order)
+template <int NCH, int GC>
+struct Stash {
+  static constexpr int NP = GC / NCH;                      // points per group
+  static constexpr int NF4 = NP / 4;                       // float4 chunks of u0
+  static constexpr int ND = GC - NP;                       // derivative values
+  static constexpr int NH8 = (ND + 7) / 8;                 // uint4 chunks of halves
+  static constexpr int CHUNKS = (NCH == 1) ? GC / 4 : NF4 + NH8;
+};
+
+template <int NCH, int GC>
 __device__ __forceinline__ void tt_stash_group(const float* u, float* dst) {
+  using S = Stash<NCH, GC>;
+  if constexpr (NCH == 1) {
 #pragma unroll
-  for (int j4 = 0; j4 < GC / 4; ++j4)
-    *reinterpret_cast<float4*>(dst + j4 * 1024) = make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
-}
-template <int GC>
-__device__ __forceinline__ void tt_unstash_group(float* u, const float* src) {
+    for (int j4 = 0; j4 < GC / 4; ++j4)
+      *reinterpret_cast<float4*>(dst + j4 * 1024) = make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
+  } else {
 #pragma unroll
-  for (int j4 = 0; j4 < GC / 4; ++j4) {
-    const float4 t = *reinterpret_cast<const float4*>(src + j4 * 1024);
-    u[j4 * 4] = t.x; u[j4 * 4 + 1] = t.y; u[j4 * 4 + 2] = t.z; u[j4 * 4 + 3] = t.w;
+    for (int j4 = 0; j4 < S::NF4; ++j4)
+      *reinterpret_cast<float4*>(dst + j4 * 1024) =
+          make_float4(u[(j4 * 4) * NCH], u[(j4 * 4 + 1) * NCH], u[(j4 * 4 + 2) * NCH], u[(j4 * 4 + 3) * NCH]);
+    float d[S::NH8 * 8];
+#pragma unroll
+    for (int pp = 0; pp < S::NP; ++pp)
+#pragma unroll
+      for (int ch = 1; ch < NCH; ++ch) d[pp * (NCH - 1) + ch - 1] = u[pp * NCH + ch];
+#pragma unroll
+    for (int j = S::ND; j < S::NH8 * 8; ++j) d[j] = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < S::NH8; ++c8)
+      *reinterpret_cast<uint4*>(dst + (S::NF4 + c8) * 1024) =
+          make_uint4(tc_pack_h2(d[8 * c8], d[8 * c8 + 1]), tc_pack_h2(d[8 * c8 + 2], d[8 * c8 + 3]),
+                     tc_pack_h2(d[8 * c8 + 4], d[8 * c8 + 5]), tc_pack_h2(d[8 * c8 + 6], d[8 * c8 + 7]));
   }
 }
 
-// reverse-sweep step of one column group: u (stash), ab (adjoints of the activations) -> adjoints of u, written to the
-// B tile (layers > 0); accumulates the thread's bias / first-layer / output-layer gradient partial sums
+template <int NCH, int GC>
+__device__ __forceinline__ void tt_unstash_group(float* u, const float* src) {
+  using S = Stash<NCH, GC>;
+  if constexpr (NCH == 1) {
+#pragma unroll
+    for (int j4 = 0; j4 < GC / 4; ++j4) {
+      const float4 t = *reinterpret_cast<const float4*>(src + j4 * 1024);
+      u[j4 * 4] = t.x; u[j4 * 4 + 1] = t.y; u[j4 * 4 + 2] = t.z; u[j4 * 4 + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j4 = 0; j4 < S::NF4; ++j4) {
+      const float4 t = *reinterpret_cast<const float4*>(src + j4 * 1024);
+      u[(j4 * 4) * NCH] = t.x; u[(j4 * 4 + 1) * NCH] = t.y; u[(j4 * 4 + 2) * NCH] = t.z; u[(j4 * 4 + 3) * NCH] = t.w;
+    }
+    float d[S::NH8 * 8];
+#pragma unroll
+    for (int c8 = 0; c8 < S::NH8; ++c8) {
+      const uint4 t = *reinterpret_cast<const uint4*>(src + (S::NF4 + c8) * 1024);
+      const __half2* hv = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f2 = __half22float2(hv[e]);
+        d[8 * c8 + 2 * e] = f2.x;
+        d[8 * c8 + 2 * e + 1] = f2.y;
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < S::NP; ++pp)
+#pragma unroll
+      for (int ch = 1; ch < NCH; ++ch) u[pp * NCH + ch] = d[pp * (NCH - 1) + ch - 1];
+  }
+}
+
+// one row segment of a training batch as the kernels see it
+struct SegDev {
+  const float* x;        // [P][3]
+  float* outp;           // forward: [P][NCH] raw channels
+  const float* seeds;    // backward: [P][NCH]
+  int64_t P;
+  int64_t npairs;
+};
+
+struct EpiCtx {
+  unsigned char* act;
+  float* xs;
+  float* os;
+  const float* wl_s;
+  uint64_t* act_ready;
+  uint64_t* acc_ready;
+  uint32_t tmem_lane;
+  uint32_t r7;
+  int n, tid, lane;
+  uint32_t acc_phase;
+};
+
+// =============================================================================================
+// forward: all layers of one sub-tile pair
+// =============================================================================================
+template <int NCH>
+__device__ __forceinline__ void tt_fwd_pair(EpiCtx& e, const NetView& net, const SegDev& sg, int64_t pair, int64_t colp, float* Ust, int64_t ld,
+                                            float r0x, float r0y, float r0z, float b0) {
+  using C = TcCfg<NCH>;
+  const int L = net.n_lin - 1;
+  const float w0 = net.w0, ww = net.ww;
+  tc_epi_bar();
+  for (int i = e.tid; i < 2 * C::PT; i += 256) {
+    const int64_t p = pair * 2 * C::PT + i;
+    float pt[3] = {0.f, 0.f, 0.f};
+    if (p < sg.P) { pt[0] = sg.x[p * 3]; pt[1] = sg.x[p * 3 + 1]; pt[2] = sg.x[p * 3 + 2]; }
+    e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
+  }
+  if (C::NV < 128) {       // idle columns of both tiles are zero for this segment's math
+    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(e.act + s * TC_ACT_BYTES, e.n) + tc_chunk_off(15, e.r7)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_epi_bar();
+  for (int l = 0; l < L; ++l) {
+    const float bias = (l > 0) ? ww * net.b[l][e.n] : 0.f;
+    for (int s = 0; s < 2; ++s) {
+      unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
+      const int64_t colt = colp + s * 128;                        // first stash column of this sub-tile
+      float* ust = Ust + ((size_t)l * ld + colt) * 256 + e.n * 4;
+      if (l > 0) {
+        mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
+        e.acc_phase ^= 1u << s;
+        tc_fence_after();
+      }
+      if (l == 0) {
+#pragma unroll 1
+        for (int g = 0; g < C::NGRP; ++g) {
+          float u[C::GC];
+          tc_first_layer_group<NCH, C::GC>(u, e.xs + (s * C::PT + g * (C::GC / NCH)) * 3, w0, r0x, r0y, r0z, b0);
+          tt_stash_group<NCH, C::GC>(u, ust + (size_t)g * C::GC * 256);
+          tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), e.r7);
+        }
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < C::NGRP; ++g) {
+          float u[C::GC];
+          tc_load_group<C::GC>(e.tmem_lane + s * 256 + g * C::GC, u);
+#pragma unroll
+          for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
+          tt_stash_group<NCH, C::GC>(u, ust + (size_t)g * C::GC * 256);
+          tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), e.r7);
+        }
+      }
+      if (l < L - 1) {
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (e.lane == 0) mbar_arrive(&e.act_ready[s]);
+      } else {
+        tc_epi_bar();
+        tc_output_dot<C::NV>(e.act + s * TC_ACT_BYTES, e.wl_s, e.os + s * 256, e.tid);
+        tc_epi_bar();
+        if (e.tid < C::NV) {
+          const int ch = e.tid % NCH;
+          const int64_t p = (pair * 2 + s) * C::PT + e.tid / NCH;
+          const float v = e.os[s * 256 + e.tid] + e.os[s * 256 + 128 + e.tid];
+          if (p < sg.P) sg.outp[p * NCH + ch] = (ch == 0) ? v + net.b[L][0] : (ch >= 4 ? v * TC_KAPPA_INV : v);
+        }
+      }
+    }
+  }
+}
+
+template <int NA, int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev sa, SegDev sb, float* __restrict__ Ust,
+                  unsigned char* __restrict__ Aimg, int64_t ld, int64_t col0) {
+  using C = TcCfg<NA>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* act = smem;
+  unsigned char* ring = smem + C::OFF_RING;
+  float* wl_s = (float*)(smem + C::OFF_WL);
+  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = net.n_lin - 1;
+  const int64_t npairs = sa.npairs + sb.npairs;
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (tid < 256) wl_s[tid] = net.W[L][tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) tc_producer(packed, ring, full, empty, npairs, L - 1, false);
+  } else if (warp == 9) {
+    if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Aimg, ld >> 6, col0 >> 6, false);
+  } else {
+    const int q = warp & 3, h = warp >> 2;
+    EpiCtx e;
+    e.act = act; e.xs = (float*)(smem + C::OFF_XS); e.os = (float*)(smem + C::OFF_OS); e.wl_s = wl_s;
+    e.act_ready = act_ready; e.acc_ready = acc_ready;
+    e.n = h * 128 + q * 32 + lane; e.tid = tid; e.lane = lane; e.r7 = e.n & 7;
+    e.tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
+    e.acc_phase = 0;
+    const float r0x = net.W[0][e.n * 3], r0y = net.W[0][e.n * 3 + 1], r0z = net.W[0][e.n * 3 + 2], b0 = net.b[0][e.n];
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int64_t colp = col0 + pair * 256;
+      if (pair < sa.npairs) {
+        tt_fwd_pair<NA>(e, net, sa, pair, colp, Ust, ld, r0x, r0y, r0z, b0);
+      } else {
+        if constexpr (NB > 0) tt_fwd_pair<NB>(e, net, sb, pair - sa.npairs, colp, Ust, ld, r0x, r0y, r0z, b0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+// =============================================================================================
+// reverse sweep
+// =============================================================================================
+// one column group: u (stash), ab (adjoints of the activations: seeds x output weights at the top, TMEM below) ->
+// adjoints of u, written to the B tile (layers > 0); accumulates the thread's gradient partial sums
 template <int NCH, int GC, bool TOP, bool FIRST>
 __device__ __forceinline__ void tt_bwd_group(const float* ust_g, uint32_t taddr, float wl, const float* sdg, const float* pts,
                                              unsigned char* trow, int chunk0, uint32_t r7, float& bsum, float& wlsum, float (&w0s)[3]) {
   float u[GC], ab[GC];
-  tt_unstash_group<GC>(u, ust_g);
+  tt_unstash_group<NCH, GC>(u, ust_g);
   if constexpr (TOP) {
 #pragma unroll
     for (int j = 0; j < GC; ++j) ab[j] = wl * sdg[j];
@@ -81,149 +290,98 @@ __device__ __forceinline__ void tt_bwd_group(const float* ust_g, uint32_t taddr,
   if constexpr (!FIRST) tc_store_group<GC>(ab, trow, chunk0, r7);
 }
 
-// =============================================================================================
-// forward with stash
-// =============================================================================================
 template <int NCH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, float* __restrict__ outp,
-                  float* __restrict__ Ust, unsigned char* __restrict__ Aimg, int64_t ld, int64_t col0) {
+__device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const GradView& grad, const SegDev& sg, int64_t pair, int64_t colp,
+                                            const float* Ust, int64_t ld, float S, float wl) {
   using C = TcCfg<NCH>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* act = smem;
-  unsigned char* ring = smem + C::OFF_RING;
-  float* wl_s = (float*)(smem + C::OFF_WL);
-  float* xs = (float*)(smem + C::OFF_XS);
-  float* os = (float*)(smem + C::OFF_OS);
-  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = net.n_lin - 1;
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
-    mbar_fence_init();
+  const float invS = 1.0f / S;
+  float* sd = e.os;                                               // stored seeds of both sub-tiles [2][256]
+  tc_epi_bar();
+  for (int i = e.tid; i < 2 * C::PT; i += 256) {
+    const int64_t p = pair * 2 * C::PT + i;
+    float pt[3] = {0.f, 0.f, 0.f};
+    if (p < sg.P) { pt[0] = sg.x[p * 3]; pt[1] = sg.x[p * 3 + 1]; pt[2] = sg.x[p * 3 + 2]; }
+    e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
-  if (tid < 256) wl_s[tid] = net.W[L][tid];
-  if (C::NV < 128 && tid < 256) {
-    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(act + s * TC_ACT_BYTES, tid) + tc_chunk_off(15, tid & 7)) = make_uint4(0, 0, 0, 0);
+  for (int i = e.tid; i < 2 * C::NV; i += 256) {
+    const int s = i / C::NV, j = i % C::NV;
+    const int64_t p = (pair * 2 + s) * C::PT + j / NCH;
+    const int ch = j % NCH;
+    float v = 0.f;
+    if (p < sg.P) {
+      v = sg.seeds[p * NCH + ch];
+      if (ch == 0 && v != 0.f) atomicAdd(&grad.b[L][0], v);
+      v *= (ch >= 4) ? S * TC_KAPPA_INV : S;
+    }
+    sd[s * 256 + j] = v;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 8) {
-    if (lane == 0) tc_producer(packed, ring, full, empty, npairs, L - 1, false);
-  } else if (warp == 9) {
-    if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Aimg, ld >> 6, col0 >> 6, false);
-  } else {
-    const int q = warp & 3, h = warp >> 2;
-    const int n = h * 128 + q * 32 + lane;
-    const uint32_t r7 = n & 7;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
-    const float w0 = net.w0, ww = net.ww;
-    const float r0x = net.W[0][n * 3], r0y = net.W[0][n * 3 + 1], r0z = net.W[0][n * 3 + 2], b0 = net.b[0][n];
-    const float bL = net.b[L][0];
-    uint32_t acc_phase = 0;
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      tc_epi_bar();
-      for (int i = tid; i < 2 * C::PT; i += 256) {
-        const int64_t p = pair * 2 * C::PT + i;
-        float pt[3] = {0.f, 0.f, 0.f};
-        if (p < P) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
-        xs[i * 3] = pt[0]; xs[i * 3 + 1] = pt[1]; xs[i * 3 + 2] = pt[2];
+  if (C::NV < 128) {
+    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(e.act + s * TC_ACT_BYTES, e.n) + tc_chunk_off(15, e.r7)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_epi_bar();
+  for (int l = L - 1; l >= 0; --l) {
+    const float wl_cur = (l == 0) ? net.w0 : net.ww;
+    const bool top = (l == L - 1), first = (l == 0);
+    for (int s = 0; s < 2; ++s) {
+      unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
+      const int64_t colt = colp + s * 128;
+      const float* ust = Ust + ((size_t)l * ld + colt) * 256 + e.n * 4;
+      if (!top) {
+        mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
+        e.acc_phase ^= 1u << s;
+        tc_fence_after();
       }
-      tc_epi_bar();
-      for (int l = 0; l < L; ++l) {
-        const float bias = (l > 0) ? ww * net.b[l][n] : 0.f;
-        for (int s = 0; s < 2; ++s) {
-          unsigned char* trow = tc_tile_row(act + s * TC_ACT_BYTES, n);
-          const int64_t colt = col0 + (pair * 2 + s) * 128;           // first stash column of this sub-tile
-          float* ust = Ust + ((size_t)l * ld + colt) * 256 + n * 4;   // thread-major: [column group][4-vector][neuron]
-          if (l > 0) {
-            mbar_wait(&acc_ready[s], (acc_phase >> s) & 1u, 0x400 + s);
-            acc_phase ^= 1u << s;
-            tc_fence_after();
-          }
-          if (l == 0) {
+      float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int g = 0; g < C::NGRP; ++g) {
-              float u[C::GC];
-              tc_first_layer_group<NCH, C::GC>(u, xs + (s * C::PT + g * (C::GC / NCH)) * 3, w0, r0x, r0y, r0z, b0);
-              tt_stash_group<C::GC>(u, ust + (size_t)g * C::GC * 256);
-              tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
-            }
-          } else {
-#pragma unroll 1
-            for (int g = 0; g < C::NGRP; ++g) {
-              float u[C::GC];
-              tc_load_group<C::GC>(tmem_lane + s * 256 + g * C::GC, u);
+      for (int g = 0; g < C::NGRP; ++g) {
+        const float* ug = ust + (size_t)g * C::GC * 256;
+        const uint32_t taddr = e.tmem_lane + s * 256 + g * C::GC;
+        const float* sdg = sd + s * 256 + g * C::GC;
+        const float* pts = e.xs + (s * C::PT + g * (C::GC / NCH)) * 3;
+        const int c0 = g * (C::GC / 8);
+        if (top && first) tt_bwd_group<NCH, C::GC, true, true>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (top)     tt_bwd_group<NCH, C::GC, true, false>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (first)   tt_bwd_group<NCH, C::GC, false, true>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else              tt_bwd_group<NCH, C::GC, false, false>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+      }
+      atomicAdd(&grad.b[l][e.n], bsum * wl_cur * invS);
+      if (top) atomicAdd(&grad.W[L][e.n], wlsum * invS);
+      if (first) {
 #pragma unroll
-              for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
-              tt_stash_group<C::GC>(u, ust + (size_t)g * C::GC * 256);
-              tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
-            }
-          }
-          if (l < L - 1) {
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&act_ready[s]);
-          } else {
-            tc_epi_bar();
-            tc_output_dot<C::NV>(act + s * TC_ACT_BYTES, wl_s, os + s * 256, tid);
-            tc_epi_bar();
-            if (tid < C::NV) {
-              const int ch = tid % NCH;
-              const int64_t p = (pair * 2 + s) * C::PT + tid / NCH;
-              const float v = os[s * 256 + tid] + os[s * 256 + 128 + tid];
-              if (p < P) outp[p * NCH + ch] = (ch == 0) ? v + bL : (ch >= 4 ? v * TC_KAPPA_INV : v);
-            }
-          }
-        }
+        for (int d = 0; d < 3; ++d) atomicAdd(&grad.W[0][e.n * 3 + d], w0s[d] * net.w0 * invS);
+      } else {
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (e.lane == 0) mbar_arrive(&e.act_ready[s]);
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-// =============================================================================================
-// reverse sweep
-// =============================================================================================
-template <int NCH>
+template <int NA, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradView grad, const float* __restrict__ x, int64_t P,
-                   const float* __restrict__ seeds, const float* __restrict__ seed_absmax, const float* __restrict__ Ust,
-                   unsigned char* __restrict__ Zimg, int64_t ld, int64_t col0) {
-  using C = TcCfg<NCH>;
+tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradView grad, SegDev sa, SegDev sb,
+                   const float* __restrict__ seed_absmax, const float* __restrict__ Ust, unsigned char* __restrict__ Zimg, int64_t ld,
+                   int64_t col0) {
+  using C = TcCfg<NA>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* act = smem;
   unsigned char* ring = smem + C::OFF_RING;
-  float* xs = (float*)(smem + C::OFF_XS);
-  float* sd = (float*)(smem + C::OFF_OS);                 // stored seeds of both sub-tiles [2][256]
   uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
   uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = net.n_lin - 1;
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
+  const int64_t npairs = sa.npairs + sb.npairs;
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
     mbar_fence_init();
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
-  if (C::NV < 128 && tid < 256) {
-    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(act + s * TC_ACT_BYTES, tid) + tc_chunk_off(15, tid & 7)) = make_uint4(0, 0, 0, 0);
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -235,73 +393,20 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
     if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Zimg, ld >> 6, col0 >> 6, true);
   } else {
     const int q = warp & 3, h = warp >> 2;
-    const int n = h * 128 + q * 32 + lane;
-    const uint32_t r7 = n & 7;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
+    EpiCtx e;
+    e.act = act; e.xs = (float*)(smem + C::OFF_XS); e.os = (float*)(smem + C::OFF_OS); e.wl_s = nullptr;
+    e.act_ready = act_ready; e.acc_ready = acc_ready;
+    e.n = h * 128 + q * 32 + lane; e.tid = tid; e.lane = lane; e.r7 = e.n & 7;
+    e.tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
+    e.acc_phase = 0;
     const float S = loss_scale_from(seed_absmax);
-    const float invS = 1.0f / S;
-    const float wl = net.W[L][n];
-    const float w0 = net.w0, ww = net.ww;
-    uint32_t acc_phase = 0;
+    const float wl = net.W[L][e.n];
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      tc_epi_bar();
-      for (int i = tid; i < 2 * C::PT; i += 256) {
-        const int64_t p = pair * 2 * C::PT + i;
-        float pt[3] = {0.f, 0.f, 0.f};
-        if (p < P) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
-        xs[i * 3] = pt[0]; xs[i * 3 + 1] = pt[1]; xs[i * 3 + 2] = pt[2];
-      }
-      for (int i = tid; i < 2 * C::NV; i += 256) {
-        const int s = i / C::NV, j = i % C::NV;
-        const int64_t p = (pair * 2 + s) * C::PT + j / NCH;
-        const int ch = j % NCH;
-        float v = 0.f;
-        if (p < P) {
-          v = seeds[p * NCH + ch];
-          if (ch == 0 && v != 0.f) atomicAdd(&grad.b[L][0], v);
-          v *= (ch >= 4) ? S * TC_KAPPA_INV : S;
-        }
-        sd[s * 256 + j] = v;
-      }
-      tc_epi_bar();
-      for (int l = L - 1; l >= 0; --l) {
-        const float wl_cur = (l == 0) ? w0 : ww;
-        for (int s = 0; s < 2; ++s) {
-          unsigned char* trow = tc_tile_row(act + s * TC_ACT_BYTES, n);
-          const int64_t colt = col0 + (pair * 2 + s) * 128;
-          const float* ust = Ust + ((size_t)l * ld + colt) * 256 + n * 4;
-          if (l < L - 1) {
-            mbar_wait(&acc_ready[s], (acc_phase >> s) & 1u, 0x400 + s);
-            acc_phase ^= 1u << s;
-            tc_fence_after();
-          }
-          float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
-          const bool top = (l == L - 1), first = (l == 0);
-#pragma unroll 1
-          for (int g = 0; g < C::NGRP; ++g) {
-            const float* ug = ust + (size_t)g * C::GC * 256;
-            const uint32_t taddr = tmem_lane + s * 256 + g * C::GC;
-            const float* sdg = sd + s * 256 + g * C::GC;
-            const float* pts = xs + (s * C::PT + g * (C::GC / NCH)) * 3;
-            const int c0 = g * (C::GC / 8);
-            if (top && first) tt_bwd_group<NCH, C::GC, true, true>(ug, taddr, wl, sdg, pts, trow, c0, r7, bsum, wlsum, w0s);
-            else if (top)     tt_bwd_group<NCH, C::GC, true, false>(ug, taddr, wl, sdg, pts, trow, c0, r7, bsum, wlsum, w0s);
-            else if (first)   tt_bwd_group<NCH, C::GC, false, true>(ug, taddr, wl, sdg, pts, trow, c0, r7, bsum, wlsum, w0s);
-            else              tt_bwd_group<NCH, C::GC, false, false>(ug, taddr, wl, sdg, pts, trow, c0, r7, bsum, wlsum, w0s);
-          }
-          atomicAdd(&grad.b[l][n], bsum * wl_cur * invS);
-          if (l == L - 1) atomicAdd(&grad.W[L][n], wlsum * invS);
-          if (l == 0) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) atomicAdd(&grad.W[0][n * 3 + d], w0s[d] * w0 * invS);
-          }
-          if (l > 0) {
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&act_ready[s]);
-          }
-        }
+      const int64_t colp = col0 + pair * 256;
+      if (pair < sa.npairs) {
+        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl);
+      } else {
+        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl);
       }
     }
   }
@@ -404,55 +509,76 @@ tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const uns
 // =============================================================================================
 // launchers
 // =============================================================================================
-template <int NCH>
-static int tt_launch_fwd(const void* packed, const NetView& net, const float* x, int64_t P, float* outp, float* Ust, void* Aimg, int64_t ld,
+static SegDev make_seg(const TcSegment& s) {
+  SegDev d;
+  d.x = s.x; d.outp = s.packed; d.seeds = s.seeds; d.P = s.rows;
+  const int pp = tc_train_pair_points(s.nch);
+  d.npairs = (s.rows + pp - 1) / pp;
+  return d;
+}
+
+template <int NA, int NB>
+static int tt_launch_fwd(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, float* Ust, void* Aimg, int64_t ld,
                          int64_t col0, int sms, cudaStream_t st) {
-  using C = TcCfg<NCH>;
-  auto k = tt_forward_kernel<NCH>;
-  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int grid = (int)std::min<int64_t>(npairs, sms);
+  auto k = tt_forward_kernel<NA, NB>;
+  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
+  const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
   if (grid < 1) return 0;
-  k<<<grid, TC_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, x, P, outp, Ust, (unsigned char*)Aimg, ld, col0);
+  k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, a, b, Ust, (unsigned char*)Aimg, ld, col0);
   DUDF_LAUNCH_OK();
   return 0;
 }
 
-int tc_train_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, float* outp, float* Ust, void* Aimg,
-                     int64_t ld, int64_t col0, int sms, cudaStream_t st) {
-  DUDF_REQUIRE(ld % 64 == 0 && col0 % 128 == 0, "tensor-core stash: ld must be a multiple of 64 and col0 of 128");
-  switch (nch) {
-    case 1: return tt_launch_fwd<1>(packed, net, x, P, outp, Ust, Aimg, ld, col0, sms, st);
-    case 4: return tt_launch_fwd<4>(packed, net, x, P, outp, Ust, Aimg, ld, col0, sms, st);
-    case 10: return tt_launch_fwd<10>(packed, net, x, P, outp, Ust, Aimg, ld, col0, sms, st);
-  }
-  DUDF_REQUIRE(false, "tensor-core training: unsupported channel count %d", nch);
-}
-
-template <int NCH>
-static int tt_launch_bwd(const void* packed, const NetView& net, const GradView& grad, const float* x, int64_t P, const float* seeds,
+template <int NA, int NB>
+static int tt_launch_bwd(const void* packed, const NetView& net, const GradView& grad, const SegDev& a, const SegDev& b,
                          const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st) {
-  using C = TcCfg<NCH>;
-  auto k = tt_backward_kernel<NCH>;
-  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int grid = (int)std::min<int64_t>(npairs, sms);
+  auto k = tt_backward_kernel<NA, NB>;
+  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
+  const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
   if (grid < 1) return 0;
-  k<<<grid, TC_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, grad, x, P, seeds, seed_absmax, Ust, (unsigned char*)Zimg, ld, col0);
+  k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, seed_absmax, Ust, (unsigned char*)Zimg, ld, col0);
   DUDF_LAUNCH_OK();
   return 0;
 }
 
-int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, int nch, const float* x, int64_t P, const float* seeds,
-                      const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st) {
+// segments must occupy consecutive column ranges of the stash starting at col0 (256 columns per pair)
+int tc_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld, int64_t col0,
+                     int sms, cudaStream_t st) {
+  DUDF_REQUIRE(ld % 64 == 0 && col0 % 128 == 0, "tensor-core stash: ld must be a multiple of 64 and col0 of 128");
+  DUDF_REQUIRE(nseg == 1 || nseg == 2, "tensor-core training: 1 or 2 segments per launch");
+  SegDev a = make_seg(segs[0]), b;
+  memset(&b, 0, sizeof(b));
+  const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
+  if (nseg == 2) b = make_seg(segs[1]);
+  if (nb == 0) {
+    if (na == 1) return tt_launch_fwd<1, 0>(packed, net, a, b, Ust, Aimg, ld, col0, sms, st);
+    if (na == 4) return tt_launch_fwd<4, 0>(packed, net, a, b, Ust, Aimg, ld, col0, sms, st);
+    if (na == 10) return tt_launch_fwd<10, 0>(packed, net, a, b, Ust, Aimg, ld, col0, sms, st);
+  } else if (na == 10) {
+    if (nb == 4) return tt_launch_fwd<10, 4>(packed, net, a, b, Ust, Aimg, ld, col0, sms, st);
+    if (nb == 1) return tt_launch_fwd<10, 1>(packed, net, a, b, Ust, Aimg, ld, col0, sms, st);
+  }
+  DUDF_REQUIRE(false, "tensor-core training: unsupported segment channel counts (%d, %d)", na, nb);
+}
+
+int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg, const float* seed_absmax,
+                      const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st) {
   DUDF_REQUIRE(seed_absmax != nullptr, "tensor-core reverse sweep needs the seed magnitude (loss scale)");
   DUDF_REQUIRE(ld % 64 == 0 && col0 % 128 == 0, "tensor-core stash: ld must be a multiple of 64 and col0 of 128");
-  switch (nch) {
-    case 1: return tt_launch_bwd<1>(packed, net, grad, x, P, seeds, seed_absmax, Ust, Zimg, ld, col0, sms, st);
-    case 4: return tt_launch_bwd<4>(packed, net, grad, x, P, seeds, seed_absmax, Ust, Zimg, ld, col0, sms, st);
-    case 10: return tt_launch_bwd<10>(packed, net, grad, x, P, seeds, seed_absmax, Ust, Zimg, ld, col0, sms, st);
+  DUDF_REQUIRE(nseg == 1 || nseg == 2, "tensor-core training: 1 or 2 segments per launch");
+  SegDev a = make_seg(segs[0]), b;
+  memset(&b, 0, sizeof(b));
+  const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
+  if (nseg == 2) b = make_seg(segs[1]);
+  if (nb == 0) {
+    if (na == 1) return tt_launch_bwd<1, 0>(packed, net, grad, a, b, seed_absmax, Ust, Zimg, ld, col0, sms, st);
+    if (na == 4) return tt_launch_bwd<4, 0>(packed, net, grad, a, b, seed_absmax, Ust, Zimg, ld, col0, sms, st);
+    if (na == 10) return tt_launch_bwd<10, 0>(packed, net, grad, a, b, seed_absmax, Ust, Zimg, ld, col0, sms, st);
+  } else if (na == 10) {
+    if (nb == 4) return tt_launch_bwd<10, 4>(packed, net, grad, a, b, seed_absmax, Ust, Zimg, ld, col0, sms, st);
+    if (nb == 1) return tt_launch_bwd<10, 1>(packed, net, grad, a, b, seed_absmax, Ust, Zimg, ld, col0, sms, st);
   }
-  DUDF_REQUIRE(false, "tensor-core training: unsupported channel count %d", nch);
+  DUDF_REQUIRE(false, "tensor-core training: unsupported segment channel counts (%d, %d)", na, nb);
 }
 
 int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,

@@ -142,6 +142,30 @@ class Engine:
                                                 Z.data_ptr(), Zb.data_ptr(), ld, col0, _ptr_array(gW), _ptr_array(gb),
                                                 PRECISIONS[precision], _lib.current_stream()), "dudf_jet_backward")
 
+    @staticmethod
+    def _segments(segs, packed_key):
+        arr = (_lib.Segment * len(segs))()
+        for i, s in enumerate(segs):
+            arr[i].x = s["x"].data_ptr()
+            arr[i].rows = s["x"].shape[0]
+            arr[i].order = s["order"]
+            arr[i].packed = s["packed"].data_ptr() if packed_key == "packed" else None
+            arr[i].seeds = s["seeds"].data_ptr() if packed_key == "seeds" else None
+            arr[i].col0 = s["col0"]
+        return arr
+
+    def jet_forward_multi(self, segs, Z, A, ld, precision="fp32"):
+        """segs: list of dict(x (rows,3), order, packed (rows*NCH,), col0) — one launch on the tensor-core path."""
+        with torch.cuda.device(Z.device):
+            _lib.check(self.L.dudf_jet_forward_multi(self.h, self._segments(segs, "packed"), len(segs), Z.data_ptr(), A.data_ptr(), ld,
+                                                     PRECISIONS[precision], _lib.current_stream()), "dudf_jet_forward_multi")
+
+    def jet_backward_multi(self, segs, Z, Zb, ld, gW, gb, precision="fp32", seed_absmax=None):
+        with torch.cuda.device(Z.device):
+            _lib.check(self.L.dudf_jet_backward_multi(self.h, self._segments(segs, "seeds"), len(segs), _lib.ptr(seed_absmax), Z.data_ptr(),
+                                                      Zb.data_ptr(), ld, _ptr_array(gW), _ptr_array(gb), PRECISIONS[precision],
+                                                      _lib.current_stream()), "dudf_jet_backward_multi")
+
     def jet_wgrad(self, Zb, A, ld, ncols, gW, precision="fp32", seed_absmax=None):
         with torch.cuda.device(Zb.device):
             _lib.check(self.L.dudf_jet_wgrad(self.h, Zb.data_ptr(), A.data_ptr(), ld, ncols, _lib.ptr(seed_absmax), _ptr_array(gW),

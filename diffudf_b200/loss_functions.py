@@ -81,10 +81,10 @@ class TrainCore:
         packed = self._buf("packed", (nout,))
         terms = torch.zeros(4, device=x.device, dtype=torch.float64)
         stats = torch.zeros(3, device=x.device, dtype=torch.float64) if mode == "s2" else None
+        eng.jet_forward_multi([dict(x=x[s["row0"]:s["row0"] + s["rows"]], order=s["order"], col0=s["col0"],
+                                    packed=packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]) for s in segs], Z, A, ld, prec)
         for s in segs:
-            xs = x[s["row0"]:s["row0"] + s["rows"]]
             pk = packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]
-            eng.jet_forward(xs, s["order"], pk, Z, A, ld, s["col0"], prec)
             ds = d[s["row0"]:s["row0"] + s["rows"]]
             if mode == "s2":
                 eng.loss_s2_stats(pk, ds, s["rows"], stats)
@@ -118,13 +118,10 @@ class TrainCore:
             sd = seeds[s["off"]:s["off"] + s["rows"] * nch]
             eng.loss(p["mode"], pk, nch, p["normals"][r0:r1] if p["normals"] is not None else None, p["d"][r0:r1], s["rows"],
                      p["P_global"], p["w"], p["alpha"], upstream=upstream, seeds=sd, s2_stats=p["stats"], seed_absmax=absmax)
-        ncols = 0
-        for s in p["segs"]:
-            r0, r1 = s["row0"], s["row0"] + s["rows"]
-            nch = NCH[s["order"]]
-            sd = seeds[s["off"]:s["off"] + s["rows"] * nch]
-            eng.jet_backward(p["x"][r0:r1], s["order"], sd, p["Z"], p["Zb"], p["ld"], s["col0"], gW, gB, prec, seed_absmax=absmax)
-            ncols = s["col0"] + s["cols"]
+        eng.jet_backward_multi([dict(x=p["x"][s["row0"]:s["row0"] + s["rows"]], order=s["order"], col0=s["col0"],
+                                     seeds=seeds[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]) for s in p["segs"]],
+                               p["Z"], p["Zb"], p["ld"], gW, gB, prec, seed_absmax=absmax)
+        ncols = max(s["col0"] + s["cols"] for s in p["segs"])
         eng.jet_wgrad(p["Zb"], p["A"], p["ld"], ncols, gW, prec, seed_absmax=absmax)
 
 

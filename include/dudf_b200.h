@@ -104,6 +104,21 @@ int dudf_jet_backward(dudf_ctx* ctx, const float* x, int64_t P, int order, const
                       int precision, void* stream);
 int dudf_jet_wgrad(dudf_ctx* ctx, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax,
                    float* const* gW_host, int precision, void* stream);
+/* Several row segments of one batch in one call (one launch on the tensor-core path, which balances its persistent
+ * grid over all segments): loss_s1 evaluates the Hessian jet (order 2) on the on-surface rows and the gradient jet on
+ * the others.  Tensor-core path: at most 2 segments, contiguous stash columns, the order-2 segment first. */
+typedef struct dudf_segment {
+  const float* x;      /* [rows][3] */
+  int64_t rows;
+  int order;           /* 0, 1, 2 */
+  float* packed;       /* forward: [rows][NCH] out */
+  const float* seeds;  /* backward: [rows][NCH] in */
+  int64_t col0;        /* first stash column */
+} dudf_segment;
+int dudf_jet_forward_multi(dudf_ctx* ctx, const dudf_segment* segs_host, int nseg, void* Z, void* A, int64_t ld, int precision,
+                           void* stream);
+int dudf_jet_backward_multi(dudf_ctx* ctx, const dudf_segment* segs_host, int nseg, const float* seed_absmax, const void* Z,
+                            void* Zb, int64_t ld, float* const* gW_host, float* const* gb_host, int precision, void* stream);
 /* With DUDF_PRECISION_TC16 the stashes change type: Z is fp32 [n_hidden][ld][256] (column-group / thread-major, private
  * to the kernel pair; ld a multiple of 64), A and Zb are fp16 operand planes [n_hidden][4 k-blocks][ld][64 neurons]
  * (128-byte swizzled rows, zero-initialised by the caller), and the reverse sweep runs

@@ -32,7 +32,7 @@ def test_stash_geometry_is_host_side():
     assert L.dudf_stash_columns(1, 17, 0) == 2 * 64          # fp32 path: 16 points x 4 channels per tile
     assert L.dudf_stash_columns(2, 9990, 0) == 1249 * 80     # 8 points x 10 channels per tile
     assert L.dudf_stash_columns(1, 65, 1) == 2 * 256         # tcgen05 path: pairs of 32-point sub-tiles, 4 channels
-    assert L.dudf_stash_columns(2, 9990, 1) == 625 * 160     # pairs of 8-point sub-tiles, 10 channels
+    assert L.dudf_stash_columns(2, 9990, 1) == 417 * 256     # pairs of 12-point sub-tiles (120 of 128 columns in use)
     assert L.dudf_stash_columns(5, 10, 0) == -1
 
 

@@ -1,0 +1,49 @@
+"""Data-parallel correctness on real GPUs (run under torchrun, world_size >= 2):
+the gradient all-reduced over ranks that each hold a [on|far|near] shard equals the single-GPU gradient of the
+whole batch, and the loss-term shares sum to the single-GPU terms.  Prints DP_CHECK_OK on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from diffudf_b200 import SIREN, synthetic  # noqa: E402
+from diffudf_b200.parallel import DataParallel, shard_batch  # noqa: E402
+from diffudf_b200.train import FusedTrainer  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+shape = synthetic.make_shape(0)
+sp, sn = shape.sample_surface(50000, np.random.default_rng(0))
+x, n, d = synthetic.make_batch(shape, sp, sn, 6000, (0.333, 0.666), np.random.default_rng(7))
+x, n, d = x[0], n[0], d[0, :, 0]
+P, n_on = x.shape[0], 1998
+n_far = (P - n_on) // 2
+ok = True
+for prec, tol in (("fp32", 2e-4), ("tc16", 2e-2)):
+    for mode, w in (("s1", [1e4, 1e4, 1e4, 1e3]), ("s2", [1e5, 1e5])):
+        torch.manual_seed(123)
+        m = SIREN(3, 1, [256] * 8, w0=30).cuda()
+        dp = DataParallel(rows_global=P)
+        tr = FusedTrainer(m, dp=dp, precision=prec)
+        xr, nr, dr, on_r = shard_batch(x, n, d, n_on, n_far, rank, world)
+        t = tr.step(mode, torch.from_numpy(xr).cuda(), torch.from_numpy(nr).cuda(), torch.from_numpy(dr).cuda(), on_r, w, 100.0, 0.0)
+        if mode == "s1":
+            dp.reduce_terms(t)
+        g_dp = tr.grad.clone()
+        if rank == 0:
+            torch.manual_seed(123)
+            m1 = SIREN(3, 1, [256] * 8, w0=30).cuda()
+            tr1 = FusedTrainer(m1, precision=prec)
+            t1 = tr1.step(mode, torch.from_numpy(x).cuda(), torch.from_numpy(n).cuda(), torch.from_numpy(d).cuda(), n_on, w, 100.0, 0.0)
+            eg = float((g_dp - tr1.grad).abs().max() / tr1.grad.abs().max())
+            et = float(((t - t1).abs() / t1.abs().clamp_min(1e-6)).max())
+            print(f"{prec} {mode}: grad err {eg:.2e} terms err {et:.2e}", flush=True)
+            ok = ok and eg < tol and et < 1e-3
+dist.barrier()
+if rank == 0:
+    print("DP_CHECK_OK" if ok else "DP_CHECK_FAILED", flush=True)
+dist.destroy_process_group()
