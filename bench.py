@@ -205,7 +205,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- per-kernel timing of one step (CUDA events on the launching stream) for the roofline object ----
     prof = {}
-    if rank == 0:
+    if True:      # every rank runs these steps (they contain the gradient all-reduce); rank 0's events are reported
         eng = model._engine_synced()
         names = ["jet_forward_multi", "loss", "jet_backward_multi", "jet_wgrad"]
         orig = {k: getattr(eng, k) for k in names}
@@ -301,6 +301,8 @@ def main():
     ap.add_argument("--precision", default="tc16", choices=["tc16", "fp32"],
                     help="arithmetic of the training step: tcgen05 fp16-operand MMAs (default) or fp32 CUDA cores")
     args = ap.parse_args()
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
