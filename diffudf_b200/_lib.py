@@ -40,6 +40,8 @@ SIGNATURES = {
     "dudf_create": [c_int, c_float, c_float, ctypes.POINTER(c_void_p)],
     "dudf_destroy": [c_void_p],
     "dudf_set_weights": [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p],
+    "dudf_bind_weights": [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)],
+    "dudf_refresh_weights": [c_void_p, c_int, c_void_p],
     "dudf_query_points": [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dudf_query_grid": [c_void_p, c_int, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dudf_eig_normals": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],

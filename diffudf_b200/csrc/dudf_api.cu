@@ -55,12 +55,14 @@ struct dudf_ctx {
   float* Wd[DUDF_MAX_LAYERS] = {};
   float* bd[DUDF_MAX_LAYERS] = {};
   float* Wtd[DUDF_MAX_LAYERS] = {};
+  const float* Wp[DUDF_MAX_LAYERS] = {};   // weights in use: the owned copies (dudf_set_weights) or borrowed (dudf_bind_weights)
+  const float* bp[DUDF_MAX_LAYERS] = {};
   void* tc_packed = nullptr;
   dudf::DevBuf ws_out, ws_x64;
   NetView view() const {
     NetView v;
     memset(&v, 0, sizeof(v));
-    for (int i = 0; i < n_lin; ++i) { v.W[i] = Wd[i]; v.b[i] = bd[i]; v.Wt[i] = Wtd[i]; }
+    for (int i = 0; i < n_lin; ++i) { v.W[i] = Wp[i]; v.b[i] = bp[i]; v.Wt[i] = Wtd[i]; }
     v.n_lin = n_lin;
     v.w0 = w0;
     v.ww = ww;
@@ -118,6 +120,34 @@ int dudf_destroy(dudf_ctx* c) {
   return 0;
 }
 
+int dudf_refresh_weights(dudf_ctx* c, int what, void* stream) {
+  DUDF_REQUIRE(c && c->Wp[0], "dudf_refresh_weights: no weights bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (what & DUDF_REFRESH_FP32) {
+    for (int i = 0; i < c->n_lin; ++i)
+      if (c->Wtd[i]) {
+        int rc = transpose256(c->Wp[i], c->Wtd[i], st);
+        if (rc) return rc;
+      }
+  }
+  if (what & DUDF_REFRESH_TC16) {
+    int rc = tc_pack(c->view(), c->tc_packed, st);
+    if (rc) return rc;
+  }
+  c->weights_set = true;
+  return 0;
+}
+
+int dudf_bind_weights(dudf_ctx* c, const float* const* W, const float* const* b) {
+  DUDF_REQUIRE(c && W && b, "dudf_bind_weights: null argument");
+  for (int i = 0; i < c->n_lin; ++i) {
+    DUDF_REQUIRE(W[i] && b[i], "dudf_bind_weights: null pointer for layer %d", i);
+    c->Wp[i] = W[i];
+    c->bp[i] = b[i];
+  }
+  return 0;
+}
+
 int dudf_set_weights(dudf_ctx* c, const float* const* W, const float* const* b, void* stream) {
   DUDF_REQUIRE(c && W && b, "dudf_set_weights: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -126,15 +156,10 @@ int dudf_set_weights(dudf_ctx* c, const float* const* W, const float* const* b, 
     DUDF_REQUIRE(W[i] && b[i], "dudf_set_weights: null pointer for layer %d", i);
     DUDF_CUDA_OK(cudaMemcpyAsync(c->Wd[i], W[i], in * outn * sizeof(float), cudaMemcpyDeviceToDevice, st));
     DUDF_CUDA_OK(cudaMemcpyAsync(c->bd[i], b[i], outn * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (c->Wtd[i]) {
-      int rc = transpose256(c->Wd[i], c->Wtd[i], st);
-      if (rc) return rc;
-    }
+    c->Wp[i] = c->Wd[i];
+    c->bp[i] = c->bd[i];
   }
-  int rc = tc_pack(c->view(), c->tc_packed, st);
-  if (rc) return rc;
-  c->weights_set = true;
-  return 0;
+  return dudf_refresh_weights(c, DUDF_REFRESH_FP32 | DUDF_REFRESH_TC16, stream);
 }
 
 static int order_to_nch(int order) { return order == 0 ? 1 : order == 1 ? 4 : order == 2 ? 10 : order == 3 ? 20 : -1; }

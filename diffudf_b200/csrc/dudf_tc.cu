@@ -18,6 +18,8 @@
 //   warp  9    MMA issuer: one thread issues tcgen05.mma; tcgen05.commit frees ring slots / publishes accumulators
 // Two sub-tiles are in flight so that the MMAs of one overlap the epilogue of the other.
 #include <cuda_fp16.h>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "dudf_common.cuh"
 #include "dudf_kernels.h"
@@ -57,7 +59,9 @@ int tc_pack(const NetView& net, void* packed, cudaStream_t st) {
   return 0;
 }
 
-template <int NCH>
+// CL = thread-block cluster size: the CTAs of a cluster share every weight chunk fetched from L2 (multicast), which
+// divides the L2 -> SM weight traffic (the measured limiter of this kernel at CL = 1, tools/pipe_probe.py) by CL.
+template <int NCH, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, int gridN,
                   int64_t grid_first, QueryOut out) {
@@ -76,9 +80,12 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = net.n_lin - 1;            // sine layers
   const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
+  // every CTA of a cluster runs the same number of rounds (a round past the end works on fully masked points)
+  const int64_t rounds = (CL > 1) ? (npairs + gridDim.x - 1) / gridDim.x
+                                  : (((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
 
   if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
     mbar_fence_init();
   }
@@ -89,14 +96,19 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                 // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    if (lane == 0) tc_producer(packed, ring, full, empty, npairs, L - 1, false);
-  } else if (warp == 9) {
-    if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, nullptr, 0, 0, false);
+  if (warp >= 8) {
+    setmaxnreg_dec<TC_REGS_AUX>();                          // warpgroup 2 hands its registers to the epilogue warpgroups
+    if (warp == 8) {
+      if (lane == 0) tc_producer<CL, true>(packed, ring, full, empty, rounds, L - 1, false, CL > 1 ? cluster_ctarank() : 0u);
+    } else if (warp == 9) {
+      if (lane == 0) tc_mma_role<CL, true>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, 0, 0, false, out.flags >> 8);
+    }
   } else {
+    setmaxnreg_inc<TC_REGS_EPI>();
     // ===================== epilogue warps (256 threads) =====================
     const int q = warp & 3, h = warp >> 2;
     const int n = h * 128 + q * 32 + lane;                  // this thread's neuron = its row of the B operand
@@ -108,7 +120,8 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
     const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
     uint32_t acc_phase = 0;                                 // bit s = parity of acc_ready[s]
 
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+      const int64_t pair = blockIdx.x + rd * gridDim.x;
       // ---- coordinates of both sub-tiles ----
       tc_epi_bar();
       for (int i = tid; i < 2 * C::PT; i += 256) {
@@ -139,11 +152,14 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
               tc_first_layer_group<NCH, C::GC>(u, xs + (s * C::PT + g * (C::GC / NCH)) * 3, w0, r0x, r0y, r0z, b0);
               tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
             }
-          } else {
+          } else if (!((out.flags >> 8) & 1)) {       // flags bit 8: pipeline diagnostics — skip the epilogue math
+            TmemRegs<C::GC> nxt;
+            tc_ld_issue<C::GC>(tmem_lane + s * 256, nxt);
 #pragma unroll 1
             for (int g = 0; g < C::NGRP; ++g) {
               float u[C::GC];
-              tc_load_group<C::GC>(tmem_lane + s * 256 + g * C::GC, u);
+              tc_ld_take<C::GC>(nxt, u);
+              if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(tmem_lane + s * 256 + (g + 1) * C::GC, nxt);   // in flight during the math below
 #pragma unroll
               for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
               tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
@@ -177,29 +193,66 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                 // nobody exits while a peer may still multicast into its ring
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-template <int NCH>
+static int g_tc_cluster = -1;      // DUDF_TC_CLUSTER=1|2|4 overrides the cluster size of the query kernel (default 2)
+static int tc_cluster_size() {
+  if (g_tc_cluster < 0) {
+    const char* e = getenv("DUDF_TC_CLUSTER");
+    const int v = e ? atoi(e) : 2;
+    g_tc_cluster = (v == 1 || v == 2 || v == 4) ? v : 2;
+  }
+  return g_tc_cluster;
+}
+
+template <int NCH, int CL>
 static int tc_launch(const void* packed, const NetView& net, const float* x, int64_t P, int gridN, int64_t first,
                      const QueryOut& out, int sms, cudaStream_t st) {
   using C = TcCfg<NCH>;
-  auto k = tc_forward_kernel<NCH>;
+  auto k = tc_forward_kernel<NCH, CL>;
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int grid = (int)std::min<int64_t>(npairs, sms);
+  int grid = (int)std::min<int64_t>(npairs, sms);
   if (grid < 1) return 0;
-  k<<<grid, TC_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, x, P, gridN, first, out);
+  if (CL > 1) grid = std::max(CL, (std::min<int>(sms, (int)((npairs + CL - 1) / CL * CL)) / CL) * CL);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DUDF_CUDA_OK(cudaLaunchKernelEx(&cfg, k, (const unsigned char*)packed, net, x, P, gridN, first, out));
   DUDF_LAUNCH_OK();
   return 0;
+}
+
+template <int NCH>
+static int tc_launch_cl(const void* packed, const NetView& net, const float* x, int64_t P, int gridN, int64_t first, const QueryOut& out,
+                        int sms, cudaStream_t st) {
+  using C = TcCfg<NCH>;
+  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
+  int cl = tc_cluster_size();
+  while (cl > 1 && npairs < 2 * cl) cl >>= 1;              // tiny queries: no point in pairing CTAs
+  if (cl == 4) return tc_launch<NCH, 4>(packed, net, x, P, gridN, first, out, sms, st);
+  if (cl == 2) return tc_launch<NCH, 2>(packed, net, x, P, gridN, first, out, sms, st);
+  return tc_launch<NCH, 1>(packed, net, x, P, gridN, first, out, sms, st);
 }
 
 int tc_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN, int64_t grid_first,
                const QueryOut& out, int sms, cudaStream_t st) {
   switch (nch) {
-    case 1: return tc_launch<1>(packed, net, x, P, gridN, grid_first, out, sms, st);
-    case 4: return tc_launch<4>(packed, net, x, P, gridN, grid_first, out, sms, st);
-    case 10: return tc_launch<10>(packed, net, x, P, gridN, grid_first, out, sms, st);
+    case 1: return tc_launch_cl<1>(packed, net, x, P, gridN, grid_first, out, sms, st);
+    case 4: return tc_launch_cl<4>(packed, net, x, P, gridN, grid_first, out, sms, st);
+    case 10: return tc_launch_cl<10>(packed, net, x, P, gridN, grid_first, out, sms, st);
   }
   DUDF_REQUIRE(false, "tensor-core path: unsupported channel count %d", nch);
 }

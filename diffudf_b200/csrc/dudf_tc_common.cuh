@@ -17,7 +17,9 @@ namespace dudf {
 
 constexpr int TC_CHUNK_BYTES = 128 * 64 * 2;   // one weight chunk: 128 neurons x 64 k, fp16
 constexpr int TC_STAGES = 5;
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 384;            // warpgroups 0-1: epilogue (216 regs), warpgroup 2: producer + MMA issuer (40 regs)
+constexpr int TC_REGS_EPI = 216;
+constexpr int TC_REGS_AUX = 56;            // 256 * 216 + 128 * 56 = 62 464 <= 65 536 registers per SM
 constexpr int TC_ACT_BYTES = 65536;
 constexpr int TC_IMG_BYTES = 32768;            // [256][64] fp16 operand image
 constexpr float TC_KAPPA = 0.125f;
@@ -61,66 +63,129 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---- producer: weight chunks through the ring.  Phase j of a pair uses image j (forward) or the transposed
-// ---- image of layer n_phase-j (reverse sweep); both sub-tiles re-stream the 8 chunks of the layer.
-__device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t npairs,
-                                            int n_phase, bool backward) {
+// ---- image of layer n_phase-j (reverse sweep).  REUSE: each of the 8 chunks of a layer is fetched once per sub-tile
+// ---- pair (the MMA issuer uses a chunk for both sub-tiles before releasing it); otherwise once per sub-tile.
+// CL > 1: the CTAs of a cluster run the same schedule; chunk c is fetched from L2 by CTA (c mod CL) only and
+// multicast into the ring slot of every CTA of the cluster (its complete_tx lands on each CTA's full barrier);
+// a slot is free again when the MMA issuers of ALL CTAs have released it (empty barriers count CL arrivals).
+template <int CL = 1, bool REUSE = false>
+__device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t rounds,
+                                            int n_phase, bool backward, uint32_t cta_rank = 0) {
   using namespace umma;
-  uint32_t stage = 0, phase = 0;
-  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+  uint32_t stage = 0, phase = 0, chunk = 0;
+  for (int64_t r = 0; r < rounds; ++r)
     for (int j = 0; j < n_phase; ++j) {
       const int idx = backward ? (n_phase + (n_phase - 1 - j)) : j;
       const unsigned char* src = packed + (size_t)idx * 8 * TC_CHUNK_BYTES;
-      for (int s = 0; s < 2; ++s)
-        for (int ck = 0; ck < 8; ++ck) {
+      for (int rep = 0; rep < (REUSE ? 1 : 2); ++rep)
+        for (int ck = 0; ck < 8; ++ck, ++chunk) {
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
           mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
-          bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
+          if constexpr (CL == 1) {
+            bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
+          } else {
+            if (chunk % CL == cta_rank)
+              bulk_g2s_multicast(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage],
+                                 (uint16_t)((1u << CL) - 1));
+          }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
     }
 }
 
-// ---- MMA issuer (one thread).  img != null: after issuing the MMAs of a sub-tile, bulk-copy its B tile (two
-// ---- 32 KB operand images) to img[layer][cb0 + 2*subtile + nb] for the weight-gradient GEMM.
-__device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
-                                            uint64_t* acc_ready, uint32_t tmem_base, int64_t npairs, int n_phase, unsigned char* img,
-                                            int64_t ncb, int64_t cb0, bool backward) {
+// after the last MMA of a sub-tile: optional operand-image copy for the weight-gradient GEMM, then publish the accumulator
+__device__ __forceinline__ void tc_finish_subtile(unsigned char* act, uint64_t* acc_ready, int s, unsigned char* img, int64_t ncb, int64_t cb0,
+                                                  int64_t pair, int layer) {
   using namespace umma;
+  if (img) {
+    const int64_t cb = cb0 + (pair * 2 + s) * 2;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+      bulk_s2g(img + ((size_t)layer * ncb + cb + nb) * TC_IMG_BYTES, act + s * TC_ACT_BYTES + nb * TC_IMG_BYTES, TC_IMG_BYTES);
+    bulk_commit();
+    bulk_wait_read0();          // the tile may be overwritten once acc_ready is published
+  }
+  mma_commit(&acc_ready[s]);
+}
+
+// ---- MMA issuer (one thread).
+// REUSE = false: per layer  A.h0 A.h1 | B.h0 B.h1  (sub-tile A/B, neuron half h): a sub-tile's accumulator is published as
+//   early as possible (best when the epilogue / HBM traffic is the limiter: training kernels).
+// REUSE = true:  per layer  A.h0 B.h0 | A.h1 B.h1: the four chunks of a half stay in the ring for both sub-tiles and are
+//   released after the second use, so weights cross L2 -> SM once per 256 columns (query kernel).
+// img != null: bulk-copy each finished B tile (two 32 KB operand images) to img[layer][cb0 + 2*subtile + nb].
+template <int CL = 1, bool REUSE = false>
+__device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                            uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, unsigned char* img,
+                                            int64_t ncb, int64_t cb0, bool backward, int dbg = 0) {
+  using namespace umma;
+  static_assert(TC_STAGES >= 5, "a neuron half (4 chunks) must fit in the ring with one slot to prefetch into");
   constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
-  uint32_t stage = 0, phase = 0;
+  constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
+  uint32_t stage = 0, phase = 0;                            // ring position of the next chunk to be consumed for the first time
   uint32_t act_phase = 0;                                   // bit s = parity of act_ready[s]
-  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
-    for (int j = 0; j < n_phase; ++j)
-      for (int s = 0; s < 2; ++s) {
-        mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
-        act_phase ^= 1u << s;
-        tc_fence_after();
-        const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
-          for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&full[stage], phase, 0x300 + stage);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + stage * TC_CHUNK_BYTES);
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t pair = blockIdx.x + r * gridDim.x;
+    for (int j = 0; j < n_phase; ++j) {
+      const int layer = backward ? (n_phase - j) : j;
+      if constexpr (!REUSE) {
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
+          act_phase ^= 1u << s;
+          tc_fence_after();
+          const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
+            for (int kb = 0; kb < 4; ++kb) {
+              mbar_wait(&full[stage], phase, 0x300 + stage);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(ring + stage * TC_CHUNK_BYTES);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              mma_f16_ss(d_tmem, make_desc_sw128(a_addr + k4 * 32, 16, 1024), make_desc_sw128(act_s + (kb * 8 + k4 * 2) * 1024, 32768, 1024),
-                         idesc, (kb | k4) != 0);
-            mma_commit(&empty[stage]);
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              for (int k4 = 0; k4 < 4; ++k4)
+                if (!(dbg & 2))
+                  mma_f16_ss(d_tmem, make_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                             make_desc_sw128(act_s + (kb * 8 + k4 * 2) * 1024, 32768, 1024), idesc, (kb | k4) != 0);
+              if constexpr (CL == 1) mma_commit(&empty[stage]);
+              else mma_commit_multicast(&empty[stage], mask);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
           }
+          tc_finish_subtile(act, acc_ready, s, img, ncb, cb0, pair, layer);
         }
-        if (img) {
-          const int layer = backward ? (n_phase - j) : j;
-          const int64_t cb = cb0 + (pair * 2 + s) * 2;
+      } else {
+        for (int h = 0; h < 2; ++h)
+          for (int s = 0; s < 2; ++s) {
+            if (h == 0) {
+              mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
+              act_phase ^= 1u << s;
+              tc_fence_after();
+            }
+            const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
+            const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
+            uint32_t st = stage, ph = phase;
+            for (int kb = 0; kb < 4; ++kb) {
+              if (s == 0) {
+                mbar_wait(&full[st], ph, 0x300 + st);
+                tc_fence_after();
+              }
+              const uint32_t a_addr = smem_u32(ring + st * TC_CHUNK_BYTES);
 #pragma unroll
-          for (int nb = 0; nb < 2; ++nb)
-            bulk_s2g(img + ((size_t)layer * ncb + cb + nb) * TC_IMG_BYTES, act + s * TC_ACT_BYTES + nb * TC_IMG_BYTES, TC_IMG_BYTES);
-          bulk_commit();
-          bulk_wait_read0();          // the tile may be overwritten once acc_ready is published
-        }
-        mma_commit(&acc_ready[s]);
+              for (int k4 = 0; k4 < 4; ++k4)
+                if (!(dbg & 2))     // dbg bit 1: pipeline diagnostics (tools/pipe_probe.py) — skip the MMAs, keep the protocol
+                  mma_f16_ss(d_tmem, make_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                             make_desc_sw128(act_s + (kb * 8 + k4 * 2) * 1024, 32768, 1024), idesc, (kb | k4) != 0);
+              if (s == 1) {
+                if constexpr (CL == 1) mma_commit(&empty[st]);
+                else mma_commit_multicast(&empty[st], mask);
+              }
+              if (++st == TC_STAGES) { st = 0; ph ^= 1; }
+            }
+            if (s == 1) { stage = st; phase = ph; }
+            if (h == 1) tc_finish_subtile(act, acc_ready, s, img, ncb, cb0, pair, layer);
+          }
       }
+    }
+  }
 }
 
 template <int GC>
@@ -138,6 +203,29 @@ __device__ __forceinline__ void tc_load_group(uint32_t taddr, float* u) {
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(r[j]);
+}
+
+// split form for software pipelining: issue the TMEM loads of the NEXT column group, work on the current one,
+// then tc_ld_take() waits and hands the registers over
+template <int GC>
+struct TmemRegs {
+  uint32_t a[32];
+  uint32_t b[GC == 40 ? 8 : 1];
+};
+template <int GC>
+__device__ __forceinline__ void tc_ld_issue(uint32_t taddr, TmemRegs<GC>& r) {
+  umma::tmem_ld_x32(taddr, r.a);
+  if constexpr (GC == 40) umma::tmem_ld_x8(taddr + 32, r.b);
+}
+template <int GC>
+__device__ __forceinline__ void tc_ld_take(const TmemRegs<GC>& r, float* u) {
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(r.a[j]);
+  if constexpr (GC == 40) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[32 + j] = __uint_as_float(r.b[j]);
+  }
 }
 
 // stored pre-activations u -> stored activations, in place

@@ -67,25 +67,34 @@ __device__ __forceinline__ void tt_stash_group(const float* u, float* dst) {
   }
 }
 
+// the reverse sweep issues the loads of the NEXT group before it works on the current one (raw 16-byte registers)
 template <int NCH, int GC>
-__device__ __forceinline__ void tt_unstash_group(float* u, const float* src) {
+__device__ __forceinline__ void tt_stash_load(uint4* raw, const float* src) {
+#pragma unroll
+  for (int j = 0; j < Stash<NCH, GC>::CHUNKS; ++j) raw[j] = __ldcs(reinterpret_cast<const uint4*>(src + j * 1024));
+}
+
+template <int NCH, int GC>
+__device__ __forceinline__ void tt_unstash_group(float* u, const uint4* raw) {
   using S = Stash<NCH, GC>;
   if constexpr (NCH == 1) {
 #pragma unroll
     for (int j4 = 0; j4 < GC / 4; ++j4) {
-      const float4 t = *reinterpret_cast<const float4*>(src + j4 * 1024);
-      u[j4 * 4] = t.x; u[j4 * 4 + 1] = t.y; u[j4 * 4 + 2] = t.z; u[j4 * 4 + 3] = t.w;
+      const uint4 t = raw[j4];
+      u[j4 * 4] = __uint_as_float(t.x); u[j4 * 4 + 1] = __uint_as_float(t.y);
+      u[j4 * 4 + 2] = __uint_as_float(t.z); u[j4 * 4 + 3] = __uint_as_float(t.w);
     }
   } else {
 #pragma unroll
     for (int j4 = 0; j4 < S::NF4; ++j4) {
-      const float4 t = *reinterpret_cast<const float4*>(src + j4 * 1024);
-      u[(j4 * 4) * NCH] = t.x; u[(j4 * 4 + 1) * NCH] = t.y; u[(j4 * 4 + 2) * NCH] = t.z; u[(j4 * 4 + 3) * NCH] = t.w;
+      const uint4 t = raw[j4];
+      u[(j4 * 4) * NCH] = __uint_as_float(t.x); u[(j4 * 4 + 1) * NCH] = __uint_as_float(t.y);
+      u[(j4 * 4 + 2) * NCH] = __uint_as_float(t.z); u[(j4 * 4 + 3) * NCH] = __uint_as_float(t.w);
     }
     float d[S::NH8 * 8];
 #pragma unroll
     for (int c8 = 0; c8 < S::NH8; ++c8) {
-      const uint4 t = *reinterpret_cast<const uint4*>(src + (S::NF4 + c8) * 1024);
+      const uint4 t = raw[S::NF4 + c8];
       const __half2* hv = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -163,10 +172,13 @@ __device__ __forceinline__ void tt_fwd_pair(EpiCtx& e, const NetView& net, const
           tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), e.r7);
         }
       } else {
+        TmemRegs<C::GC> nxt;
+        tc_ld_issue<C::GC>(e.tmem_lane + s * 256, nxt);
 #pragma unroll 1
         for (int g = 0; g < C::NGRP; ++g) {
           float u[C::GC];
-          tc_load_group<C::GC>(e.tmem_lane + s * 256 + g * C::GC, u);
+          tc_ld_take<C::GC>(nxt, u);
+          if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(e.tmem_lane + s * 256 + (g + 1) * C::GC, nxt);
 #pragma unroll
           for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
           tt_stash_group<NCH, C::GC>(u, ust + (size_t)g * C::GC * 256);
@@ -209,6 +221,7 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = net.n_lin - 1;
   const int64_t npairs = sa.npairs + sb.npairs;
+  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // pairs of this CTA
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
@@ -221,11 +234,15 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    if (lane == 0) tc_producer(packed, ring, full, empty, npairs, L - 1, false);
-  } else if (warp == 9) {
-    if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Aimg, ld >> 6, col0 >> 6, false);
+  if (warp >= 8) {
+    setmaxnreg_dec<TC_REGS_AUX>();
+    if (warp == 8) {
+      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, false);
+    } else if (warp == 9) {
+      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, ld >> 6, col0 >> 6, false);
+    }
   } else {
+    setmaxnreg_inc<TC_REGS_EPI>();
     const int q = warp & 3, h = warp >> 2;
     EpiCtx e;
     e.act = act; e.xs = (float*)(smem + C::OFF_XS); e.os = (float*)(smem + C::OFF_OS); e.wl_s = wl_s;
@@ -254,15 +271,17 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
 // one column group: u (stash), ab (adjoints of the activations: seeds x output weights at the top, TMEM below) ->
 // adjoints of u, written to the B tile (layers > 0); accumulates the thread's gradient partial sums
 template <int NCH, int GC, bool TOP, bool FIRST>
-__device__ __forceinline__ void tt_bwd_group(const float* ust_g, uint32_t taddr, float wl, const float* sdg, const float* pts,
-                                             unsigned char* trow, int chunk0, uint32_t r7, float& bsum, float& wlsum, float (&w0s)[3]) {
+__device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr, uint32_t next_taddr, float wl, const float* sdg,
+                                             const float* pts, unsigned char* trow, int chunk0, uint32_t r7, float& bsum, float& wlsum,
+                                             float (&w0s)[3]) {
   float u[GC], ab[GC];
-  tt_unstash_group<NCH, GC>(u, ust_g);
+  tt_unstash_group<NCH, GC>(u, raw);
   if constexpr (TOP) {
 #pragma unroll
     for (int j = 0; j < GC; ++j) ab[j] = wl * sdg[j];
   } else {
-    tc_load_group<GC>(taddr, ab);
+    tc_ld_take<GC>(tr, ab);
+    if (next_taddr) tc_ld_issue<GC>(next_taddr, tr);           // next group's accumulators, in flight during the math
   }
 #pragma unroll
   for (int pp = 0; pp < GC / NCH; ++pp) {
@@ -327,23 +346,31 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
       unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
       const int64_t colt = colp + s * 128;
       const float* ust = Ust + ((size_t)l * ld + colt) * 256 + e.n * 4;
+      constexpr int NRAW = Stash<NCH, C::GC>::CHUNKS;
+      uint4 nxt[NRAW];
+      tt_stash_load<NCH, C::GC>(nxt, ust);                       // in flight while we wait for the accumulator
       if (!top) {
         mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
         e.acc_phase ^= 1u << s;
         tc_fence_after();
       }
       float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
+      TmemRegs<C::GC> tr;
+      if (!top) tc_ld_issue<C::GC>(e.tmem_lane + s * 256, tr);
 #pragma unroll 1
       for (int g = 0; g < C::NGRP; ++g) {
-        const float* ug = ust + (size_t)g * C::GC * 256;
-        const uint32_t taddr = e.tmem_lane + s * 256 + g * C::GC;
+        uint4 ug[NRAW];
+#pragma unroll
+        for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
+        if (g + 1 < C::NGRP) tt_stash_load<NCH, C::GC>(nxt, ust + (size_t)(g + 1) * C::GC * 256);
+        const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * C::GC : 0u;
         const float* sdg = sd + s * 256 + g * C::GC;
         const float* pts = e.xs + (s * C::PT + g * (C::GC / NCH)) * 3;
         const int c0 = g * (C::GC / 8);
-        if (top && first) tt_bwd_group<NCH, C::GC, true, true>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else if (top)     tt_bwd_group<NCH, C::GC, true, false>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else if (first)   tt_bwd_group<NCH, C::GC, false, true>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else              tt_bwd_group<NCH, C::GC, false, false>(ug, taddr, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        if (top && first) tt_bwd_group<NCH, C::GC, true, true>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (top)     tt_bwd_group<NCH, C::GC, true, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (first)   tt_bwd_group<NCH, C::GC, false, true>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else              tt_bwd_group<NCH, C::GC, false, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
       }
       atomicAdd(&grad.b[l][e.n], bsum * wl_cur * invS);
       if (top) atomicAdd(&grad.W[L][e.n], wlsum * invS);
@@ -376,6 +403,7 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = net.n_lin - 1;
   const int64_t npairs = sa.npairs + sb.npairs;
+  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // pairs of this CTA
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
@@ -387,11 +415,15 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    if (lane == 0) tc_producer(packed, ring, full, empty, npairs, L - 1, true);
-  } else if (warp == 9) {
-    if (lane == 0) tc_mma_role(act, ring, full, empty, act_ready, acc_ready, tmem_base, npairs, L - 1, Zimg, ld >> 6, col0 >> 6, true);
+  if (warp >= 8) {
+    setmaxnreg_dec<TC_REGS_AUX>();
+    if (warp == 8) {
+      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, true);
+    } else if (warp == 9) {
+      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Zimg, ld >> 6, col0 >> 6, true);
+    }
   } else {
+    setmaxnreg_inc<TC_REGS_EPI>();
     const int q = warp & 3, h = warp >> 2;
     EpiCtx e;
     e.act = act; e.xs = (float*)(smem + C::OFF_XS); e.os = (float*)(smem + C::OFF_OS); e.wl_s = nullptr;

@@ -42,6 +42,8 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.L.dudf_create(n_hidden, float(w0), float(ww), ctypes.byref(self.h)), "dudf_create")
         self._sig = None
+        self._fresh = 0
+        self._bound = None
 
     def __del__(self):
         try:
@@ -52,19 +54,26 @@ class Engine:
             pass
 
     # ---- weights ----
-    def sync_weights(self, weights, biases):
-        """Re-pack when any parameter changed (version counters / storage pointers)."""
+    def sync_weights(self, weights, biases, need=3):
+        """Bind the parameter tensors (zero copy) and rebuild the derived operand images that `need` asks for
+        (bit 1: fp32 transposes, bit 2: tensor-core fp16 images) when any parameter changed since they were built
+        (torch version counters / storage pointers; in-place updates behind torch's back must reset `_sig`)."""
         sig = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
-        if sig == self._sig:
-            return
-        ws = [w.detach() for w in weights]
-        bs = [b.detach() for b in biases]
-        for t in ws + bs:
-            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
-                raise RuntimeError("SIREN parameters must be contiguous float32 CUDA tensors")
-        with torch.cuda.device(self.device):
-            _lib.check(self.L.dudf_set_weights(self.h, _ptr_array(ws), _ptr_array(bs), _lib.current_stream()), "dudf_set_weights")
-        self._sig = sig
+        if sig != self._sig:
+            ws = [w.detach() for w in weights]
+            bs = [b.detach() for b in biases]
+            for t in ws + bs:
+                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                    raise RuntimeError("SIREN parameters must be contiguous float32 CUDA tensors")
+            _lib.check(self.L.dudf_bind_weights(self.h, _ptr_array(ws), _ptr_array(bs)), "dudf_bind_weights")
+            self._bound = (ws, bs)               # keep the storages alive while the library holds their pointers
+            self._sig = sig
+            self._fresh = 0
+        todo = need & ~self._fresh
+        if todo:
+            with torch.cuda.device(self.device):
+                _lib.check(self.L.dudf_refresh_weights(self.h, todo, _lib.current_stream()), "dudf_refresh_weights")
+            self._fresh |= todo
 
     # ---- queries ----
     def query(self, x, order, precision="fp32", flags=0, alpha=0.0):

@@ -40,7 +40,7 @@ class TrainCore:
         return t
 
     def plan(self, mode, P, n_on, w, prec):
-        eng = self.model._engine_synced()
+        eng = self.model._engine_synced(2 if prec == "tc16" else 1)
         if mode == "s1":
             base = 1 if (w[3] != 0 or w[2] != 0) else 0
             nh = n_on if w[2] != 0 else 0
@@ -72,8 +72,8 @@ class TrainCore:
     def forward(self, mode, x, normals, d, n_on, w, alpha, P_global=None, stats_reduce=None):
         """Returns a (4,) float64 device tensor with this rank's share of the loss terms."""
         m = self.model
-        eng = m._engine_synced()
         prec = self._prec()
+        eng = m._engine_synced(2 if prec == "tc16" else 1)
         P = x.shape[0]
         P_global = P if P_global is None else P_global
         segs, ld, nout = self.plan(mode, P, n_on, w, prec)
@@ -105,10 +105,10 @@ class TrainCore:
         if p is None:
             raise RuntimeError("TrainCore.backward without a pending forward")
         m = self.model
-        eng = m._engine_synced()
+        prec = p["prec"]
+        eng = m._engine_synced(2 if prec == "tc16" else 1)
         if eng._sig != p["sig"]:
             raise RuntimeError("SIREN parameters changed between the loss forward and backward")
-        prec = p["prec"]
         seeds = self._buf("seeds", tuple(p["packed"].shape))
         absmax = torch.zeros(1, device=p["x"].device, dtype=torch.float32) if prec == "tc16" else None
         for s in p["segs"]:                 # all seeds (and their magnitude) before the first reverse sweep

@@ -207,14 +207,15 @@ class SIREN(nn.Module):
             out += [self.net[i][0].weight, self.net[i][0].bias]
         return out
 
-    def _engine_synced(self):
+    def _engine_synced(self, need=3):
+        """The native engine with the weight images `need`ed up to date (1: fp32 path, 2: tensor-core path, 3: both)."""
         ws, bs = self._weights_biases()
         dev = ws[0].device
         if dev.type != "cuda":
             raise RuntimeError("diffudf_b200.SIREN has no CPU path: move the module to a CUDA (sm_100) device")
         if self._engine is None or self._engine.device != dev:
             self._engine = Engine(self.n_hidden, self.w0, self.ww, dev)
-        self._engine.sync_weights(ws, bs)
+        self._engine.sync_weights(ws, bs, need)
         return self._engine
 
     def forward(self, x):

@@ -46,6 +46,13 @@ int dudf_destroy(dudf_ctx* ctx);
 /* W_host[i] / b_host[i] (HOST arrays of n_hidden+1 DEVICE pointers) use the nn.Linear layout of the
  * state_dict keys net.{i}.0.weight / net.{i}.0.bias.  Copies and re-packs the operand images. */
 int dudf_set_weights(dudf_ctx* ctx, const float* const* W_host, const float* const* b_host, void* stream);
+/* Zero-copy variant for callers that keep the parameters alive (the Python module does): dudf_bind_weights records the
+ * device pointers, dudf_refresh_weights rebuilds the derived operand images after the parameters changed
+ * (optimizer.step()): the fp32 transposes used by the CUDA-core forward and / or the fp16 tensor-core images. */
+#define DUDF_REFRESH_FP32 1
+#define DUDF_REFRESH_TC16 2
+int dudf_bind_weights(dudf_ctx* ctx, const float* const* W_host, const float* const* b_host);
+int dudf_refresh_weights(dudf_ctx* ctx, int what, void* stream);
 
 /* Field query at arbitrary points: SIREN.forward + diff_operators.gradient / hessian
  * (src/model.py:116-135, src/diff_operators.py:187-212) and the third derivatives that
