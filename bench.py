@@ -123,6 +123,74 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def aux_full_size_queries(dev):
+    """BASELINE configs 3-5 at full size on one GPU (tensor-core path, trained fixture weights when present):
+    512^3 grid for marching cubes, evaluate() with host buffers, 1024^2 sphere tracing, 2 M-point NDF projection."""
+    import numpy as np
+    import torch
+    from diffudf_b200 import SIREN, evaluate, render_st
+    from diffudf_b200.render_mc import extract_fields
+    from diffudf_b200.render_pc import Sampler
+    out = {}
+    m = SIREN(3, 1, [256] * 8, w0=30).to(dev)
+    wpath = os.path.join(ROOT, "tests", "golden", "weights_trained.npz")
+    if os.path.exists(wpath):
+        z = np.load(wpath)
+        m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(z[f"{c}{i}"]) for i in range(9) for k, c in (("weight", "W"), ("bias", "b"))})
+        m.to(dev)
+    m.precision = "tc16"
+
+    def timed(fn, reps=1):
+        fn()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            r = fn()
+        t.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(t) * 1e-3 / reps, r
+
+    sec, _ = timed(lambda: extract_fields(m, None, 512, "tanh", dev, ALPHA))
+    out["grid512_extract_fields_tc16_queries_per_s"] = 512 ** 3 / sec
+    out["grid512_extract_fields_tc16_s"] = sec
+    # evaluate(): host numpy in, float64 host arrays out (value + gradient), 2 M points
+    xs = np.random.default_rng(0).uniform(-1, 1, (2_000_000, 3)).astype(np.float32)
+    grads = np.zeros((xs.shape[0], 3))
+    t0 = time.perf_counter()
+    evaluate(m, xs, device=dev, gradients=grads, max_batch=1 << 20)
+    out["evaluate_host_2M_value_grad_queries_per_s"] = xs.shape[0] / (time.perf_counter() - t0)
+    # NDF projection (config 5): 2 M seeds, 3 steps (2 gradient queries + 1 Hessian query per point)
+    smp = Sampler(decoder=m, device=dev)
+    seeds = torch.from_numpy(xs.astype(np.float64)).to(dev)
+    sec, _ = timed(lambda: smp.project(seeds, "tanh", ALPHA, 3))
+    out["project_2M_x3steps_points_per_s"] = xs.shape[0] / sec
+    for p in m.parameters():
+        p.requires_grad_(True)
+    # sphere tracing 1024 x 1024 (config 4) + eigen-normals and mean curvature at the hits
+    R = 1024
+    cam = np.array([0.8939, 0.7, 2.86]) * 0.45
+    u, v = np.meshgrid(np.linspace(-0.6, 0.6, R), np.linspace(-0.6, 0.6, R))
+    d = np.stack([u.ravel(), v.ravel(), -np.ones(R * R)], 1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    fwd = -cam / np.linalg.norm(cam)
+    right = np.cross(fwd, [0, 1.0, 0]); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    rays = d[:, :1] * right + d[:, 1:2] * up - d[:, 2:3] * fwd
+    start = np.tile(cam, (R * R, 1)) + rays * 0.35
+    rays_d = torch.from_numpy(rays).to(dev)
+    t0_d = torch.from_numpy(start).to(dev)
+    idx = torch.arange(R * R, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hits, _, nq = render_st._march(m, rays_d, t0_d.clone(), idx, "tanh", ALPHA, 0.004, 100)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    out["sphere_trace_1024_rays_per_s"] = R * R / sec
+    out["sphere_trace_1024_value_queries_per_s"] = nq / sec
+    out["sphere_trace_1024_hit_fraction"] = float(hits.float().mean())
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -248,6 +316,11 @@ def run_ours(args, rank, local_rank, world):
             q = 3 * cnt / (s.elapsed_time(t) * 1e-3)
             aux[f"grid{N}_{prec}_queries_per_s"] = q
             aux[f"grid{N}_{prec}_tflops"] = q * F[4] / 1e12
+        del df, vecs
+        try:
+            aux.update(aux_full_size_queries(dev))
+        except Exception as exc:          # the secondary numbers must never cost the headline line
+            aux["full_size_error"] = repr(exc)[:200]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

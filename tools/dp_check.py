@@ -43,6 +43,19 @@ for prec, tol in (("fp32", 2e-4), ("tc16", 2e-2)):
             et = float(((t - t1).abs() / t1.abs().clamp_min(1e-6)).max())
             print(f"{prec} {mode}: grad err {eg:.2e} terms err {et:.2e}", flush=True)
             ok = ok and eg < tol and et < 1e-3
+# grid query sharded by contiguous ranges of the flat index + all-gather == the single-GPU grid, bit for bit
+from diffudf_b200.parallel import extract_fields_sharded  # noqa: E402
+from diffudf_b200.render_mc import extract_fields  # noqa: E402
+torch.manual_seed(123)
+mg = SIREN(3, 1, [256] * 8, w0=30).cuda()
+for prec in ("fp32", "tc16"):
+    mg.precision = prec
+    df, vecs = extract_fields_sharded(mg, 45, "tanh", 100.0, DataParallel())
+    if rank == 0:
+        df1, v1 = extract_fields(mg, None, 45, "tanh", torch.device("cuda", local), 100.0)
+        same = bool(torch.equal(df, df1) and torch.equal(vecs, v1))
+        print(f"{prec} sharded grid identical: {same}", flush=True)
+        ok = ok and same
 dist.barrier()
 if rank == 0:
     print("DP_CHECK_OK" if ok else "DP_CHECK_FAILED", flush=True)
