@@ -74,19 +74,69 @@ class FusedTrainer:
         return terms
 
 
+class BatchFeeder:
+    """Double-buffered host -> device feed of (coords, normals, dist) batches: the copy of batch i+1 runs on a side
+    stream while step i computes (the reference copies synchronously inside the loop, train.py:200-202).
+    Host tensors should be pinned for the copies to be asynchronous."""
+
+    def __init__(self, device, n_buffers=2):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.n = n_buffers
+        self.bufs = [None] * n_buffers
+        self.ready = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.free = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.i = 0
+
+    def _stage(self, slot, batch):
+        x, n, d = batch
+        shapes = ((x.numel() // 3, 3), (n.numel() // 3, 3), (d.numel(),))
+        if self.bufs[slot] is None or any(b.shape != s for b, s in zip(self.bufs[slot], shapes)):
+            self.bufs[slot] = tuple(torch.empty(s, device=self.device, dtype=torch.float32) for s in shapes)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])        # the step that used this buffer has been enqueued and finished
+            for dst, src in zip(self.bufs[slot], (x, n, d)):
+                dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def feed(self, batches):
+        """Yields device batches (x (P,3), normals (P,3), dist (P,)); call `release()` semantics are automatic:
+        a buffer is recycled after the NEXT yielded batch's step has been enqueued."""
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        slot = self.i % self.n
+        self._stage(slot, nxt)
+        while True:
+            cur_slot = slot
+            try:
+                nxt = next(it)
+                slot = (cur_slot + 1) % self.n
+                self._stage(slot, nxt)
+                more = True
+            except StopIteration:
+                more = False
+            torch.cuda.current_stream(self.device).wait_event(self.ready[cur_slot])
+            yield self.bufs[cur_slot]
+            self.free[cur_slot].record(torch.cuda.current_stream(self.device))
+            self.i += 1
+            if not more:
+                return
+
+
 def _epoch_loop(dataset, model, device, config, stage_fn):
     epochs = config["epochs"]
-    trainer = FusedTrainer(model.to(device), dp=config.get("dp"))
+    trainer = FusedTrainer(model.to(device), dp=config.get("dp"), precision=config.get("precision"))
+    feeder = BatchFeeder(device)
     losses, best_loss, best_weights = {}, np.inf, None
     torch.cuda.synchronize(device)
     start = time.time()
     for epoch in range(epochs):
         mode, keys, weights, lr = stage_fn(epoch)
         running = torch.zeros(4, device=device, dtype=torch.float64)
-        for input_data, normals, sdf in iter(dataset):
-            x = input_data.to(device).reshape(-1, 3).float().contiguous()
-            n = normals.to(device).reshape(-1, 3).float().contiguous()
-            d = sdf.to(device).reshape(-1).float().contiguous()
+        for x, n, d in feeder.feed((tuple(torch.as_tensor(t, dtype=torch.float32) for t in b) for b in iter(dataset))):
             n_on = getattr(dataset, "samplesOnSurface", None)
             if n_on is None and mode == "s1" and weights[2] != 0:
                 from .loss_functions import on_surface_prefix

@@ -1,0 +1,87 @@
+"""The public training loops (train_model_tanh / train_model_siren, BatchFeeder, FusedTrainer) against the drop-in
+route the reference's own loop takes (loss_fn -> backward -> torch.optim.Adam.step, train.py:195-222)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class TinyDataset:
+    """Same iteration protocol as the reference's PointCloud dataset (src/dataset.py:134-185)."""
+
+    def __init__(self, batches, n_on):
+        self.batches = batches
+        self.batchesPerEpoch = len(batches)
+        self.samplesOnSurface = n_on
+
+    def __iter__(self):
+        for x, n, d in self.batches:
+            yield torch.from_numpy(x), torch.from_numpy(n), torch.from_numpy(d)
+
+
+def _make(weights, n_batches=2, rows=1500):
+    from diffudf_b200 import SIREN, synthetic
+    shape = synthetic.make_shape(0)
+    sp, sn = shape.sample_surface(20000, np.random.default_rng(0))
+    batches = [synthetic.make_batch(shape, sp, sn, rows, (0.333, 0.666), np.random.default_rng(40 + i)) for i in range(n_batches)]
+    m = SIREN(3, 1, [256] * 8, w0=30, delay_init=True)
+    m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(v) for i, (W, b) in enumerate(weights["trained"])
+                       for k, v in (("weight", W), ("bias", b))})
+    return m.cuda(), batches, int(rows * 0.333)
+
+
+def test_fused_loop_matches_dropin_adam_loop(weights):
+    import diffudf_b200 as D
+    from diffudf_b200.train import train_model_tanh
+    cfg = dict(epochs=3, s1_epochs=2, warmup_epochs=1, warmup_lr=1e-5, lr_s1=1e-6, lr_s2=1e-7, loss_s1_weights=[1e4, 1e4, 1e4, 1e3],
+               loss_s2_weights=[1e5, 1e5], alpha=100.0)
+    m1, batches, n_on = _make(weights)
+    losses, best, seconds = train_model_tanh(TinyDataset(batches, n_on), m1, torch.device("cuda:0"), cfg)
+    assert set(losses) == {"sdf_on_surf", "sdf_off_surf", "hessian_constraint", "grad_constraint", "std_on_surf"}
+    assert all(len(v) == 3 for v in losses.values()) and best is not None and seconds > 0
+    # the reference-style loop on the drop-in surface
+    m2, _, _ = _make(weights)
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-5)
+    ref = {k: [0.0] * 3 for k in losses}
+    for epoch in range(3):
+        lr = 1e-5 if epoch < 1 else (1e-6 if epoch < 2 else 0.5 * (np.cos(epoch / 1 * np.pi) + 1) * 1e-7)
+        for g in opt.param_groups:
+            g["lr"] = lr
+        for x, n, d in batches:
+            opt.zero_grad()
+            gt = {"normals": torch.from_numpy(n).cuda(), "sdf": torch.from_numpy(d).cuda()}
+            loss = (D.loss_s1(m2, torch.from_numpy(x).cuda(), gt, cfg["loss_s1_weights"], 100.0) if epoch < 2
+                    else D.loss_s2(m2, torch.from_numpy(x).cuda(), gt, cfg["loss_s2_weights"], 100.0))
+            tot = 0
+            for k, v in loss.items():
+                tot = tot + v
+                ref[k][epoch] += float(v.detach())
+            tot.backward()
+            opt.step()
+    for k in losses:
+        assert np.allclose(losses[k], ref[k], rtol=2e-3, atol=1e-3), (k, losses[k], ref[k])
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(p1, p2, rtol=0, atol=3e-5)          # 5 Adam steps of <= 1e-5 each
+
+
+def test_siren_loop_and_tc16_precision_run(weights):
+    from diffudf_b200.train import train_model_siren
+    m, batches, n_on = _make(weights, n_batches=1)
+    cfg = dict(epochs=2, loss_weights=[3e3, 1e2, 1e2, 5e1], lr=1e-5, precision="tc16")
+    losses, best, _ = train_model_siren(TinyDataset(batches, n_on), m, torch.device("cuda:0"), cfg)
+    assert set(losses) == {"sdf_on_surf", "sdf_off_surf", "normal_constraint", "grad_constraint"}
+    assert all(np.isfinite(v).all() for v in losses.values())
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+def test_batch_feeder_preserves_order_and_content():
+    from diffudf_b200.train import BatchFeeder
+    feeder = BatchFeeder(torch.device("cuda:0"))
+    batches = [(torch.full((7, 3), float(i)).pin_memory(), torch.full((7, 3), float(-i)).pin_memory(), torch.full((7,), float(10 * i)).pin_memory())
+               for i in range(9)]
+    seen = []
+    for x, n, d in feeder.feed(batches):
+        seen.append((float(x[3, 1]), float(n[0, 2]), float(d[6])))
+    assert seen == [(float(i), float(-i), float(10 * i)) for i in range(9)]
+    assert list(feeder.feed([])) == []
