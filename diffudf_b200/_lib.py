@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
 SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_misc.cu"]
-HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh",
+HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh",
            os.path.join(ROOT, "include", "dudf_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
@@ -30,11 +30,21 @@ class Segment(ctypes.Structure):
     _fields_ = [("x", c_void_p), ("rows", c_int64), ("order", c_int), ("packed", c_void_p), ("seeds", c_void_p), ("col0", c_int64)]
 
 
+class TrainSegment(ctypes.Structure):
+    """struct dudf_train_segment of include/dudf_b200.h"""
+    _fields_ = [("x", c_void_p), ("normals", c_void_p), ("dist", c_void_p), ("rows", c_int64), ("order", c_int), ("packed", c_void_p)]
+
+
 # name -> (argtypes) ; every function returns int except the two noted below
 SIGNATURES = {
     "dudf_jet_forward_multi": [c_void_p, ctypes.POINTER(Segment), c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "dudf_jet_backward_multi": [c_void_p, ctypes.POINTER(Segment), c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                 ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_void_p],
+    "dudf_fused_scratch_bytes": [c_void_p],
+    "dudf_train_step_fused": [c_void_p, c_int, ctypes.POINTER(TrainSegment), c_int, c_int64, ctypes.POINTER(c_float), c_float, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(c_void_p),
+                              ctypes.POINTER(c_void_p), c_int, c_void_p],
+    "dudf_bench_umma": [c_int, c_int, c_int, ctypes.POINTER(c_float)],
     "dudf_version": [],
     "dudf_launch_count": [],
     "dudf_create": [c_int, c_float, c_float, ctypes.POINTER(c_void_p)],
@@ -114,7 +124,7 @@ def lib():
             for name, args in SIGNATURES.items():
                 fn = getattr(L, name)
                 fn.argtypes = args
-                fn.restype = c_int64 if name in ("dudf_stash_columns", "dudf_launch_count") else c_int
+                fn.restype = c_int64 if name in ("dudf_stash_columns", "dudf_launch_count", "dudf_fused_scratch_bytes") else c_int
             L.dudf_last_error.argtypes = []
             L.dudf_last_error.restype = ctypes.c_char_p
             _lib = L

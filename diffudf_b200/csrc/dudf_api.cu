@@ -365,6 +365,39 @@ int dudf_jet_wgrad(dudf_ctx* c, const void* Zb, const void* A, int64_t ld, int64
   return simt_wgrad(c->view(), gv, (const float*)Zb, (const float*)A, ld, ncols, c->sms, (cudaStream_t)stream);
 }
 
+int64_t dudf_fused_scratch_bytes(const dudf_ctx* c) {
+  if (!c) return -1;
+  return (int64_t)tc_fused_scratch_bytes(c->view(), c->sms);
+}
+
+int dudf_train_step_fused(dudf_ctx* c, int mode, const dudf_train_segment* segs, int nseg, int64_t P_global, const float* w_host, float alpha,
+                          double* terms, const float* amax_prev, float* amax_next, void* scratch, void* A, void* Zb, int64_t ld,
+                          float* const* gW, float* const* gb, int flags, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_train_step_fused: weights not set");
+  DUDF_REQUIRE(segs && nseg >= 1 && nseg <= 2 && w_host && terms && amax_prev && amax_next && scratch && A && Zb && gW && gb,
+               "dudf_train_step_fused: null argument");
+  DUDF_REQUIRE(P_global > 0, "dudf_train_step_fused: P_global must be positive");
+  GradView gv;
+  int rc = fill_grad_view(c, gW, gb, gv, "dudf_train_step_fused");
+  if (rc) return rc;
+  TcSegment ts[2];
+  for (int i = 0; i < nseg; ++i) {
+    const dudf_train_segment& s = segs[i];
+    DUDF_REQUIRE(s.rows > 0 && s.x && s.normals && s.dist, "dudf_train_step_fused: empty or null segment");
+    DUDF_REQUIRE(s.order == 1 || s.order == 2, "dudf_train_step_fused: order %d (1 or 2)", s.order);
+    DUDF_REQUIRE(i == 0 || segs[0].order == 2, "dudf_train_step_fused: Hessian segment first");
+    ts[i] = TcSegment{s.x, s.rows, order_to_nch(s.order), s.packed, nullptr, s.normals, s.dist};
+  }
+  TcFusedLoss fl;
+  fl.mode = mode; fl.alpha = alpha; fl.P_global = P_global; fl.terms = terms; fl.amax_prev = amax_prev; fl.amax_next = amax_next;
+  fl.flags = flags;
+  for (int k = 0; k < 4; ++k) fl.w[k] = w_host[k];
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = tc_train_fused(c->tc_packed, c->view(), gv, ts, nseg, fl, (float*)scratch, A, Zb, ld, c->sms, st);
+  if (rc) return rc;
+  return tc_train_wgrad(c->view(), gv, Zb, A, ld, amax_prev, c->sms, st);
+}
+
 int dudf_loss(int mode, const float* packed, int nch, const float* normals, const float* dist, int64_t P, int64_t P_global,
               const float* w_host, float alpha, const float* upstream, float* seeds, float* seed_absmax, double* terms,
               double* s2_stats, void* stream) {
@@ -400,6 +433,11 @@ int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
 int dudf_selftest_umma(int variant, float* max_err_host) {
   DUDF_REQUIRE(max_err_host != nullptr, "dudf_selftest_umma: null output");
   return tc_selftest(variant, max_err_host, 0);
+}
+
+int dudf_bench_umma(int variant, int ctas, int iters, float* clk_per_mma_host) {
+  DUDF_REQUIRE(clk_per_mma_host != nullptr, "dudf_bench_umma: null output");
+  return tc_mma_bench(variant, ctas, iters, clk_per_mma_host, 0);
 }
 
 }  // extern "C"

@@ -35,6 +35,7 @@ int tc_pack(const NetView& net, void* packed, cudaStream_t st);
 int tc_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN,
                int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
 int tc_selftest(int variant, float* max_err, cudaStream_t st);
+int tc_mma_bench(int variant, int ctas, int iters, float* clk_host, cudaStream_t st);
 
 // ---- loss epilogues, optimiser, utilities (dudf_misc.cu) ----
 struct LossArgs {
@@ -62,7 +63,22 @@ struct TcSegment {          // one row segment of a training batch (consecutive 
   int nch;
   float* packed;            // forward: [rows][nch] raw channels out
   const float* seeds;       // backward: [rows][nch]
+  const float* normals;     // fused step: [rows][3]
+  const float* dist;        // fused step: [rows]
 };
+struct TcFusedLoss {        // loss configuration of the fused step (dudf_tc_train.cu)
+  int mode;                 // DUDF_LOSS_S1 or DUDF_LOSS_SIREN
+  float w[4];
+  float alpha;
+  int64_t P_global;
+  double* terms;            // [4] accumulated
+  const float* amax_prev;   // max|stored seed| of the previous step (loss scale)
+  float* amax_next;         // this step's, raised with atomicMax
+  int flags;                // DUDF_FUSED_* tuning bits
+};
+size_t tc_fused_scratch_bytes(const NetView& net, int sms);
+int tc_train_fused(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg, const TcFusedLoss& fl,
+                   float* scratch, void* Aimg, void* Zimg, int64_t ld, int sms, cudaStream_t st);
 int tc_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld,
                      int64_t col0, int sms, cudaStream_t st);
 int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg,

@@ -2,11 +2,9 @@
 // curvature, the extract_fields fallback and small utilities.  All HBM-bound, one thread per row.
 #include "dudf_common.cuh"
 #include "dudf_kernels.h"
+#include "dudf_loss.cuh"
 
 namespace dudf {
-
-__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
-__device__ __forceinline__ double sgnd(double x) { return (double)((x > 0.0) - (x < 0.0)); }
 
 template <int N>
 __device__ __forceinline__ void block_reduce_add(double (&v)[N], double* dst) {
@@ -41,94 +39,25 @@ __global__ void __launch_bounds__(256) loss_seed_kernel(LossArgs a) {
     const float f = v[0];
     const float d = a.dist[p];
     const bool on = (d == 0.f);
-    const float up0 = a.upstream ? a.upstream[0] : 1.f, up1 = a.upstream ? a.upstream[1] : 1.f;
-    const float up2 = a.upstream ? a.upstream[2] : 1.f, up3 = a.upstream ? a.upstream[3] : 1.f;
-    const float invP = 1.0f / (float)a.P_global;
     float sd[10];
 #pragma unroll
     for (int c = 0; c < 10; ++c) sd[c] = 0.f;
-    if (a.mode == DUDF_LOSS_S1) {
-      const float th = tanhf(a.alpha * d);
-      const float tdf = d * th;
-      if (on) {
-        t[0] = fabsf(f);
-        sd[0] = up0 * a.w[0] * invP * sgnf(f);
-      } else {
-        t[1] = fabsf(tdf - f);
-        sd[0] = -up1 * a.w[1] * invP * sgnf(tdf - f);
-      }
-      if (a.w[3] != 0.f && nch >= 4) {
-        const float gx = v[1], gy = v[2], gz = v[3];
-        const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
-        const float tgt = fabsf(th + d * a.alpha * (1.f - th * th));
-        t[3] = fabsf(gn - tgt);
-        if (gn > 0.f) {
-          const float k = up3 * a.w[3] * invP * sgnf(gn - tgt) / gn;
-          sd[1] = k * gx; sd[2] = k * gy; sd[3] = k * gz;
-        }
-      }
-      if (a.w[2] != 0.f && nch >= 10 && on) {
-        double H[3][3], lam[3], V[3][3];
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) H[i][j] = (double)v[4 + sym2(i, j)];
-        eigh3<double>(H, lam, V);
-        const double n0 = a.normals[p * 3], n1 = a.normals[p * 3 + 1], n2 = a.normals[p * 3 + 2];
-        const double nn = fmax(sqrt(n0 * n0 + n1 * n1 + n2 * n2), 1e-8);
-        const double vx = V[0][2], vy = V[1][2], vz = V[2][2];
-        const double vn = fmax(sqrt(vx * vx + vy * vy + vz * vz), 1e-8);
-        const double cs = (n0 * vx + n1 * vy + n2 * vz) / (nn * vn);
-        t[2] = 1.0 - fabs(cs);
-        const double coef = -(double)up2 * a.w[2] * invP * sgnd(cs);
-        const double nb[3] = {coef * (n0 / (nn * vn) - cs * vx / (vn * vn)), coef * (n1 / (nn * vn) - cs * vy / (vn * vn)),
-                              coef * (n2 / (nn * vn) - cs * vz / (vn * vn))};
-        double Hb[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        const double vv[3] = {vx, vy, vz};
-        for (int j = 0; j < 2; ++j) {
-          const double cj = (V[0][j] * nb[0] + V[1][j] * nb[1] + V[2][j] * nb[2]) / (lam[2] - lam[j]);
-          for (int r = 0; r < 3; ++r)
-            for (int q = 0; q < 3; ++q) Hb[r][q] += cj * 0.5 * (V[r][j] * vv[q] + vv[r] * V[q][j]);
-        }
-        for (int i = 0; i < 3; ++i)
-          for (int j = i; j < 3; ++j) sd[4 + sym2(i, j)] = (float)((i == j) ? Hb[i][i] : Hb[i][j] + Hb[j][i]);
-      }
-      t[0] *= a.w[0] * (double)invP; t[1] *= a.w[1] * (double)invP;
-      t[2] *= a.w[2] * (double)invP; t[3] *= a.w[3] * (double)invP;
-    } else if (a.mode == DUDF_LOSS_SIREN) {
-      if (on) {
-        t[0] = fabsf(f);
-        sd[0] = up0 * a.w[0] * invP * sgnf(f);
-      } else {
-        const float e = expf(-1e2f * fabsf(f));
-        t[1] = e;
-        sd[0] = up1 * a.w[1] * invP * (-1e2f) * sgnf(f) * e;
-      }
-      const float gx = v[1], gy = v[2], gz = v[3];
-      const float gr = sqrtf(gx * gx + gy * gy + gz * gz);
-      const float gn = fmaxf(gr, 1e-8f);
-      if (on) {
-        const float n0 = a.normals[p * 3], n1 = a.normals[p * 3 + 1], n2 = a.normals[p * 3 + 2];
-        const float nn = fmaxf(sqrtf(n0 * n0 + n1 * n1 + n2 * n2), 1e-8f);
-        const float cs = (gx * n0 + gy * n1 + gz * n2) / (gn * nn);
-        t[2] = 1.f - cs;
-        const float k = -up2 * a.w[2] * invP;
-        sd[1] = k * (n0 / (gn * nn) - cs * gx / (gn * gn));
-        sd[2] = k * (n1 / (gn * nn) - cs * gy / (gn * gn));
-        sd[3] = k * (n2 / (gn * nn) - cs * gz / (gn * gn));
-      }
-      t[3] = (double)(gr - 1.f) * (double)(gr - 1.f);
-      if (gr > 0.f) {
-        const float k = up3 * a.w[3] * invP * 2.f * (gr - 1.f) / gr;
-        sd[1] += k * gx; sd[2] += k * gy; sd[3] += k * gz;
-      }
-      t[0] *= a.w[0] * (double)invP; t[1] *= a.w[1] * (double)invP;
-      t[2] *= a.w[2] * (double)invP; t[3] *= a.w[3] * (double)invP;
+    if (a.mode != DUDF_LOSS_S2) {
+      LossRowCfg cfg;
+      cfg.mode = a.mode; cfg.alpha = a.alpha; cfg.invP = 1.0f / (float)a.P_global;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { cfg.w[k] = a.w[k]; cfg.up[k] = a.upstream ? a.upstream[k] : 1.f; }
+      float vv[10];
+#pragma unroll
+      for (int c = 0; c < 10; ++c) vv[c] = (c < nch) ? v[c] : 0.f;
+      loss_row(cfg, nch, vv, d, a.normals ? a.normals + p * 3 : nullptr, t, sd);
     } else {  // S2: seeds from the global statistics
       if (on && a.s2_stats) {
         const double n = a.s2_stats[0], s1 = a.s2_stats[1], s2 = a.s2_stats[2];
         const double mean = s1 / n;
         const double var = (s2 - n * mean * mean) / (n - 1.0);
         const double sdv = sqrt(var);
-        sd[0] = (float)(up0 * a.w[0] * sgnd(mean) / n + up1 * a.w[1] * ((double)f - mean) / ((n - 1.0) * sdv));
+        sd[0] = (float)((a.upstream ? a.upstream[0] : 1.f) * a.w[0] * sgnd(mean) / n + (a.upstream ? a.upstream[1] : 1.f) * a.w[1] * ((double)f - mean) / ((n - 1.0) * sdv));
       }
     }
     if (a.seeds) {

@@ -61,7 +61,7 @@ int tc_pack(const NetView& net, void* packed, cudaStream_t st) {
 
 // CL = thread-block cluster size: the CTAs of a cluster share every weight chunk fetched from L2 (multicast), which
 // divides the L2 -> SM weight traffic (the measured limiter of this kernel at CL = 1, tools/pipe_probe.py) by CL.
-template <int NCH, int CL>
+template <int NCH, int CL, bool RU>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, int gridN,
                   int64_t grid_first, QueryOut out) {
@@ -103,9 +103,9 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   if (warp >= 8) {
     setmaxnreg_dec<TC_REGS_AUX>();                          // warpgroup 2 hands its registers to the epilogue warpgroups
     if (warp == 8) {
-      if (lane == 0) tc_producer<CL, true>(packed, ring, full, empty, rounds, L - 1, false, CL > 1 ? cluster_ctarank() : 0u);
+      if (lane == 0) tc_producer<CL, RU>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD, CL > 1 ? cluster_ctarank() : 0u, CL > 1 ? 0 : (int)(out.flags >> 8));
     } else if (warp == 9) {
-      if (lane == 0) tc_mma_role<CL, true>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, 0, 0, false, out.flags >> 8);
+      if (lane == 0) tc_mma_role<CL, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -207,11 +207,11 @@ static int tc_cluster_size() {
   return g_tc_cluster;
 }
 
-template <int NCH, int CL>
+template <int NCH, int CL, bool RU = true>
 static int tc_launch(const void* packed, const NetView& net, const float* x, int64_t P, int gridN, int64_t first,
                      const QueryOut& out, int sms, cudaStream_t st) {
   using C = TcCfg<NCH>;
-  auto k = tc_forward_kernel<NCH, CL>;
+  auto k = tc_forward_kernel<NCH, CL, RU>;
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
   int grid = (int)std::min<int64_t>(npairs, sms);
@@ -244,6 +244,8 @@ static int tc_launch_cl(const void* packed, const NetView& net, const float* x, 
   while (cl > 1 && npairs < 2 * cl) cl >>= 1;              // tiny queries: no point in pairing CTAs
   if (cl == 4) return tc_launch<NCH, 4>(packed, net, x, P, gridN, first, out, sms, st);
   if (cl == 2) return tc_launch<NCH, 2>(packed, net, x, P, gridN, first, out, sms, st);
+  static const bool no_reuse = getenv("DUDF_TC_REUSE") && atoi(getenv("DUDF_TC_REUSE")) == 0;   // diagnostics: ping-pong order, CL = 1
+  if (no_reuse) return tc_launch<NCH, 1, false>(packed, net, x, P, gridN, first, out, sms, st);
   return tc_launch<NCH, 1>(packed, net, x, P, gridN, first, out, sms, st);
 }
 
@@ -361,6 +363,81 @@ int tc_selftest(int variant, float* max_err, cudaStream_t st) {
       if (e > worst) worst = e;
     }
   *max_err = (float)worst;
+  return 0;
+}
+
+// =============================================================================================
+// tensor-pipe micro-benchmark (tools/umma_bench.py): one thread per CTA issues `iters` x 16 back-to-back
+// tcgen05.mma (K = 16 each) on resident shared-memory operands, alternating between two accumulators, and reports
+// clocks per instruction.  Results are meaningless numerically; only the issue/operand-fetch rate matters.
+//   variant 0: A K-major, B MN-major, N = 128 (the chain kernels)   1: A, B K-major, N = 128
+//   variant 2: A K-major, B MN-major, N = 256                        3: A, B K-major, N = 256
+//   variant 4: A in TMEM, B K-major, N = 256                         5: A in TMEM, B K-major, N = 128
+// =============================================================================================
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int variant, int iters, float* __restrict__ clk_per_mma) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid * 16; i < 196608; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (tid == 0) {
+    const int N = (variant == 2 || variant == 3 || variant == 4) ? 256 : 128;
+    const bool b_mn = (variant == 0 || variant == 2), a_tmem = (variant >= 4);
+    const uint32_t idesc = make_idesc_f16(128, N, 0, 0, b_mn ? 1 : 0);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 65536);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem_base + (a_tmem ? 0 : (uint32_t)(it & 1) * (N == 256 ? 256 : 128));
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        const uint64_t bd = b_mn ? make_desc_sw128(b0 + ks * 2048, 32768, 1024)
+                                 : make_desc_sw128(b0 + (ks >> 2) * (N * 128) + (ks & 3) * 32, 16, 1024);
+        if (a_tmem) mma_f16_ts(d, tmem_base + 256 + ks * 8, bd, idesc, ks != 0);
+        else mma_f16_ss(d, make_desc_sw128(a0 + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), bd, idesc, ks != 0);
+      }
+    }
+    mma_commit(&bar);
+    mbar_wait(&bar, 0, 0xA00);
+    const long long t1 = clock64();
+    clk_per_mma[blockIdx.x] = (float)(t1 - t0) / (float)(iters * 16);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+int tc_mma_bench(int variant, int ctas, int iters, float* clk_host, cudaStream_t st) {
+  DUDF_REQUIRE(variant >= 0 && variant <= 5 && ctas >= 1 && ctas <= 1024 && iters >= 1, "umma bench: bad arguments");
+  float* d = nullptr;
+  DUDF_CUDA_OK(cudaMalloc(&d, ctas * sizeof(float)));
+  const int smem = 196608 + 1024;
+  DUDF_CUDA_OK(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_mma_bench_kernel<<<ctas, 128, smem, st>>>(variant, iters, d);
+  DUDF_LAUNCH_OK();
+  DUDF_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<float> h(ctas);
+  DUDF_CUDA_OK(cudaMemcpy(h.data(), d, ctas * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  double sum = 0.0;
+  for (float v : h) sum += v;
+  *clk_host = (float)(sum / ctas);
   return 0;
 }
 

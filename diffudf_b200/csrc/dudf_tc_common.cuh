@@ -24,6 +24,7 @@ constexpr int TC_ACT_BYTES = 65536;
 constexpr int TC_IMG_BYTES = 32768;            // [256][64] fp16 operand image
 constexpr float TC_KAPPA = 0.125f;
 constexpr float TC_KAPPA_INV = 8.0f;
+constexpr int TC_DIR_FWD = 0, TC_DIR_BWD = 1, TC_DIR_BOTH = 2;
 
 template <int NCH>
 struct TcCfg {
@@ -59,27 +60,48 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(umma::smem_u32(src_smem)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(umma::smem_u32(src_smem)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// drop a 128-byte line from L2 without writing it back (the data is dead: scratch that will be rewritten before its next read)
+__device__ __forceinline__ void l2_discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---- producer: weight chunks through the ring.  Phase j of a pair uses image j (forward) or the transposed
-// ---- image of layer n_phase-j (reverse sweep).  REUSE: each of the 8 chunks of a layer is fetched once per sub-tile
+// ---- image of layer n_phase-j (reverse sweep).  dir: TC_DIR_FWD, TC_DIR_BWD, or TC_DIR_BOTH (fused training step:
+// ---- the n_phase forward phases of a pair followed by its n_phase reverse phases).  REUSE: each of the 8 chunks of a layer is fetched once per sub-tile
 // ---- pair (the MMA issuer uses a chunk for both sub-tiles before releasing it); otherwise once per sub-tile.
 // CL > 1: the CTAs of a cluster run the same schedule; chunk c is fetched from L2 by CTA (c mod CL) only and
 // multicast into the ring slot of every CTA of the cluster (its complete_tx lands on each CTA's full barrier);
 // a slot is free again when the MMA issuers of ALL CTAs have released it (empty barriers count CL arrivals).
 template <int CL = 1, bool REUSE = false>
 __device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t rounds,
-                                            int n_phase, bool backward, uint32_t cta_rank = 0) {
+                                            int n_phase, int dir, uint32_t cta_rank = 0, int dbg = 0) {
   using namespace umma;
   uint32_t stage = 0, phase = 0, chunk = 0;
+  const int n_tot = (dir == TC_DIR_BOTH) ? 2 * n_phase : n_phase;
   for (int64_t r = 0; r < rounds; ++r)
-    for (int j = 0; j < n_phase; ++j) {
+    for (int jt = 0; jt < n_tot; ++jt) {
+      const bool backward = (dir == TC_DIR_BWD) || (jt >= n_phase);
+      const int j = (jt >= n_phase) ? jt - n_phase : jt;
       const int idx = backward ? (n_phase + (n_phase - 1 - j)) : j;
       const unsigned char* src = packed + (size_t)idx * 8 * TC_CHUNK_BYTES;
       for (int rep = 0; rep < (REUSE ? 1 : 2); ++rep)
         for (int ck = 0; ck < 8; ++ck, ++chunk) {
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
+          if ((dbg & 4) && chunk >= (uint32_t)TC_STAGES) {        // pipeline diagnostics: stale weights, no L2 -> SM traffic
+            mbar_arrive(&full[stage]);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
           if constexpr (CL == 1) {
             bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
@@ -93,19 +115,25 @@ __device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigne
     }
 }
 
-// after the last MMA of a sub-tile: optional operand-image copy for the weight-gradient GEMM, then publish the accumulator
-__device__ __forceinline__ void tc_finish_subtile(unsigned char* act, uint64_t* acc_ready, int s, unsigned char* img, int64_t ncb, int64_t cb0,
-                                                  int64_t pair, int layer) {
-  using namespace umma;
+// operand-image copy of a B tile for the weight-gradient GEMM (two 32 KB images), issued BEFORE the MMAs that read the
+// tile so that both proceed concurrently; tc_finish_subtile waits for its shared-memory reads before it publishes the
+// accumulator (the epilogue overwrites the tile after that).
+__device__ __forceinline__ void tc_copy_subtile(unsigned char* act, int s, unsigned char* img, int64_t ncb, int64_t cb0, int64_t pair, int layer,
+                                                uint64_t img_policy) {
   if (img) {
     const int64_t cb = cb0 + (pair * 2 + s) * 2;
 #pragma unroll
-    for (int nb = 0; nb < 2; ++nb)
-      bulk_s2g(img + ((size_t)layer * ncb + cb + nb) * TC_IMG_BYTES, act + s * TC_ACT_BYTES + nb * TC_IMG_BYTES, TC_IMG_BYTES);
+    for (int nb = 0; nb < 2; ++nb) {
+      unsigned char* dst = img + ((size_t)layer * ncb + cb + nb) * TC_IMG_BYTES;
+      if (img_policy) bulk_s2g_hint(dst, act + s * TC_ACT_BYTES + nb * TC_IMG_BYTES, TC_IMG_BYTES, img_policy);
+      else bulk_s2g(dst, act + s * TC_ACT_BYTES + nb * TC_IMG_BYTES, TC_IMG_BYTES);
+    }
     bulk_commit();
-    bulk_wait_read0();          // the tile may be overwritten once acc_ready is published
   }
-  mma_commit(&acc_ready[s]);
+}
+__device__ __forceinline__ void tc_finish_subtile(uint64_t* acc_ready, int s, bool copied) {
+  if (copied) bulk_wait_read0();
+  umma::mma_commit(&acc_ready[s]);
 }
 
 // ---- MMA issuer (one thread).
@@ -113,11 +141,12 @@ __device__ __forceinline__ void tc_finish_subtile(unsigned char* act, uint64_t* 
 //   early as possible (best when the epilogue / HBM traffic is the limiter: training kernels).
 // REUSE = true:  per layer  A.h0 B.h0 | A.h1 B.h1: the four chunks of a half stay in the ring for both sub-tiles and are
 //   released after the second use, so weights cross L2 -> SM once per 256 columns (query kernel).
-// img != null: bulk-copy each finished B tile (two 32 KB operand images) to img[layer][cb0 + 2*subtile + nb].
+// img_f / img_b != null: bulk-copy each finished B tile of a forward / reverse phase (two 32 KB operand images) to
+// img[layer][cb0 + 2*subtile + nb].
 template <int CL = 1, bool REUSE = false>
 __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
-                                            uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, unsigned char* img,
-                                            int64_t ncb, int64_t cb0, bool backward, int dbg = 0) {
+                                            uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, unsigned char* img_f,
+                                            unsigned char* img_b, int64_t ncb, int64_t cb0, int dir, int dbg = 0, uint64_t img_policy = 0) {
   using namespace umma;
   static_assert(TC_STAGES >= 5, "a neuron half (4 chunks) must fit in the ring with one slot to prefetch into");
   constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
@@ -126,13 +155,18 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
   uint32_t act_phase = 0;                                   // bit s = parity of act_ready[s]
   for (int64_t r = 0; r < rounds; ++r) {
     const int64_t pair = blockIdx.x + r * gridDim.x;
-    for (int j = 0; j < n_phase; ++j) {
+    const int n_tot = (dir == TC_DIR_BOTH) ? 2 * n_phase : n_phase;
+    for (int jt = 0; jt < n_tot; ++jt) {
+      const bool backward = (dir == TC_DIR_BWD) || (jt >= n_phase);
+      const int j = (jt >= n_phase) ? jt - n_phase : jt;
       const int layer = backward ? (n_phase - j) : j;
+      unsigned char* img = backward ? img_b : img_f;
       if constexpr (!REUSE) {
         for (int s = 0; s < 2; ++s) {
           mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
           act_phase ^= 1u << s;
           tc_fence_after();
+          tc_copy_subtile(act, s, img, ncb, cb0, pair, layer, img_policy);
           const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
           for (int h = 0; h < 2; ++h) {
             const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
@@ -150,7 +184,7 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
               if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
           }
-          tc_finish_subtile(act, acc_ready, s, img, ncb, cb0, pair, layer);
+          tc_finish_subtile(acc_ready, s, img != nullptr);
         }
       } else {
         for (int h = 0; h < 2; ++h)
@@ -159,6 +193,7 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
               mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
               act_phase ^= 1u << s;
               tc_fence_after();
+              tc_copy_subtile(act, s, img, ncb, cb0, pair, layer, img_policy);
             }
             const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
             const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
@@ -181,7 +216,7 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
               if (++st == TC_STAGES) { st = 0; ph ^= 1; }
             }
             if (s == 1) { stage = st; phase = ph; }
-            if (h == 1) tc_finish_subtile(act, acc_ready, s, img, ncb, cb0, pair, layer);
+            if (h == 1) tc_finish_subtile(acc_ready, s, img != nullptr);
           }
       }
     }

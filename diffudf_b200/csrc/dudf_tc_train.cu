@@ -19,6 +19,7 @@
 #include "dudf_device.cuh"
 #include "dudf_umma.cuh"
 #include "dudf_tc_common.cuh"
+#include "dudf_loss.cuh"
 
 namespace dudf {
 
@@ -115,6 +116,8 @@ struct SegDev {
   const float* x;        // [P][3]
   float* outp;           // forward: [P][NCH] raw channels
   const float* seeds;    // backward: [P][NCH]
+  const float* normals;  // fused step: [P][3] ground-truth normals
+  const float* dist;     // fused step: [P] ground-truth distances
   int64_t P;
   int64_t npairs;
 };
@@ -237,9 +240,9 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
   if (warp >= 8) {
     setmaxnreg_dec<TC_REGS_AUX>();
     if (warp == 8) {
-      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, false);
+      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD);
     } else if (warp == 9) {
-      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, ld >> 6, col0 >> 6, false);
+      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, nullptr, ld >> 6, col0 >> 6, TC_DIR_FWD);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -270,12 +273,15 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
 // =============================================================================================
 // one column group: u (stash), ab (adjoints of the activations: seeds x output weights at the top, TMEM below) ->
 // adjoints of u, written to the B tile (layers > 0); accumulates the thread's gradient partial sums
-template <int NCH, int GC, bool TOP, bool FIRST>
+// RECOMP0 (with FIRST): the first layer's pre-activations are recomputed from the points instead of read from the stash
+struct FirstRow { float w0, rx, ry, rz, b; };
+template <int NCH, int GC, bool TOP, bool FIRST, bool RECOMP0 = false>
 __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr, uint32_t next_taddr, float wl, const float* sdg,
                                              const float* pts, unsigned char* trow, int chunk0, uint32_t r7, float& bsum, float& wlsum,
-                                             float (&w0s)[3]) {
+                                             float (&w0s)[3], const FirstRow* fr = nullptr) {
   float u[GC], ab[GC];
-  tt_unstash_group<NCH, GC>(u, raw);
+  if constexpr (FIRST && RECOMP0) tc_first_layer_group<NCH, GC>(u, pts, fr->w0, fr->rx, fr->ry, fr->rz, fr->b);
+  else tt_unstash_group<NCH, GC>(u, raw);
   if constexpr (TOP) {
 #pragma unroll
     for (int j = 0; j < GC; ++j) ab[j] = wl * sdg[j];
@@ -418,9 +424,9 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
   if (warp >= 8) {
     setmaxnreg_dec<TC_REGS_AUX>();
     if (warp == 8) {
-      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, true);
+      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BWD);
     } else if (warp == 9) {
-      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Zimg, ld >> 6, col0 >> 6, true);
+      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -543,7 +549,7 @@ tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const uns
 // =============================================================================================
 static SegDev make_seg(const TcSegment& s) {
   SegDev d;
-  d.x = s.x; d.outp = s.packed; d.seeds = s.seeds; d.P = s.rows;
+  d.x = s.x; d.outp = s.packed; d.seeds = s.seeds; d.normals = s.normals; d.dist = s.dist; d.P = s.rows;
   const int pp = tc_train_pair_points(s.nch);
   d.npairs = (s.rows + pp - 1) / pp;
   return d;
@@ -627,6 +633,310 @@ int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, c
                                                          seed_absmax);
   DUDF_LAUNCH_OK();
   return 0;
+}
+
+// =============================================================================================
+// fused step (loss_s1 / loss_siren): forward, loss epilogue and reverse sweep of a sub-tile pair inside one CTA.
+// The pre-activation stash becomes a per-CTA scratch of 2 sub-tiles x n_hidden layers that is written, read back and
+// overwritten by the same CTA: it lives in L2 (consumed lines are discarded, not written back), so the HBM traffic
+// of a step is the operand images of the weight-gradient GEMM only.  The first layer is recomputed in the reverse
+// sweep.  The loss scale of the adjoints comes from the PREVIOUS step's max|seed| (the seeds of a step are not known
+// before its forward); this step's maximum is collected for the next one.
+// =============================================================================================
+struct FusedDev {
+  LossRowCfg loss;
+  double* terms;             // [4], accumulated
+  const float* amax_prev;    // max|stored seed| of the previous step -> loss scale
+  float* amax_next;          // this step's (atomicMax)
+  int flags;                 // bit 0: discard consumed scratch lines from L2
+};
+
+template <int NCH>
+__device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, const GradView& grad, const SegDev& sg, const FusedDev& fd,
+                                              int64_t pair, float* Ucta, float S, float wl, const FirstRow& fr, double* acc_terms,
+                                              float* acc_misc) {
+  using C = TcCfg<NCH>;
+  constexpr int GC = C::GC;
+  constexpr int NRAW = Stash<NCH, GC>::CHUNKS;
+  const int L = net.n_lin - 1;
+  const float ww = net.ww;
+  const float invS = 1.0f / S;
+  float* sd = e.os;                                               // outputs, then stored seeds, of both sub-tiles [2][256]
+  tc_epi_bar();
+  for (int i = e.tid; i < 2 * C::PT; i += 256) {
+    const int64_t p = pair * 2 * C::PT + i;
+    float pt[3] = {0.f, 0.f, 0.f};
+    if (p < sg.P) { pt[0] = sg.x[p * 3]; pt[1] = sg.x[p * 3 + 1]; pt[2] = sg.x[p * 3 + 2]; }
+    e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
+  }
+  if (C::NV < 128) {
+    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(e.act + s * TC_ACT_BYTES, e.n) + tc_chunk_off(15, e.r7)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_epi_bar();
+  // ---------------- forward ----------------
+  for (int l = 0; l < L; ++l) {
+    const float bias = (l > 0) ? ww * net.b[l][e.n] : 0.f;
+    for (int s = 0; s < 2; ++s) {
+      unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
+      float* ust = Ucta + ((size_t)l * 256 + s * 128) * 256 + e.n * 4;
+      if (l > 0) {
+        mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
+        e.acc_phase ^= 1u << s;
+        tc_fence_after();
+      }
+      if (l == 0) {
+#pragma unroll 1
+        for (int g = 0; g < C::NGRP; ++g) {
+          float u[GC];
+          tc_first_layer_group<NCH, GC>(u, e.xs + (s * C::PT + g * (GC / NCH)) * 3, fr.w0, fr.rx, fr.ry, fr.rz, fr.b);
+          tc_emit_group<NCH, GC, true>(u, trow, g * (GC / 8), e.r7);
+        }
+      } else {
+        TmemRegs<GC> nxt;
+        tc_ld_issue<GC>(e.tmem_lane + s * 256, nxt);
+#pragma unroll 1
+        for (int g = 0; g < C::NGRP; ++g) {
+          float u[GC];
+          tc_ld_take<GC>(nxt, u);
+          if (g + 1 < C::NGRP) tc_ld_issue<GC>(e.tmem_lane + s * 256 + (g + 1) * GC, nxt);
+#pragma unroll
+          for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
+          tt_stash_group<NCH, GC>(u, ust + (size_t)g * GC * 256);
+          tc_emit_group<NCH, GC, true>(u, trow, g * (GC / 8), e.r7);
+        }
+      }
+      if (l < L - 1) {
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (e.lane == 0) mbar_arrive(&e.act_ready[s]);
+      }
+    }
+  }
+  // ---------------- output layer + loss: one thread per point of the pair ----------------
+  tc_epi_bar();
+  for (int s = 0; s < 2; ++s) tc_output_dot<C::NV>(e.act + s * TC_ACT_BYTES, e.wl_s, e.os + s * 256, e.tid);
+  tc_epi_bar();
+  if ((e.tid & ~31) < 2 * C::PT) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    float bl = 0.f, amax = 0.f;
+    if (e.tid < 2 * C::PT) {
+      const int s = e.tid / C::PT, i = e.tid % C::PT;
+      const int64_t p = pair * 2 * C::PT + e.tid;
+      float* col = sd + s * 256 + i * NCH;
+      float v[10], sv[10];
+#pragma unroll
+      for (int ch = 0; ch < 10; ++ch) {
+        v[ch] = 0.f;
+        if (ch < NCH) {
+          const float r = col[ch] + col[128 + ch];
+          v[ch] = (ch == 0) ? r + net.b[L][0] : (ch >= 4 ? r * TC_KAPPA_INV : r);
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < 10; ++ch) sv[ch] = 0.f;
+      if (p < sg.P) {
+        loss_row(fd.loss, NCH, v, sg.dist[p], sg.normals + p * 3, t, sv);
+        if (sg.outp) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) sg.outp[p * NCH + ch] = v[ch];
+        }
+      }
+      bl = sv[0];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float st = sv[ch] * (ch >= 4 ? TC_KAPPA_INV : 1.f);
+        amax = fmaxf(amax, fabsf(st));
+        col[ch] = st * S;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+      bl += __shfl_xor_sync(0xffffffffu, bl, o);
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    if (e.lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t[k] != 0.0) atomicAdd(&acc_terms[k], t[k]);
+      if (bl != 0.f) atomicAdd(&acc_misc[0], bl);
+      if (amax > 0.f && isfinite(amax)) atomicMax(reinterpret_cast<int*>(&acc_misc[1]), __float_as_int(amax));
+    }
+  }
+  tc_epi_bar();
+  // ---------------- reverse sweep: layers L-1 .. 1 read the scratch, layer 0 is recomputed from the points ----------------
+  for (int l = L - 1; l >= 1; --l) {
+    const bool top = (l == L - 1);
+    for (int s = 0; s < 2; ++s) {
+      unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
+      const float* ust = Ucta + ((size_t)l * 256 + s * 128) * 256 + e.n * 4;
+      uint4 nxt[NRAW];
+      tt_stash_load<NCH, GC>(nxt, ust);
+      if (!top) {
+        mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
+        e.acc_phase ^= 1u << s;
+        tc_fence_after();
+      }
+      float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
+      TmemRegs<GC> tr;
+      if (!top) tc_ld_issue<GC>(e.tmem_lane + s * 256, tr);
+#pragma unroll 1
+      for (int g = 0; g < C::NGRP; ++g) {
+        uint4 ug[NRAW];
+#pragma unroll
+        for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
+        if (g + 1 < C::NGRP) tt_stash_load<NCH, GC>(nxt, ust + (size_t)(g + 1) * GC * 256);
+        const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * GC : 0u;
+        const float* sdg = sd + s * 256 + g * GC;
+        const float* pts = e.xs + (s * C::PT + g * (GC / NCH)) * 3;
+        const int c0 = g * (GC / 8);
+        if (top) tt_bwd_group<NCH, GC, true, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else     tt_bwd_group<NCH, GC, false, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        if ((fd.flags & 1) && (e.lane & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < NRAW; ++j) l2_discard_line(ust + (size_t)g * GC * 256 + j * 1024);
+        }
+      }
+      atomicAdd(&grad.b[l][e.n], bsum * ww * invS);
+      if (top) atomicAdd(&grad.W[L][e.n], wlsum * invS);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (e.lane == 0) mbar_arrive(&e.act_ready[s]);
+    }
+  }
+  for (int s = 0; s < 2; ++s) {
+    mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
+    e.acc_phase ^= 1u << s;
+    tc_fence_after();
+    float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
+    TmemRegs<GC> tr;
+    tc_ld_issue<GC>(e.tmem_lane + s * 256, tr);
+#pragma unroll 1
+    for (int g = 0; g < C::NGRP; ++g) {
+      const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * GC : 0u;
+      const float* pts = e.xs + (s * C::PT + g * (GC / NCH)) * 3;
+      tt_bwd_group<NCH, GC, false, true, true>(nullptr, tr, tnext, wl, nullptr, pts, nullptr, 0, e.r7, bsum, wlsum, w0s, &fr);
+    }
+    atomicAdd(&grad.b[0][e.n], bsum * net.w0 * invS);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) atomicAdd(&grad.W[0][e.n * 3 + d], w0s[d] * net.w0 * invS);
+  }
+}
+
+template <int NA, int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tt_fused_kernel(const unsigned char* __restrict__ packed, NetView net, GradView grad, SegDev sa, SegDev sb, FusedDev fd,
+                float* __restrict__ scratch, unsigned char* __restrict__ Aimg, unsigned char* __restrict__ Zimg, int64_t ncb) {
+  using C = TcCfg<NA>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* act = smem;
+  unsigned char* ring = smem + C::OFF_RING;
+  float* wl_s = (float*)(smem + C::OFF_WL);
+  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+  double* acc_terms = (double*)(smem + C::OFF_BAR + 128);          // [4] loss-term shares of this CTA
+  float* acc_misc = (float*)(smem + C::OFF_BAR + 160);             // [0] output-bias gradient, [1] max|stored seed|
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = net.n_lin - 1;
+  const int64_t npairs = sa.npairs + sb.npairs;
+  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
+    mbar_fence_init();
+    for (int k = 0; k < 4; ++k) acc_terms[k] = 0.0;
+    acc_misc[0] = 0.f; acc_misc[1] = 0.f;
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (tid < 256) wl_s[tid] = net.W[L][tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    setmaxnreg_dec<TC_REGS_AUX>();
+    if (warp == 8) {
+      if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BOTH, 0, fd.flags >> 8);
+    } else if (warp == 9) {
+      if (lane == 0)
+        tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, Zimg, ncb, 0, TC_DIR_BOTH, fd.flags >> 8,
+                       (fd.flags & 2) ? l2_policy_evict_first() : 0ull);
+    }
+  } else {
+    setmaxnreg_inc<TC_REGS_EPI>();
+    const int q = warp & 3, h = warp >> 2;
+    EpiCtx e;
+    e.act = act; e.xs = (float*)(smem + C::OFF_XS); e.os = (float*)(smem + C::OFF_OS); e.wl_s = wl_s;
+    e.act_ready = act_ready; e.acc_ready = acc_ready;
+    e.n = h * 128 + q * 32 + lane; e.tid = tid; e.lane = lane; e.r7 = e.n & 7;
+    e.tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
+    e.acc_phase = 0;
+    const float S = loss_scale_from(fd.amax_prev);
+    const float wl = net.W[L][e.n];
+    FirstRow fr;
+    fr.w0 = net.w0; fr.rx = net.W[0][e.n * 3]; fr.ry = net.W[0][e.n * 3 + 1]; fr.rz = net.W[0][e.n * 3 + 2]; fr.b = net.b[0][e.n];
+    float* Ucta = scratch + (size_t)blockIdx.x * L * 256 * 256;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      if (pair < sa.npairs) {
+        tt_fused_pair<NA>(e, net, grad, sa, fd, pair, Ucta, S, wl, fr, acc_terms, acc_misc);
+      } else {
+        if constexpr (NB > 0) tt_fused_pair<NB>(e, net, grad, sb, fd, pair - sa.npairs, Ucta, S, wl, fr, acc_terms, acc_misc);
+      }
+    }
+    tc_epi_bar();
+    if (tid < 4 && acc_terms[tid] != 0.0) atomicAdd(&fd.terms[tid], acc_terms[tid]);
+    if (tid == 4 && acc_misc[0] != 0.f) atomicAdd(&grad.b[L][0], acc_misc[0]);
+    if (tid == 5 && acc_misc[1] > 0.f) atomicMax(reinterpret_cast<int*>(fd.amax_next), __float_as_int(acc_misc[1]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+size_t tc_fused_scratch_bytes(const NetView& net, int sms) { return (size_t)sms * (net.n_lin - 1) * 256 * 256 * sizeof(float); }
+
+template <int NA, int NB>
+static int tt_launch_fused(const void* packed, const NetView& net, const GradView& grad, const SegDev& a, const SegDev& b, const FusedDev& fd,
+                           float* scratch, void* Aimg, void* Zimg, int64_t ld, int sms, cudaStream_t st) {
+  auto k = tt_fused_kernel<NA, NB>;
+  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
+  const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
+  if (grid < 1) return 0;
+  k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, fd, scratch, (unsigned char*)Aimg,
+                                               (unsigned char*)Zimg, ld >> 6);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
+// One fused launch over 1 or 2 row segments (segment columns are consecutive from column 0 of the operand images).
+int tc_train_fused(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg, const TcFusedLoss& fl,
+                   float* scratch, void* Aimg, void* Zimg, int64_t ld, int sms, cudaStream_t st) {
+  DUDF_REQUIRE(ld % 64 == 0, "tensor-core stash: ld must be a multiple of 64");
+  DUDF_REQUIRE(nseg == 1 || nseg == 2, "tensor-core training: 1 or 2 segments per launch");
+  DUDF_REQUIRE(fl.mode == DUDF_LOSS_S1 || fl.mode == DUDF_LOSS_SIREN, "fused step: loss_s1 or loss_siren (loss_s2 needs batch statistics first)");
+  DUDF_REQUIRE(fl.terms && fl.amax_prev && fl.amax_next && scratch, "fused step: null argument");
+  SegDev a = make_seg(segs[0]), b;
+  memset(&b, 0, sizeof(b));
+  const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
+  if (nseg == 2) b = make_seg(segs[1]);
+  DUDF_REQUIRE((a.npairs + b.npairs) * 256 <= ld, "fused step: operand images too small");
+  FusedDev fd;
+  fd.loss.mode = fl.mode; fd.loss.alpha = fl.alpha; fd.loss.invP = 1.0f / (float)fl.P_global;
+  for (int k = 0; k < 4; ++k) { fd.loss.w[k] = fl.w[k]; fd.loss.up[k] = 1.f; }
+  fd.terms = fl.terms; fd.amax_prev = fl.amax_prev; fd.amax_next = fl.amax_next; fd.flags = fl.flags;
+  if (nb == 0) {
+    if (na == 4) return tt_launch_fused<4, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
+    if (na == 10) return tt_launch_fused<10, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
+  } else if (na == 10 && nb == 4) {
+    return tt_launch_fused<10, 4>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
+  }
+  DUDF_REQUIRE(false, "fused step: unsupported segment channel counts (%d, %d)", na, nb);
 }
 
 }  // namespace dudf

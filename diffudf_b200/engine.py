@@ -180,6 +180,24 @@ class Engine:
             _lib.check(self.L.dudf_jet_wgrad(self.h, Zb.data_ptr(), A.data_ptr(), ld, ncols, _lib.ptr(seed_absmax), _ptr_array(gW),
                                              PRECISIONS[precision], _lib.current_stream()), "dudf_jet_wgrad")
 
+    def fused_scratch_bytes(self):
+        return int(self.L.dudf_fused_scratch_bytes(self.h))
+
+    def train_step_fused(self, mode, segs, P_global, w, alpha, terms, amax_prev, amax_next, scratch, A, Zb, ld, gW, gb, flags=3):
+        """loss_s1 / loss_siren forward + loss + reverse sweep + weight gradients, tensor-core path, two launches.
+        segs: list of dict(x, normals, d, order[, packed])."""
+        arr = (_lib.TrainSegment * len(segs))()
+        for i, s in enumerate(segs):
+            arr[i].x, arr[i].normals, arr[i].dist = s["x"].data_ptr(), s["normals"].data_ptr(), s["d"].data_ptr()
+            arr[i].rows, arr[i].order = s["x"].shape[0], s["order"]
+            arr[i].packed = s["packed"].data_ptr() if s.get("packed") is not None else None
+        w4 = (ctypes.c_float * 4)(*([float(v) for v in w] + [0.0] * (4 - len(w))))
+        with torch.cuda.device(A.device):
+            _lib.check(self.L.dudf_train_step_fused(self.h, LOSS_MODES[mode], arr, len(segs), P_global, w4, float(alpha), terms.data_ptr(),
+                                                    amax_prev.data_ptr(), amax_next.data_ptr(), scratch.data_ptr(), A.data_ptr(),
+                                                    Zb.data_ptr(), ld, _ptr_array(gW), _ptr_array(gb), flags, _lib.current_stream()),
+                       "dudf_train_step_fused")
+
     def loss(self, mode, packed, nch, normals, dist, P, P_global, w, alpha, upstream=None, seeds=None, terms=None, s2_stats=None,
              seed_absmax=None):
         w4 = (ctypes.c_float * 4)(*([float(v) for v in w] + [0.0] * (4 - len(w))))

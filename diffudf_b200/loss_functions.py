@@ -24,6 +24,9 @@ class TrainCore:
         self.ws = {}
         self.pending = None
         self.precision = precision          # None -> model.train_precision (default 'fp32')
+        self.amax = None                    # (2,) fp32: max|stored seed| of the last two tensor-core steps (loss scale source)
+        self.amax_key, self.amax_slot = None, 0
+        self.fused_flags = 3
 
     def _prec(self):
         return self.precision or getattr(self.model, "train_precision", "fp32")
@@ -59,8 +62,8 @@ class TrainCore:
         ld = (col + 63) // 64 * 64 if prec == "tc16" else (col + 3) // 4 * 4
         return segs, ld, off
 
-    def _stashes(self, L, ld, prec):
-        Z = self._buf("Z", (L, 256, ld))
+    def _stashes(self, L, ld, prec, need_z=True):
+        Z = self._buf("Z", (L, 256, ld)) if need_z else None
         if prec == "tc16":       # fp16 operand planes [layer][k-block][column][64 neurons]; zero tails are part of the contract
             A = self._buf("A", (L, 4, ld, 64), torch.float16, zero=True)
             Zb = self._buf("Zb", (L, 4, ld, 64), torch.float16, zero=True)
@@ -99,7 +102,42 @@ class TrainCore:
                             ld=ld, Z=Z, A=A, Zb=Zb, packed=packed, stats=stats, sig=eng._sig, prec=prec)
         return terms
 
-    def backward(self, upstream, gW, gB):
+    def fused_step(self, mode, x, normals, d, n_on, w, alpha, P_global, gW, gB):
+        """Tensor-core fast path of forward()+backward(None, ...) for loss_s1 / loss_siren: one fused launch + the
+        weight-gradient GEMM.  The adjoints' loss scale comes from the previous step's max|seed|, so the first step of a
+        loss configuration (and every step the fused kernel cannot take) runs the unfused route, which measures it.
+        Returns the (4,) float64 loss-term shares."""
+        prec = self._prec()
+        P = x.shape[0]
+        P_global = P if P_global is None else P_global
+        key = (mode, tuple(float(v) for v in w), float(alpha), int(P_global), int(n_on), int(P))
+        if self.amax is None:
+            self.amax = torch.zeros(2, device=x.device, dtype=torch.float32)
+        if prec != "tc16" or mode == "s2" or self.amax_key != key:
+            terms = self.forward(mode, x, normals, d, n_on, w, alpha, P_global, None)
+            slot = 1 - self.amax_slot
+            self.amax[slot:slot + 1].zero_()
+            self.backward(None, gW, gB, absmax=self.amax[slot:slot + 1] if prec == "tc16" else None)
+            if prec == "tc16" and mode != "s2":
+                self.amax_key, self.amax_slot = key, slot
+            return terms
+        m = self.model
+        eng = m._engine_synced(2)
+        segs, ld, _ = self.plan(mode, P, n_on, w, prec)
+        _, A, Zb = self._stashes(m.n_hidden, ld, prec, need_z=False)
+        scratch = self._buf("fused_scratch", (eng.fused_scratch_bytes() // 4,))
+        terms = torch.zeros(4, device=x.device, dtype=torch.float64)
+        prev, nxt = self.amax_slot, 1 - self.amax_slot
+        self.amax[nxt:nxt + 1].zero_()
+        eng.train_step_fused(mode, [dict(x=x[s["row0"]:s["row0"] + s["rows"]], normals=normals[s["row0"]:s["row0"] + s["rows"]],
+                                         d=d[s["row0"]:s["row0"] + s["rows"]], order=s["order"]) for s in segs],
+                             P_global, w, alpha, terms, self.amax[prev:prev + 1], self.amax[nxt:nxt + 1], scratch, A, Zb, ld, gW, gB,
+                             self.fused_flags)
+        self.amax_slot = nxt
+        self.pending = None
+        return terms
+
+    def backward(self, upstream, gW, gB, absmax=None):
         """Accumulates d(sum_k upstream[k] term_k)/d(params) into gW / gB (lists of tensors)."""
         p = self.pending
         if p is None:
@@ -110,7 +148,8 @@ class TrainCore:
         if eng._sig != p["sig"]:
             raise RuntimeError("SIREN parameters changed between the loss forward and backward")
         seeds = self._buf("seeds", tuple(p["packed"].shape))
-        absmax = torch.zeros(1, device=p["x"].device, dtype=torch.float32) if prec == "tc16" else None
+        if absmax is None and prec == "tc16":
+            absmax = torch.zeros(1, device=p["x"].device, dtype=torch.float32)
         for s in p["segs"]:                 # all seeds (and their magnitude) before the first reverse sweep
             r0, r1 = s["row0"], s["row0"] + s["rows"]
             nch = NCH[s["order"]]

@@ -29,8 +29,9 @@ class FusedTrainer:
     """Owns flat fp32 parameter / gradient / Adam-moment buffers; the module's parameters become views
     of the flat buffer so that state_dict()/load_state_dict() keep working."""
 
-    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None, precision=None):
+    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None, precision=None, fused=True):
         self.model = model
+        self.fused = fused                  # tensor-core steps of loss_s1 / loss_siren go through the single fused launch
         self.betas, self.eps, self.dp = betas, eps, dp
         ws, bs = model._weights_biases()
         dev = ws[0].device
@@ -61,9 +62,12 @@ class FusedTrainer:
         Returns the (4,) float64 device tensor of this rank's loss-term shares (no sync)."""
         dp = self.dp
         P_global = dp.global_rows(x.shape[0]) if dp is not None else None
-        terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None)
         self.grad.zero_()
-        self.core.backward(None, self.gW, self.gB)
+        if mode != "s2" and self.core._prec() == "tc16" and self.fused:
+            terms = self.core.fused_step(mode, x, normals, d, n_on, weights, alpha, P_global, self.gW, self.gB)
+        else:
+            terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None)
+            self.core.backward(None, self.gW, self.gB)
         if dp is not None:
             dp.reduce_grads(self.grad)
         self.t += 1

@@ -131,6 +131,28 @@ int dudf_jet_backward_multi(dudf_ctx* ctx, const dudf_segment* segs_host, int ns
  * (128-byte swizzled rows, zero-initialised by the caller), and the reverse sweep runs
  * under a power-of-two loss scale derived from seed_absmax (1 device float, zeroed by the caller before the dudf_loss
  * calls of a step, which raise it with atomicMax; all dudf_loss calls of a step must precede its first backward). */
+/* Fused training step on the tensor-core path (loss_s1 / loss_siren; train.py:204-216 = loss_fn + backward):
+ * ONE launch runs forward jets, the loss terms, their adjoint seeds and the reverse sweep for every sub-tile pair
+ * inside a CTA (the pre-activation stash stays in a per-CTA, L2-resident scratch), then the weight-gradient GEMM.
+ * Segments as in dudf_jet_forward_multi (order-2 segment first; their columns start at column 0 of the images).
+ * terms (4 device doubles) and the gradients are ACCUMULATED.  The reverse sweep's power-of-two loss scale is taken
+ * from amax_prev = max|stored seed| of the PREVIOUS step with the same loss configuration (1 device float, e.g. the
+ * seed_absmax a dudf_loss pass or an earlier fused step produced); amax_next (zeroed by the caller) receives this
+ * step's.  scratch: dudf_fused_scratch_bytes(ctx) bytes.  A, Zb: fp16 operand images as for dudf_jet_wgrad, ld columns. */
+typedef struct dudf_train_segment {
+  const float* x;        /* [rows][3] */
+  const float* normals;  /* [rows][3] */
+  const float* dist;     /* [rows] */
+  int64_t rows;
+  int order;             /* 1 or 2 */
+  float* packed;         /* optional out: [rows][NCH] jets (may be NULL) */
+} dudf_train_segment;
+#define DUDF_FUSED_DISCARD 1      /* drop consumed scratch lines from L2 instead of letting them be written back */
+#define DUDF_FUSED_IMG_EVICT_FIRST 2 /* operand-image stores carry an L2 evict-first hint */
+int64_t dudf_fused_scratch_bytes(const dudf_ctx* ctx);
+int dudf_train_step_fused(dudf_ctx* ctx, int mode, const dudf_train_segment* segs_host, int nseg, int64_t P_global,
+                          const float* w_host, float alpha, double* terms, const float* amax_prev, float* amax_next, void* scratch,
+                          void* A, void* Zb, int64_t ld, float* const* gW_host, float* const* gb_host, int flags, void* stream);
 /* Loss epilogue over P rows.  w_host: 4 host floats (loss weights); P_global: divisor of the means (sum of rows over
  * data-parallel ranks).  terms (4 device doubles, may be NULL) is ACCUMULATED with this call's share of each term in
  * the order of the reference dicts: S1 {sdf_on_surf, sdf_off_surf, hessian_constraint, grad_constraint}, SIREN
@@ -150,6 +172,9 @@ int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
 
 /* bring-up / regression tests of the tcgen05 building blocks (tests/test_gpu_umma.py) */
 int dudf_selftest_umma(int variant, float* max_err_host);
+/* Tensor-pipe micro-benchmark (tools/umma_bench.py): average clocks per tcgen05.mma (K = 16) over `ctas` CTAs that each
+ * issue iters x 16 instructions on resident operands; variants in dudf_tc.cu. */
+int dudf_bench_umma(int variant, int ctas, int iters, float* clk_per_mma_host);
 
 #ifdef __cplusplus
 }

@@ -88,3 +88,50 @@ def test_tc16_trainer_matches_fp32_trainer_for_a_few_steps(weights):
         assert all(torch.isfinite(v).all() for v in m.state_dict().values())
     print(out)
     assert np.allclose(out["fp32"], out["tc16"], rtol=1e-2, atol=1e-2)
+
+
+def _trainer_grads(weights, tag, mode, w, x, n, d, n_on, fused, steps):
+    from diffudf_b200 import SIREN
+    from diffudf_b200.train import FusedTrainer
+    m = SIREN(3, 1, [256] * 8, w0=30, delay_init=True)
+    m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(v) for i, (W, b) in enumerate(weights[tag])
+                       for k, v in (("weight", W), ("bias", b))})
+    tr = FusedTrainer(m.cuda(), precision="tc16", fused=fused)
+    xd, nd, dd = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x, n, d))
+    for _ in range(steps):                      # lr = 0: every step sees the same weights
+        t = tr.step(mode, xd, nd, dd, n_on, w, 100.0, 0.0)
+    return t.cpu().numpy(), [g.clone() for g in tr.gW], [g.clone() for g in tr.gB], tr
+
+
+@pytest.mark.parametrize("tag", ["init", "trained"])
+@pytest.mark.parametrize("mode,w", [("s1", [1e4, 1e4, 1e4, 1e3]), ("s1", [1e4, 1e4, 0, 1e3]), ("siren", [3e3, 1e2, 1e2, 5e1])])
+def test_fused_step_matches_unfused_tc16_step(tag, mode, w, golden, weights):
+    """The single-launch step (forward + loss + reverse sweep inside the CTA) computes the same arithmetic as the
+    three-kernel route: identical fp16 operands and fp32 accumulation, so only the atomics' order and (for the first
+    layer) a recomputed instead of stashed pre-activation differ."""
+    Ld = golden(f"losses_{tag}.npz")
+    x, n, d = Ld["x"].reshape(-1, 3), Ld["normals"].reshape(-1, 3), Ld["d"].reshape(-1)
+    n_on = int((d == 0).sum())
+    assert (d[:n_on] == 0).all()
+    t0, gW0, gB0, _ = _trainer_grads(weights, tag, mode, w, x, n, d, n_on, False, 1)
+    t1, gW1, gB1, tr = _trainer_grads(weights, tag, mode, w, x, n, d, n_on, True, 3)   # step 1 unfused (measures the scale), 2-3 fused
+    assert tr.core.amax_key is not None and tr.core.pending is None                    # the fused route really ran
+    assert np.allclose(t0, t1, rtol=1e-6, atol=1e-9), (t0, t1)
+    for a, b in zip(gW0 + gB0, gW1 + gB1):
+        scale = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-12, (float((a - b).abs().max()), scale)
+
+
+def test_fused_step_against_oracle(golden, oracle, weights):
+    Ld = golden("losses_trained.npz")
+    x, n, d = Ld["x"].reshape(-1, 3), Ld["normals"].reshape(-1, 3), Ld["d"].reshape(-1)
+    n_on = int((d == 0).sum())
+    w = [1e4, 1e4, 1e4, 1e3]
+    t, gW, gB, _ = _trainer_grads(weights, "trained", "s1", w, x, n, d, n_on, True, 2)
+    terms_ref, grads_ref = oracle.train_grads(weights["trained"], Ld["x"], Ld["normals"], Ld["d"], "s1", w, 100.0)
+    for i, k in enumerate(("sdf_on_surf", "sdf_off_surf", "hessian_constraint", "grad_constraint")):
+        assert abs(t[i] - float(terms_ref[k])) / max(abs(float(terms_ref[k])), 1e-2) < 1e-3, (k, t[i], terms_ref[k])
+    for i in range(len(grads_ref)):
+        assert rel_max(gW[i].cpu().numpy(), grads_ref[i][0].reshape(tuple(gW[i].shape))) < 2e-2
+        assert rel_l2(gW[i].cpu().numpy(), grads_ref[i][0].reshape(tuple(gW[i].shape))) < 1.5e-2
+        assert rel_max(gB[i].cpu().numpy(), grads_ref[i][1].reshape(tuple(gB[i].shape))) < 2e-2
