@@ -105,7 +105,7 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
     if (warp == 8) {
       if (lane == 0) tc_producer<CL, RU>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD, CL > 1 ? cluster_ctarank() : 0u, CL > 1 ? 0 : (int)(out.flags >> 8));
     } else if (warp == 9) {
-      if (lane == 0) tc_mma_role<CL, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8);
+      tc_mma_role<CL, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -197,6 +197,159 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
+// =============================================================================================
+// 16-epilogue-warp variant: the two sub-tiles of a pair are owned by two independent sets of 8 warps (set s = warps
+// 8s..8s+7, one thread per neuron), so four warps per scheduler hide the TMEM / MUFU / shared-memory latencies of the
+// sine-jet instead of two.  Registers: 640 threads start with 96 each (61 440, the CTA's pool); the auxiliary warpgroup
+// drops to 56 and frees 5 120, the epilogue warps rise to 104 and take 4 096.
+// =============================================================================================
+constexpr int TC16_THREADS = 640;
+constexpr int TC16_REGS_EPI = 104;
+constexpr int TC16_REGS_AUX = 56;
+__device__ __forceinline__ void tc_set_bar(int s) { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); }
+
+template <int NCH, bool RU>
+__global__ void __launch_bounds__(TC16_THREADS, 1)
+tc_forward16_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, int gridN,
+                    int64_t grid_first, QueryOut out) {
+  using C = TcCfg<NCH>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* act = smem;
+  unsigned char* ring = smem + C::OFF_RING;
+  float* wl_s = (float*)(smem + C::OFF_WL);
+  float* xs = (float*)(smem + C::OFF_XS);
+  float* os = (float*)(smem + C::OFF_OS);
+  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
+  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = net.n_lin - 1;
+  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
+  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  if (tid < 256) wl_s[tid] = net.W[L][tid];
+  if (C::NV < 128 && tid < 256) {
+    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(act + s * TC_ACT_BYTES, tid) + tc_chunk_off(15, tid & 7)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 16) {
+    setmaxnreg_dec<TC16_REGS_AUX>();
+    if (warp == 16) {
+      if (lane == 0) tc_producer<1, RU>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD, 0u, (int)(out.flags >> 8));
+    } else if (warp == 17) {
+      tc_mma_role<1, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8);
+    }
+  } else {
+    setmaxnreg_inc<TC16_REGS_EPI>();
+    const int s = warp >> 3;                                // this warp set's sub-tile
+    const int ts = tid & 255;
+    const int q = warp & 3, h = (warp >> 2) & 1;
+    const int n = h * 128 + q * 32 + lane;
+    const uint32_t r7 = n & 7;
+    const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + s * 256 + h * 128;
+    const float w0 = net.w0, ww = net.ww;
+    const float r0x = net.W[0][n * 3], r0y = net.W[0][n * 3 + 1], r0z = net.W[0][n * 3 + 2], b0 = net.b[0][n];
+    const float bL = net.b[L][0];
+    const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
+    unsigned char* trow = tc_tile_row(act + s * TC_ACT_BYTES, n);
+    float* xss = xs + s * C::PT * 3;
+    float* oss = os + s * 256;
+    uint32_t acc_phase = 0;
+
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+      const int64_t pair = blockIdx.x + rd * gridDim.x;
+      tc_set_bar(s);
+      for (int i = ts; i < C::PT; i += 256) {
+        const int64_t p = (pair * 2 + s) * C::PT + i;
+        float pt[3] = {0.f, 0.f, 0.f};
+        if (p < P) {
+          if (x) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
+          else grid_point(grid_first + p, gridN, vs, pt);
+        }
+        xss[i * 3] = pt[0]; xss[i * 3 + 1] = pt[1]; xss[i * 3 + 2] = pt[2];
+      }
+      tc_set_bar(s);
+      for (int l = 0; l < L; ++l) {
+        const float bias = (l > 0) ? ww * net.b[l][n] : 0.f;
+        if (l > 0) {
+          mbar_wait(&acc_ready[s], acc_phase, 0x400 + s);
+          acc_phase ^= 1u;
+          tc_fence_after();
+        }
+        if (l == 0) {
+#pragma unroll 1
+          for (int g = 0; g < C::NGRP; ++g) {
+            float u[C::GC];
+            tc_first_layer_group<NCH, C::GC>(u, xss + g * (C::GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
+            tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
+          }
+        } else if (!((out.flags >> 8) & 1)) {
+          TmemRegs<C::GC> nxt;
+          tc_ld_issue<C::GC>(tmem_acc, nxt);
+#pragma unroll 1
+          for (int g = 0; g < C::NGRP; ++g) {
+            float u[C::GC];
+            tc_ld_take<C::GC>(nxt, u);
+            if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(tmem_acc + (g + 1) * C::GC, nxt);
+#pragma unroll
+            for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
+            tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
+          }
+        }
+        if (l < L - 1) {
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&act_ready[s]);
+        } else {
+          tc_set_bar(s);
+          tc_output_dot<C::NV>(act + s * TC_ACT_BYTES, wl_s, oss, ts);
+          tc_set_bar(s);
+          if (ts < C::NV) {
+            const int ch = ts % NCH;
+            const float v = oss[ts] + oss[128 + ts];
+            oss[ts] = (ch == 0) ? v + bL : (ch >= 4 ? v * TC_KAPPA_INV : v);
+          }
+          tc_set_bar(s);
+          if (ts < C::PT) {
+            const int64_t p = (pair * 2 + s) * C::PT + ts;
+            if (p < P) finalize_point<NCH>(out, p, oss + ts * NCH);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
+}
+
+template <int NCH, bool RU>
+static int tc_launch16(const void* packed, const NetView& net, const float* x, int64_t P, int gridN, int64_t first, const QueryOut& out,
+                       int sms, cudaStream_t st) {
+  using C = TcCfg<NCH>;
+  auto k = tc_forward16_kernel<NCH, RU>;
+  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
+  const int grid = (int)std::min<int64_t>(npairs, sms);
+  if (grid < 1) return 0;
+  k<<<grid, TC16_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, x, P, gridN, first, out);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
 static int g_tc_cluster = -1;      // DUDF_TC_CLUSTER=1|2|4 overrides the cluster size of the query kernel (default 2)
 static int tc_cluster_size() {
   if (g_tc_cluster < 0) {
@@ -240,12 +393,19 @@ static int tc_launch_cl(const void* packed, const NetView& net, const float* x, 
                         int sms, cudaStream_t st) {
   using C = TcCfg<NCH>;
   const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
+  static const int w16 = getenv("DUDF_TC_WARPS16") ? atoi(getenv("DUDF_TC_WARPS16")) : 0;   // 1: ping-pong order, 2: chunk-reuse order
+  if (w16 == 1) return tc_launch16<NCH, false>(packed, net, x, P, gridN, first, out, sms, st);
+  if (w16 == 2) return tc_launch16<NCH, true>(packed, net, x, P, gridN, first, out, sms, st);
   int cl = tc_cluster_size();
   while (cl > 1 && npairs < 2 * cl) cl >>= 1;              // tiny queries: no point in pairing CTAs
+  static const bool no_reuse = getenv("DUDF_TC_REUSE") && atoi(getenv("DUDF_TC_REUSE")) == 0;   // ping-pong order instead of chunk reuse
+  if (no_reuse) {
+    if (cl == 4) return tc_launch<NCH, 4, false>(packed, net, x, P, gridN, first, out, sms, st);
+    if (cl == 2) return tc_launch<NCH, 2, false>(packed, net, x, P, gridN, first, out, sms, st);
+    return tc_launch<NCH, 1, false>(packed, net, x, P, gridN, first, out, sms, st);
+  }
   if (cl == 4) return tc_launch<NCH, 4>(packed, net, x, P, gridN, first, out, sms, st);
   if (cl == 2) return tc_launch<NCH, 2>(packed, net, x, P, gridN, first, out, sms, st);
-  static const bool no_reuse = getenv("DUDF_TC_REUSE") && atoi(getenv("DUDF_TC_REUSE")) == 0;   // diagnostics: ping-pong order, CL = 1
-  if (no_reuse) return tc_launch<NCH, 1, false>(packed, net, x, P, gridN, first, out, sms, st);
   return tc_launch<NCH, 1>(packed, net, x, P, gridN, first, out, sms, st);
 }
 
@@ -373,6 +533,9 @@ int tc_selftest(int variant, float* max_err, cudaStream_t st) {
 //   variant 0: A K-major, B MN-major, N = 128 (the chain kernels)   1: A, B K-major, N = 128
 //   variant 2: A K-major, B MN-major, N = 256                        3: A, B K-major, N = 256
 //   variant 4: A in TMEM, B K-major, N = 256                         5: A in TMEM, B K-major, N = 128
+//   variant 6 / 7 / 8: as 0 with a tcgen05.commit (to a second mbarrier) after every 4 / 8 / 16 instructions
+//   variant 9: as 0, consecutive instructions alternate between two accumulators; 10: between four
+//   variant 11: as 0, issued from warp-uniform code (elect per instruction) with descriptors advanced by adds
 // =============================================================================================
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -386,18 +549,36 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 __global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int variant, int iters, float* __restrict__ clk_per_mma) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int commit_every = variant == 6 ? 4 : variant == 7 ? 8 : variant == 8 ? 16 : 0;
+  const int alt = variant == 9 ? 1 : variant == 10 ? 3 : 0;
+  const bool variant11 = (variant == 11);
+  if (variant >= 6) variant = 0;
   for (int i = tid * 16; i < 196608; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
-  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (tid == 0) {
+  if (variant11 && warp == 0) {
+    constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, 0, 1);
+    const uint64_t ad0 = make_desc_sw128(smem_u32(smem), 16, 1024), bd0 = make_desc_sw128(smem_u32(smem + 65536), 32768, 1024);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem_base + (uint32_t)(it & 1) * 128;
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks)
+        mma_f16_ss_warp(d, desc_advance(ad0, (ks >> 2) * 16384 + (ks & 3) * 32), desc_advance(bd0, ks * 2048), idesc, ks != 0);
+    }
+    mma_commit_warp(&bar);
+    mbar_wait(&bar, 0, 0xA00);
+    const long long t1 = clock64();
+    if (tid == 0) clk_per_mma[blockIdx.x] = (float)(t1 - t0) / (float)(iters * 16);
+  } else if (!variant11 && tid == 0) {
     const int N = (variant == 2 || variant == 3 || variant == 4) ? 256 : 128;
     const bool b_mn = (variant == 0 || variant == 2), a_tmem = (variant >= 4);
     const uint32_t idesc = make_idesc_f16(128, N, 0, 0, b_mn ? 1 : 0);
@@ -410,7 +591,9 @@ __global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int variant, int i
         const uint64_t bd = b_mn ? make_desc_sw128(b0 + ks * 2048, 32768, 1024)
                                  : make_desc_sw128(b0 + (ks >> 2) * (N * 128) + (ks & 3) * 32, 16, 1024);
         if (a_tmem) mma_f16_ts(d, tmem_base + 256 + ks * 8, bd, idesc, ks != 0);
-        else mma_f16_ss(d, make_desc_sw128(a0 + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), bd, idesc, ks != 0);
+        else mma_f16_ss(alt ? tmem_base + (uint32_t)(ks & alt) * 128 : d, make_desc_sw128(a0 + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), bd, idesc,
+                        alt ? (it | (ks > alt)) != 0 : ks != 0);
+        if (commit_every && ((ks + 1) % commit_every) == 0) mma_commit(&bar2);
       }
     }
     mma_commit(&bar);
@@ -424,7 +607,7 @@ __global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int variant, int i
 }
 
 int tc_mma_bench(int variant, int ctas, int iters, float* clk_host, cudaStream_t st) {
-  DUDF_REQUIRE(variant >= 0 && variant <= 5 && ctas >= 1 && ctas <= 1024 && iters >= 1, "umma bench: bad arguments");
+  DUDF_REQUIRE(variant >= 0 && variant <= 11 && ctas >= 1 && ctas <= 1024 && iters >= 1, "umma bench: bad arguments");
   float* d = nullptr;
   DUDF_CUDA_OK(cudaMalloc(&d, ctas * sizeof(float)));
   const int smem = 196608 + 1024;

@@ -115,12 +115,12 @@ __device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigne
     }
 }
 
-// operand-image copy of a B tile for the weight-gradient GEMM (two 32 KB images), issued BEFORE the MMAs that read the
-// tile so that both proceed concurrently; tc_finish_subtile waits for its shared-memory reads before it publishes the
-// accumulator (the epilogue overwrites the tile after that).
+// operand-image copy of a B tile for the weight-gradient GEMM (two 32 KB images), issued by lane 0 of the MMA warp BEFORE
+// the MMAs that read the tile so that both proceed concurrently; tc_finish_subtile waits for its shared-memory reads
+// before the accumulator is published (the epilogue overwrites the tile after that).
 __device__ __forceinline__ void tc_copy_subtile(unsigned char* act, int s, unsigned char* img, int64_t ncb, int64_t cb0, int64_t pair, int layer,
                                                 uint64_t img_policy) {
-  if (img) {
+  if (img && (threadIdx.x & 31) == 0) {
     const int64_t cb = cb0 + (pair * 2 + s) * 2;
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
@@ -130,15 +130,22 @@ __device__ __forceinline__ void tc_copy_subtile(unsigned char* act, int s, unsig
     }
     bulk_commit();
   }
+  __syncwarp();
 }
 __device__ __forceinline__ void tc_finish_subtile(uint64_t* acc_ready, int s, bool copied) {
-  if (copied) bulk_wait_read0();
-  umma::mma_commit(&acc_ready[s]);
+  if (copied) {
+    if ((threadIdx.x & 31) == 0) bulk_wait_read0();
+    __syncwarp();
+  }
+  umma::mma_commit_warp(&acc_ready[s]);
 }
 
-// ---- MMA issuer (one thread).
+// ---- MMA issuer: the WHOLE warp runs this role in converged, warp-uniform code and one elected lane issues each
+// ---- tcgen05 instruction.  (Issued from a single-lane branch, every tcgen05.mma drags a register -> uniform-register
+// ---- election loop and a recomputed descriptor with it: 107-160 clocks per instruction for 64 clocks of tensor work,
+// ---- tools/umma_bench.py.  Warp-uniform issue with descriptors advanced by adds reaches 64.1.)
 // REUSE = false: per layer  A.h0 A.h1 | B.h0 B.h1  (sub-tile A/B, neuron half h): a sub-tile's accumulator is published as
-//   early as possible (best when the epilogue / HBM traffic is the limiter: training kernels).
+//   early as possible (training kernels).
 // REUSE = true:  per layer  A.h0 B.h0 | A.h1 B.h1: the four chunks of a half stay in the ring for both sub-tiles and are
 //   released after the second use, so weights cross L2 -> SM once per 256 columns (query kernel).
 // img_f / img_b != null: bulk-copy each finished B tile of a forward / reverse phase (two 32 KB operand images) to
@@ -151,11 +158,14 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
   static_assert(TC_STAGES >= 5, "a neuron half (4 chunks) must fit in the ring with one slot to prefetch into");
   constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
   constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
+  const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);       // chunk in ring slot 0, k = 0
+  const uint64_t b_desc0 = make_desc_sw128(smem_u32(act), 32768, 1024);     // sub-tile 0, k = 0
+  const bool skip = (dbg & 2) != 0;                         // pipeline diagnostics (tools/pipe_probe.py): keep the protocol, no MMAs
   uint32_t stage = 0, phase = 0;                            // ring position of the next chunk to be consumed for the first time
   uint32_t act_phase = 0;                                   // bit s = parity of act_ready[s]
+  const int n_tot = (dir == TC_DIR_BOTH) ? 2 * n_phase : n_phase;
   for (int64_t r = 0; r < rounds; ++r) {
     const int64_t pair = blockIdx.x + r * gridDim.x;
-    const int n_tot = (dir == TC_DIR_BOTH) ? 2 * n_phase : n_phase;
     for (int jt = 0; jt < n_tot; ++jt) {
       const bool backward = (dir == TC_DIR_BWD) || (jt >= n_phase);
       const int j = (jt >= n_phase) ? jt - n_phase : jt;
@@ -167,20 +177,20 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
           act_phase ^= 1u << s;
           tc_fence_after();
           tc_copy_subtile(act, s, img, ncb, cb0, pair, layer, img_policy);
-          const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
+          const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
           for (int h = 0; h < 2; ++h) {
             const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
             for (int kb = 0; kb < 4; ++kb) {
               mbar_wait(&full[stage], phase, 0x300 + stage);
               tc_fence_after();
-              const uint32_t a_addr = smem_u32(ring + stage * TC_CHUNK_BYTES);
+              const uint64_t a_desc = desc_advance(a_desc0, stage * TC_CHUNK_BYTES);
+              if (!skip) {
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                if (!(dbg & 2))
-                  mma_f16_ss(d_tmem, make_desc_sw128(a_addr + k4 * 32, 16, 1024),
-                             make_desc_sw128(act_s + (kb * 8 + k4 * 2) * 1024, 32768, 1024), idesc, (kb | k4) != 0);
-              if constexpr (CL == 1) mma_commit(&empty[stage]);
-              else mma_commit_multicast(&empty[stage], mask);
+                for (int k4 = 0; k4 < 4; ++k4)
+                  mma_f16_ss_warp(d_tmem, desc_advance(a_desc, k4 * 32), desc_advance(b_desc, (kb * 8 + k4 * 2) * 1024), idesc, (kb | k4) != 0);
+              }
+              if constexpr (CL == 1) mma_commit_warp(&empty[stage]);
+              else mma_commit_multicast_warp(&empty[stage], mask);
               if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -195,7 +205,7 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
               tc_fence_after();
               tc_copy_subtile(act, s, img, ncb, cb0, pair, layer, img_policy);
             }
-            const uint32_t act_s = smem_u32(act + s * TC_ACT_BYTES);
+            const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
             const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
             uint32_t st = stage, ph = phase;
             for (int kb = 0; kb < 4; ++kb) {
@@ -203,15 +213,15 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
                 mbar_wait(&full[st], ph, 0x300 + st);
                 tc_fence_after();
               }
-              const uint32_t a_addr = smem_u32(ring + st * TC_CHUNK_BYTES);
+              const uint64_t a_desc = desc_advance(a_desc0, st * TC_CHUNK_BYTES);
+              if (!skip) {
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                if (!(dbg & 2))     // dbg bit 1: pipeline diagnostics (tools/pipe_probe.py) — skip the MMAs, keep the protocol
-                  mma_f16_ss(d_tmem, make_desc_sw128(a_addr + k4 * 32, 16, 1024),
-                             make_desc_sw128(act_s + (kb * 8 + k4 * 2) * 1024, 32768, 1024), idesc, (kb | k4) != 0);
+                for (int k4 = 0; k4 < 4; ++k4)
+                  mma_f16_ss_warp(d_tmem, desc_advance(a_desc, k4 * 32), desc_advance(b_desc, (kb * 8 + k4 * 2) * 1024), idesc, (kb | k4) != 0);
+              }
               if (s == 1) {
-                if constexpr (CL == 1) mma_commit(&empty[st]);
-                else mma_commit_multicast(&empty[st], mask);
+                if constexpr (CL == 1) mma_commit_warp(&empty[st]);
+                else mma_commit_multicast_warp(&empty[st], mask);
               }
               if (++st == TC_STAGES) { st = 0; ph ^= 1; }
             }

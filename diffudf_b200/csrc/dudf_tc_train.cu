@@ -242,7 +242,7 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
     if (warp == 8) {
       if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD);
     } else if (warp == 9) {
-      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, nullptr, ld >> 6, col0 >> 6, TC_DIR_FWD);
+      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, nullptr, ld >> 6, col0 >> 6, TC_DIR_FWD);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -426,7 +426,7 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
     if (warp == 8) {
       if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BWD);
     } else if (warp == 9) {
-      if (lane == 0) tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD);
+      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -497,25 +497,25 @@ tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const uns
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0, 0);
-      uint32_t stage = 0, phase = 0;
-      for (int64_t cb = cb0; cb < cb1; ++cb) {
-        mbar_wait(&full[stage], phase, 0x600 + stage);
-        tc_fence_after();
-        const uint32_t z_addr = smem_u32(smem + stage * 2 * TC_IMG_BYTES);
-        const uint32_t a_addr = z_addr + TC_IMG_BYTES;
+    // whole warp, warp-uniform code, one elected lane issues (see tc_mma_role)
+    constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0, 0);
+    const uint64_t desc0 = make_desc_sw128(smem_u32(smem), 16, 1024);
+    uint32_t stage = 0, phase = 0;
+    for (int64_t cb = cb0; cb < cb1; ++cb) {
+      mbar_wait(&full[stage], phase, 0x600 + stage);
+      tc_fence_after();
+      const uint64_t z_desc = desc_advance(desc0, stage * 2 * TC_IMG_BYTES);
+      const uint64_t a_desc = desc_advance(z_desc, TC_IMG_BYTES);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            mma_f16_ss(tmem_base + h * 256, make_desc_sw128(z_addr + h * 16384 + k4 * 32, 16, 1024),
-                       make_desc_sw128(a_addr + k4 * 32, 16, 1024), idesc, (cb > cb0) || (k4 != 0));
-        mma_commit(&empty[stage]);
-        if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
-      }
-      mma_commit(done);
+        for (int k4 = 0; k4 < 4; ++k4)
+          mma_f16_ss_warp(tmem_base + h * 256, desc_advance(z_desc, h * 16384 + k4 * 32), desc_advance(a_desc, k4 * 32), idesc,
+                          (cb > cb0) || (k4 != 0));
+      mma_commit_warp(&empty[stage]);
+      if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
     }
+    mma_commit_warp(done);
   } else if (cb1 > cb0) {
     // warps 0-3: drain the two 128 x 256 accumulators into the gradient with vector reductions
     mbar_wait(done, 0, 0x700);
@@ -864,8 +864,7 @@ tt_fused_kernel(const unsigned char* __restrict__ packed, NetView net, GradView 
     if (warp == 8) {
       if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BOTH, 0, fd.flags >> 8);
     } else if (warp == 9) {
-      if (lane == 0)
-        tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, Zimg, ncb, 0, TC_DIR_BOTH, fd.flags >> 8,
+      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, Zimg, ncb, 0, TC_DIR_BOTH, fd.flags >> 8,
                        (fd.flags & 2) ? l2_policy_evict_first() : 0ull);
     }
   } else {

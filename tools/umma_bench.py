@@ -11,8 +11,10 @@ torch.cuda.init()
 L = _lib.lib()
 names = ["A smem K-major, B smem MN-major, N=128 (current)", "A smem K-major, B smem K-major, N=128",
          "A smem K-major, B smem MN-major, N=256", "A smem K-major, B smem K-major, N=256",
-         "A TMEM, B smem K-major, N=256", "A TMEM, B smem K-major, N=128"]
-for ctas in (1, 148):
+         "A TMEM, B smem K-major, N=256", "A TMEM, B smem K-major, N=128",
+         "as current, commit every 4 MMAs", "as current, commit every 8 MMAs", "as current, commit every 16 MMAs",
+         "as current, alternate 2 accumulators", "as current, alternate 4 accumulators", "as current, warp-uniform issue + descriptor adds"]
+for ctas in (148,):
     for v, name in enumerate(names):
         out = ctypes.c_float(0)
         _lib.check(L.dudf_bench_umma(v, ctas, 512, ctypes.byref(out)), "dudf_bench_umma")
