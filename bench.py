@@ -280,21 +280,28 @@ def run_ours(args, rank, local_rank, world):
     prof = {}
     if True:      # every rank runs these steps (they contain the gradient all-reduce); rank 0's events are reported
         eng = model._engine_synced()
-        names = ["jet_forward_multi", "loss", "jet_backward_multi", "jet_wgrad"]
+        names = ["jet_forward_multi", "loss", "jet_backward_multi", "jet_wgrad", "train_step_fused"]
         orig = {k: getattr(eng, k) for k in names}
         events = []
 
+        def timed(name, fn, *a, **kw):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **kw)
+            t.record()
+            events.append((name, s, t))
+            return r
+
         def wrap(name, fn):
-            def inner(*a, **kw):
-                s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                r = fn(*a, **kw)
-                t.record()
-                events.append((name, s, t))
-                return r
-            return inner
+            return lambda *a, **kw: timed(name, fn, *a, **kw)
+
+        def fused_split(mode, segs, P_global, w, alpha, terms, amax_prev, amax_next, scratch, A, Zb, ld, gW, gb, flags=3):
+            # the same two launches as the single C call, timed separately: fused forward+loss+reverse sweep, then the weight gradients
+            timed("fused_fwd_loss_bwd", orig["train_step_fused"], mode, segs, P_global, w, alpha, terms, amax_prev, amax_next, scratch, A, Zb, ld,
+                  gW, gb, flags | 4)
+            timed("jet_wgrad", orig["jet_wgrad"], Zb, A, ld, ld, gW, "tc16", seed_absmax=amax_prev)
         for k in names:
-            setattr(eng, k, wrap(k, orig[k]))
+            setattr(eng, k, fused_split if k == "train_step_fused" else wrap(k, orig[k]))
         reps = 3
         for i in range(reps):
             step_resident(i)
@@ -338,13 +345,19 @@ def run_ours(args, rank, local_rank, world):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
     third = n_on * F[10] + (P - n_on) * F[4]        # forward = reverse sweep = weight gradient in algorithmic FLOPs
-    flops = {"jet_forward_multi": third, "jet_backward_multi": third, "jet_wgrad": third}
+    flops = {"jet_forward_multi": third, "jet_backward_multi": third, "jet_wgrad": third, "fused_fwd_loss_bwd": 2 * third}
+    traffic = {}
+    try:        # DRAM bytes per launch from the committed ncu --set full capture of the same kernels (tools/ncu_summary.py)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    except Exception:
+        pass
     dom = max((k for k in prof if k in flops), key=lambda k: prof[k]) if prof else None
     roof = None
     if dom:
         ach = flops[dom] / (prof[dom] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "peak_source": peak_src, "ms": prof[dom],
+                "traffic": traffic.get(dom), "traffic_source": traffic.get("source") if dom in traffic else None,
+                "peak_source": peak_src, "ms": prof[dom],
                 "step_share": prof[dom] / max(sum(prof.values()), 1e-9),
                 "kernel_ms": {k: round(v, 4) for k, v in prof.items()},
                 "step_algorithmic_gflop": (n_on * F[10] + (P - n_on) * F[4]) * 3 / 1e9}
@@ -361,7 +374,8 @@ def run_ours(args, rank, local_rank, world):
                                    "(w=[1e4,1e4,1e4,1e3], alpha=100, Adam lr 1e-4), 29 970 rows per GPU per step [9990 on|9990 far|9990 near]",
                        "rows_per_gpu": P, "global_rows": world * P, "parallelism": f"dp{world}",
                        "precision": "tcgen05 fp16-operand step (tc16)" if args.precision == "tc16" else "fp32 CUDA-core step",
-                       "l2": "per-step working set (activation stashes, ~4 GB) exceeds the 126 MB L2; 4 distinct batches cycled"},
+                       "l2": "per-step working set (operand images of the weight-gradient GEMM, ~1.3 GB written + read per step) exceeds the "
+                             "126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / args.steps,
                     "mode": "diffudf_b200.train.BatchFeeder: batch i+1 copied from pinned host memory on a side stream during step i; "

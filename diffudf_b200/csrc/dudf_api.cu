@@ -394,7 +394,7 @@ int dudf_train_step_fused(dudf_ctx* c, int mode, const dudf_train_segment* segs,
   for (int k = 0; k < 4; ++k) fl.w[k] = w_host[k];
   cudaStream_t st = (cudaStream_t)stream;
   rc = tc_train_fused(c->tc_packed, c->view(), gv, ts, nseg, fl, (float*)scratch, A, Zb, ld, c->sms, st);
-  if (rc) return rc;
+  if (rc || (flags & DUDF_FUSED_NO_WGRAD)) return rc;
   return tc_train_wgrad(c->view(), gv, Zb, A, ld, amax_prev, c->sms, st);
 }
 
