@@ -123,6 +123,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def aux_device_sampler(dev, trainer):
+    """batches drawn on the device from a 200k-point oriented cloud (diffudf_b200.dataset.PointCloud,
+    src/dataset.py:80-131 semantics) — the sampler alone, and sampler + training step back to back through the public loop."""
+    import numpy as np
+    import torch
+    from diffudf_b200 import synthetic
+    from diffudf_b200.dataset import PointCloud
+    shape = synthetic.make_shape(0)
+    pts, nrm = shape.sample_surface(200000, np.random.default_rng(0))
+    ds = PointCloud(pts.astype(np.float32), nrm.astype(np.float32), 30000, [0.333, 0.666], 20, dev, seed=5)
+    out = {}
+    for _ in ds:
+        break
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    nb = 0
+    for _ in ds:
+        nb += 1
+    t.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(t) / nb
+    rows = ds.samplesOnSurface + ds.samplesFarSurface
+    out["sampler_pc_200k_ms_per_batch"] = ms
+    out["sampler_pc_200k_rows_per_s"] = rows / (ms * 1e-3)
+    out["sampler_pc_200k_pair_distances_per_s"] = (ds.samplesFarSurface // 2) * 200000 / (ms * 1e-3)
+    for x, n, d in ds:      # warm the step on this batch shape
+        trainer.step("s1", x[0], n[0], d[0, :, 0], ds.samplesOnSurface, W_S1, ALPHA, LR)
+        break
+    s.record()
+    nb = 0
+    for x, n, d in ds:
+        trainer.step("s1", x[0], n[0], d[0, :, 0], ds.samplesOnSurface, W_S1, ALPHA, LR)
+        nb += 1
+    t.record()
+    torch.cuda.synchronize()
+    out["train_with_device_sampler_points_per_s"] = rows * nb / (s.elapsed_time(t) * 1e-3)
+    return out
+
+
 def aux_full_size_queries(dev):
     """BASELINE configs 3-5 at full size on one GPU (tensor-core path, trained fixture weights when present):
     512^3 grid for marching cubes, evaluate() with host buffers, 1024^2 sphere tracing, 2 M-point NDF projection."""
@@ -331,6 +370,8 @@ def run_ours(args, rank, local_rank, world):
         del df, vecs
         try:
             aux.update(aux_full_size_queries(dev))
+            if args.precision == "tc16":
+                aux.update(aux_device_sampler(dev, FusedTrainer(SIREN(3, 1, [256] * 8, w0=30).to(dev), precision="tc16")))
         except Exception as exc:          # the secondary numbers must never cost the headline line
             aux["full_size_error"] = repr(exc)[:200]
     if rank != 0:

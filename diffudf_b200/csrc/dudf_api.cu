@@ -423,6 +423,33 @@ int dudf_loss_s2_finish(const double* stats, float w0, float w1, double* terms, 
   return s2_finish(stats, w0, w1, terms, (cudaStream_t)stream);
 }
 
+static int device_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int dudf_sample_batch_pc(const float* surf_pts, const float* surf_normals, int64_t n_surf, int64_t n_on, int64_t n_far, int64_t n_near,
+                         float sigma, const float* lo_host, const float* hi_host, uint64_t seed, uint64_t batch_index,
+                         const int64_t* on_idx, const float* far_pts, const int64_t* near_idx, const float* near_off, float* coords,
+                         float* normals, float* dist, void* stream) {
+  DUDF_REQUIRE(surf_pts && surf_normals && coords && normals && dist, "dudf_sample_batch_pc: null argument");
+  DUDF_REQUIRE(n_surf > 0 && n_on >= 0 && n_far >= 0 && n_near >= 0, "dudf_sample_batch_pc: bad sizes");
+  DUDF_REQUIRE(n_near == 0 || n_on > 0, "dudf_sample_batch_pc: near rows are displaced ON rows; n_on must be positive");
+  SampleArgs a;
+  a.surf_pts = surf_pts; a.surf_nrm = surf_normals; a.n_surf = n_surf; a.n_on = n_on; a.n_far = n_far; a.n_near = n_near;
+  a.sigma = sigma; a.seed = seed; a.batch = batch_index;
+  for (int k = 0; k < 3; ++k) { a.lo[k] = lo_host ? lo_host[k] : -1.f; a.hi[k] = hi_host ? hi_host[k] : 1.f; }
+  a.on_idx = on_idx; a.far_pts = far_pts; a.near_idx = near_idx; a.near_off = near_off;
+  a.coords = coords; a.normals = normals; a.dist = dist;
+  return sample_batch_pc(a, device_sms(), (cudaStream_t)stream);
+}
+
+int dudf_nearest_distance(const float* queries, int64_t n_q, const float* cloud, int64_t n_x, float* dist, void* stream) {
+  DUDF_REQUIRE(queries && cloud && dist, "dudf_nearest_distance: null argument");
+  return nn_distance(queries, n_q, cloud, n_x, dist, device_sms(), (cudaStream_t)stream);
+}
+
 int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    int64_t t, void* stream) {
   DUDF_REQUIRE(p && g && m && v, "dudf_adam_step: null argument");

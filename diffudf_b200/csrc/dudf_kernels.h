@@ -85,6 +85,24 @@ int tc_train_backward(const void* packed, const NetView& net, const GradView& gr
                       const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st);
 int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,
                    int sms, cudaStream_t st);
+// ---- device-side batch sampler for oriented point clouds (dudf_sampler.cu; src/dataset.py:72-131) ----
+struct SampleArgs {
+  const float* surf_pts;    // [n_surf][3]
+  const float* surf_nrm;    // [n_surf][3]
+  int64_t n_surf, n_on, n_far, n_near;
+  float sigma;              // std of the normal offsets of the near rows (0.01 in the reference)
+  float lo[3], hi[3];       // domain of the far rows
+  uint64_t seed, batch;     // Philox key / counter prefix
+  const int64_t* on_idx;    // optional caller-supplied draws (parity tests): [n_on] cloud indices,
+  const float* far_pts;     //   [n_far][3] domain points,
+  const int64_t* near_idx;  //   [n_near] indices into the ON rows,
+  const float* near_off;    //   [n_near] offsets
+  float* coords;            // out [P][3]
+  float* normals;           // out [P][3]
+  float* dist;              // out [P]
+};
+int sample_batch_pc(const SampleArgs& a, int sms, cudaStream_t st);
+int nn_distance(const float* q, int64_t nq, const float* X, int64_t nx, float* dist, int sms, cudaStream_t st);
 int loss_seeds(const LossArgs& a, cudaStream_t st);
 int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st);
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);

@@ -11,11 +11,12 @@
 // A sub-tile is 128 columns: 128 points (value only), 32 points x 4 channels, or 12 points x 10 channels
 // (+ 8 idle columns).  Second-order channels are carried scaled by KAPPA = 1/8 (fp16 range head-room).
 //
-// Pipeline per CTA (persistent, one CTA per SM, 320 threads):
+// Pipeline per CTA (persistent, one CTA per SM, 384 threads = 3 warpgroups; setmaxnreg moves registers to the epilogue):
 //   warps 0-7  epilogue: TMEM -> registers -> sin/cos jet -> fp16 -> swizzled smem (+ first and last layer)
 //   warp  8    producer: streams 16 KB weight chunks (128 neurons x 64 k) global/L2 -> smem ring with
 //              cp.async.bulk (TMA engine) completing on mbarriers
-//   warp  9    MMA issuer: one thread issues tcgen05.mma; tcgen05.commit frees ring slots / publishes accumulators
+//   warp  9    MMA issuer: the whole warp runs warp-uniform code, one elected lane issues tcgen05.mma; tcgen05.commit
+//              frees ring slots / publishes accumulators
 // Two sub-tiles are in flight so that the MMAs of one overlap the epilogue of the other.
 #include <cuda_fp16.h>
 #include <cstdlib>

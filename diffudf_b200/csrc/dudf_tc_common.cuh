@@ -17,7 +17,7 @@ namespace dudf {
 
 constexpr int TC_CHUNK_BYTES = 128 * 64 * 2;   // one weight chunk: 128 neurons x 64 k, fp16
 constexpr int TC_STAGES = 5;
-constexpr int TC_THREADS = 384;            // warpgroups 0-1: epilogue (216 regs), warpgroup 2: producer + MMA issuer (40 regs)
+constexpr int TC_THREADS = 384;            // warpgroups 0-1: epilogue (216 regs), warpgroup 2: producer + MMA issuer (56 regs)
 constexpr int TC_REGS_EPI = 216;
 constexpr int TC_REGS_AUX = 56;            // 256 * 216 + 128 * 56 = 62 464 <= 65 536 registers per SM
 constexpr int TC_ACT_BYTES = 65536;

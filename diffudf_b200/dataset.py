@@ -1,0 +1,87 @@
+"""Drop-in for the point-cloud half of /root/reference/src/dataset.py: `PointCloud(onlyPCloud=True)` (:134-185),
+`sampleTrainingDataPC` (:80-131) and `shortestDistance` (:72-78), produced on the device by
+`dudf_sample_batch_pc` / `dudf_nearest_distance` (include/dudf_b200.h) — no host sampling, no host->device copy.
+
+The mesh half (`sampleTrainingData`, Open3D RaycastingScene signed distances, :14-70) and `.ply` IO are not rebuilt
+(Open3D is a third-party consumer): construct from arrays.  Iterating yields the reference's triple
+`(coords (1, P, 3), normals (1, P, 3), sdf (1, P, 1))`, fp32, as CUDA tensors ordered [on | far | near]."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _as_dev(t, device, dtype=torch.float32):
+    return torch.as_tensor(t).to(device=device, dtype=dtype).contiguous()
+
+
+def shortestDistance(P, X):
+    """Distance from each row of P to its nearest row of X (CUDA tensors (n, 3), (m, 3)) -> (n,) fp32."""
+    if P.device.type != "cuda":
+        raise RuntimeError("diffudf_b200.dataset.shortestDistance needs CUDA (sm_100) tensors; there is no CPU fallback")
+    P = P.detach().to(torch.float32).contiguous()
+    X = X.detach().to(device=P.device, dtype=torch.float32).contiguous()
+    out = torch.empty(P.shape[0], device=P.device, dtype=torch.float32)
+    if P.shape[0] == 0:
+        return out
+    with torch.cuda.device(P.device):
+        _lib.check(_lib.lib().dudf_nearest_distance(P.data_ptr(), P.shape[0], X.data_ptr(), X.shape[0], out.data_ptr(),
+                                                    _lib.current_stream()), "dudf_nearest_distance")
+    return out
+
+
+def sampleTrainingDataPC(surface_pc, surface_normals, samplesOnSurface, samplesOffSurface, domainBounds=([-1, -1, -1], [1, 1, 1]),
+                         seed=0, batch_index=0, draws=None, sigma=0.01):
+    """One batch (reference :80-131).  `draws` (optional): dict with any of on_idx (n_on,) int64, far (n_far, 3),
+    near_idx (n_near,) int64, near_off (n_near,) — replaces the corresponding Philox draws (parity tests)."""
+    dev = surface_pc.device
+    if dev.type != "cuda":
+        raise RuntimeError("diffudf_b200.dataset.sampleTrainingDataPC needs the cloud on a CUDA (sm_100) device; there is no CPU fallback")
+    X = surface_pc.detach().to(torch.float32).contiguous()
+    N = surface_normals.detach().to(device=dev, dtype=torch.float32).contiguous()
+    n_on, n_off = int(samplesOnSurface), int(samplesOffSurface)
+    n_far = n_off // 2
+    n_near = n_off - n_far
+    P = n_on + n_off
+    coords = torch.empty(1, P, 3, device=dev, dtype=torch.float32)
+    normals = torch.empty(1, P, 3, device=dev, dtype=torch.float32)
+    sdf = torch.empty(1, P, 1, device=dev, dtype=torch.float32)
+    d = draws or {}
+    keep = [_as_dev(d[k], dev, torch.int64 if k.endswith("idx") else torch.float32) if d.get(k) is not None else None
+            for k in ("on_idx", "far", "near_idx", "near_off")]
+    lo = (ctypes.c_float * 3)(*[float(v) for v in domainBounds[0]])
+    hi = (ctypes.c_float * 3)(*[float(v) for v in domainBounds[1]])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dudf_sample_batch_pc(X.data_ptr(), N.data_ptr(), X.shape[0], n_on, n_far, n_near, float(sigma), lo, hi,
+                                                   int(seed) & (2 ** 64 - 1), int(batch_index), _lib.ptr(keep[0]), _lib.ptr(keep[1]),
+                                                   _lib.ptr(keep[2]), _lib.ptr(keep[3]), coords.data_ptr(), normals.data_ptr(),
+                                                   sdf.data_ptr(), _lib.current_stream()), "dudf_sample_batch_pc")
+    return coords, normals, sdf
+
+
+class PointCloud(torch.utils.data.IterableDataset):
+    """Iterable of device-generated batches; same attributes as the reference dataset (`batchesPerEpoch`,
+    `samplesOnSurface`, `samplesFarSurface`) so the training loops take it unchanged."""
+
+    def __init__(self, points, normals, batchSize, samplingPercentiles, batchesPerEpoch, device, seed=0):
+        super().__init__()
+        self.device = torch.device(device)
+        self.surface_pc = _as_dev(np.asarray(points) if not torch.is_tensor(points) else points, self.device)
+        self.surface_normals = _as_dev(np.asarray(normals) if not torch.is_tensor(normals) else normals, self.device)
+        if self.surface_pc.ndim != 2 or self.surface_pc.shape[1] != 3 or self.surface_pc.shape != self.surface_normals.shape:
+            raise ValueError("PointCloud: points and normals must both be (n, 3)")
+        self.batchSize = batchSize
+        self.samplesOnSurface = int(batchSize * samplingPercentiles[0])
+        self.samplesFarSurface = int(batchSize * samplingPercentiles[1])
+        self.batchesPerEpoch = batchesPerEpoch
+        self.seed = seed
+        self.batches_drawn = 0
+
+    def __iter__(self):
+        for _ in range(self.batchesPerEpoch):
+            out = sampleTrainingDataPC(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
+                                       seed=self.seed, batch_index=self.batches_drawn)
+            self.batches_drawn += 1
+            yield out

@@ -64,7 +64,7 @@ class TrainCore:
 
     def _stashes(self, L, ld, prec, need_z=True):
         Z = self._buf("Z", (L, 256, ld)) if need_z else None
-        if prec == "tc16":       # fp16 operand planes [layer][k-block][column][64 neurons]; zero tails are part of the contract
+        if prec == "tc16":       # fp16 operand images [layer][column block of 64][256 neurons][64 columns]; zero tails are part of the contract
             A = self._buf("A", (L, 4, ld, 64), torch.float16, zero=True)
             Zb = self._buf("Zb", (L, 4, ld, 64), torch.float16, zero=True)
         else:

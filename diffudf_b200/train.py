@@ -95,6 +95,11 @@ class BatchFeeder:
     def _stage(self, slot, batch):
         x, n, d = batch
         shapes = ((x.numel() // 3, 3), (n.numel() // 3, 3), (d.numel(),))
+        if all(torch.is_tensor(t) and t.device == self.device for t in (x, n, d)):
+            # produced on the device (diffudf_b200.dataset.PointCloud) in the consumer's stream order: nothing to copy
+            self.bufs[slot] = tuple(t.reshape(s) for t, s in zip((x, n, d), shapes))
+            self.ready[slot].record(torch.cuda.current_stream(self.device))
+            return
         if self.bufs[slot] is None or any(b.shape != s for b, s in zip(self.bufs[slot], shapes)):
             self.bufs[slot] = tuple(torch.empty(s, device=self.device, dtype=torch.float32) for s in shapes)
         with torch.cuda.stream(self.copy_stream):

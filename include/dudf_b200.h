@@ -127,8 +127,9 @@ int dudf_jet_forward_multi(dudf_ctx* ctx, const dudf_segment* segs_host, int nse
 int dudf_jet_backward_multi(dudf_ctx* ctx, const dudf_segment* segs_host, int nseg, const float* seed_absmax, const void* Z,
                             void* Zb, int64_t ld, float* const* gW_host, float* const* gb_host, int precision, void* stream);
 /* With DUDF_PRECISION_TC16 the stashes change type: Z is fp32 [n_hidden][ld][256] (column-group / thread-major, private
- * to the kernel pair; ld a multiple of 64), A and Zb are fp16 operand planes [n_hidden][4 k-blocks][ld][64 neurons]
- * (128-byte swizzled rows, zero-initialised by the caller), and the reverse sweep runs
+ * to the kernel pair; ld a multiple of 64), A and Zb are fp16 operand images [n_hidden][ld / 64][256 neurons][64 columns]
+ * (32 KB each, 128-byte swizzled rows: the K-major operands of the weight-gradient GEMM; zero-initialised by the
+ * caller), and the reverse sweep runs
  * under a power-of-two loss scale derived from seed_absmax (1 device float, zeroed by the caller before the dudf_loss
  * calls of a step, which raise it with atomicMax; all dudf_loss calls of a step must precede its first backward). */
 /* Fused training step on the tensor-core path (loss_s1 / loss_siren; train.py:204-216 = loss_fn + backward):
@@ -166,6 +167,19 @@ int dudf_loss(int mode, const float* packed, int nch, const float* normals, cons
               double* s2_stats, void* stream);
 int dudf_loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, void* stream);
 int dudf_loss_s2_finish(const double* stats, float w0, float w1, double* terms, void* stream);
+/* ---- Batch sampler for oriented point clouds (src/dataset.py:72-131, PointCloud(onlyPCloud=True)) ----
+ * dudf_sample_batch_pc replaces sampleTrainingDataPC: writes one [n_on | n_far | n_near] batch (coords [P][3], normals
+ * [P][3], dist [P], fp32, P = n_on + n_far + n_near; the reference's samplesFar = samplesOffSurface // 2 split is the
+ * caller's) entirely on the device: cloud rows, uniform points of [lo, hi] with their nearest-cloud-point distance,
+ * cloud rows displaced along the normal by N(0, sigma) with distance |offset|.  Draws come from Philox4x32-10 keyed by
+ * (seed, batch_index) unless the caller supplies them (any of on_idx / far_pts / near_idx / near_off may be NULL).
+ * dudf_nearest_distance replaces shortestDistance (:72-78): dist[i] = min_j |q_i - X_j| without materialising the
+ * n_q x n_x matrix.  All pointers device. */
+int dudf_sample_batch_pc(const float* surf_pts, const float* surf_normals, int64_t n_surf, int64_t n_on, int64_t n_far, int64_t n_near,
+                         float sigma, const float* lo_host, const float* hi_host, uint64_t seed, uint64_t batch_index,
+                         const int64_t* on_idx, const float* far_pts, const int64_t* near_idx, const float* near_off, float* coords,
+                         float* normals, float* dist, void* stream);
+int dudf_nearest_distance(const float* queries, int64_t n_q, const float* cloud, int64_t n_x, float* dist, void* stream);
 /* torch.optim.Adam.step as configured in train.py:334-337 (betas, eps given explicitly, no weight decay);
  * t is the 1-based step count.  Flat fp32 arrays of n elements. */
 int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

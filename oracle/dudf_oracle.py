@@ -542,3 +542,32 @@ def project_points(params, samples, num_steps, gt_mode, alpha, w0=30.0, dtype=np
         gn = np.linalg.norm(g, axis=1, keepdims=True)
         samples = samples - steps * (g / gn)
     return samples, steps, g, H
+
+
+# ---------------------------------------------------------------------------------------------
+# Point-cloud batch sampler: src/dataset.py:72-131 with the random draws as inputs
+# ---------------------------------------------------------------------------------------------
+def shortest_distance(P, X):
+    """Distance from each row of P to its nearest row of X, with the reference's expansion
+    sqrt(min_x(|x|^2 - 2 p.x) + |p|^2) (src/dataset.py:72-78)."""
+    sqP = np.sum(P * P, axis=1)
+    sqX = np.sum(X * X, axis=1)
+    m = np.min(sqX[None, :] - 2.0 * (P @ X.T), axis=1)
+    return np.sqrt(m + sqP)
+
+
+def sample_training_data_pc(surf_pts, surf_nrm, n_on, n_off, on_idx, far, near_idx, near_off):
+    """One [on | far | near] batch from an oriented point cloud (src/dataset.py:80-131).  Draws: on_idx (n_on,) indices
+    into the cloud, far (n_off // 2, 3) uniform domain points, near_idx (n_near,) indices into the ON rows, near_off
+    (n_near, 1) normal offsets.  Returns coords (1, P, 3), normals (1, P, 3), sdf (1, P, 1), float32."""
+    X = np.asarray(surf_pts, np.float64)
+    Nn = np.asarray(surf_nrm, np.float64)
+    on_p, on_n = X[on_idx], Nn[on_idx]
+    far = np.asarray(far, np.float64)
+    far_d = shortest_distance(far, X)
+    off = np.asarray(near_off, np.float64).reshape(-1, 1)
+    near_p = on_p[near_idx] + on_n[near_idx] * off
+    coords = np.vstack([on_p, far, near_p])
+    normals = np.vstack([on_n, np.zeros((n_off, 3))])
+    sdf = np.concatenate([np.zeros(n_on), far_d, np.abs(off[:, 0])])[:, None]
+    return coords.astype(np.float32)[None], normals.astype(np.float32)[None], sdf.astype(np.float32)[None]

@@ -158,3 +158,13 @@ def test_autograd_port_matches_reference_fixtures(tag, golden, weights):
     E = golden(f"evaluate_{tag}.npz")
     f, g, H = AP.evaluate(AP.make_params(weights[tag], requires_grad=False), E["x"][:300], True, True)
     assert rel_max(f, E["f"][:300]) < 1e-5 and rel_max(g, E["g"][:300]) < 1e-5 and rel_max(H, E["H"][:300]) < 1e-5
+
+
+def test_sampler_oracle_matches_reference_outputs(golden, oracle):
+    """src/dataset.py:72-131 (sampleTrainingDataPC, shortestDistance) run unmodified on CPU -> tests/golden/sampler_pc.npz."""
+    g = golden("sampler_pc.npz")
+    c, n, s = oracle.sample_training_data_pc(g["surf_pts"], g["surf_nrm"], int(g["n_on"]), int(g["n_off"]), g["on_idx"], g["far"],
+                                             g["near_idx"], g["near_off"])
+    assert np.array_equal(c, g["coords"]) and np.array_equal(n, g["normals"]) and np.array_equal(s, g["sdf"])
+    assert np.abs(oracle.shortest_distance(g["sd_queries"], g["surf_pts"].astype(np.float64)) - g["sd64"]).max() < 1e-14
+    assert np.abs(g["sd32"] ** 2 - g["sd64"] ** 2).max() < 5e-6        # what fp32 costs the reference's own expansion
