@@ -25,6 +25,19 @@ ALPHA = 100.0
 LR = 1e-4
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def make_batches(n_batches, seed, rows=30000):
     import numpy as np
     from diffudf_b200 import synthetic
@@ -120,7 +133,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "probe_s": round(time.perf_counter() - t_probe, 1)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def aux_device_sampler(dev, trainer):
@@ -422,7 +435,7 @@ def run_ours(args, rank, local_rank, world):
                     "mode": "diffudf_b200.train.BatchFeeder: batch i+1 copied from pinned host memory on a side stream during step i; "
                             "the 4 loss terms of every step copied to pinned host memory; one synchronisation at the end"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "aux": aux}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -437,7 +450,12 @@ def main():
                     help="arithmetic of the training step: tcgen05 fp16-operand MMAs (default) or fp32 CUDA cores")
     args = ap.parse_args()
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints ONE JSON line on stdout: everything else that writes to fd 1 (NCCL's version banner comes from C) goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
