@@ -364,6 +364,29 @@ def run_ours(args, rank, local_rank, world):
             prof[tag] = prof.get(tag, 0.0) + s.elapsed_time(t) / reps
     # ---- field queries (secondary metric: UDF+grad queries/s on a dense grid) ----
     aux = {}
+    if world > 1:
+        # BASELINE's second metric at N GPUs: the 512^3 grid sharded by contiguous slabs of the flat index (no data-path
+        # collective), then gathered on every rank (all-gather of 2.15 GB); max over ranks, like the headline
+        from diffudf_b200.parallel import extract_fields_sharded, shard_range
+        from diffudf_b200.render_mc import extract_fields
+        model.precision = "tc16"
+        Ng = 512
+        lo, hi = shard_range(Ng ** 3, rank, world)
+        extract_fields(model, None, 64, "tanh", dev, ALPHA)
+        barrier()
+        q0, q1, q2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        q0.record()
+        df, vecs = extract_fields(model, None, Ng, "tanh", dev, ALPHA, first=lo, count=hi - lo)
+        q1.record()
+        del df, vecs
+        df, vecs = extract_fields_sharded(model, Ng, "tanh", ALPHA, dp)
+        q2.record()
+        barrier()
+        del df, vecs
+        tq = torch.tensor([q0.elapsed_time(q1), q1.elapsed_time(q2)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        aux["grid512_sharded_compute_queries_per_s"] = Ng ** 3 / (float(tq[0]) * 1e-3)
+        aux["grid512_sharded_compute_plus_allgather_queries_per_s"] = Ng ** 3 / (float(tq[1]) * 1e-3)
     if rank == 0:
         eng = model._engine_synced()
         for prec, N in (("tc16", 256), ("fp32", 128)):
