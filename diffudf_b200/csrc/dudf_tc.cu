@@ -148,7 +148,7 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
           if (l == 0) {
             // first layer in fp32 on CUDA cores: u0 = w0 (W0 x + b0); derivative channels are w0 W0[:, i]
 #pragma unroll 1
-            for (int g = 0; g < C::NGRP; ++g) {
+            for (int g = 0; g < (((out.flags >> 8) & 8) ? 0 : C::NGRP); ++g) {      // flags bit 11: diagnostics, skip
               float u[C::GC];
               tc_first_layer_group<NCH, C::GC>(u, xs + (s * C::PT + g * (C::GC / NCH)) * 3, w0, r0x, r0y, r0z, b0);
               tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
@@ -172,7 +172,7 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&act_ready[s]);
-          } else {
+          } else if (!((out.flags >> 8) & 8)) {
             // ---- output layer (256 -> 1 per channel) from the fp16 tile, then per-point finalisation ----
             tc_epi_bar();
             tc_output_dot<C::NV>(act + s * TC_ACT_BYTES, wl_s, os + s * 256, tid);

@@ -19,7 +19,9 @@ vecs = torch.empty(cnt, 3, device="cuda")
 H = None
 for order_name, want_h in (("f+grad (4 ch)", False), ("f+grad+hess (10 ch)", True)):
     for name, dbg in (("full", 0), ("no MMA", 2 << 8), ("no epilogue math", 1 << 8), ("neither", 3 << 8),
-                      ("no weight streaming", 4 << 8), ("no weights, no epilogue math", 5 << 8)):
+                      ("no weight streaming", 4 << 8), ("no weights, no epilogue math", 5 << 8),
+                      ("no weights, no MMA", 6 << 8), ("no weights, neither", 7 << 8),
+                      ("protocol only (no first/output layer either)", 15 << 8), ("full minus first/output layer", 8 << 8)):
         flags = 3 | dbg
         for rep in range(2):
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
