@@ -49,6 +49,7 @@ SIGNATURES = {
                              ctypes.POINTER(c_float), ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p],
     "dudf_nearest_distance": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
+    "dudf_debug_set_trace": [c_void_p],
     "dudf_version": [],
     "dudf_launch_count": [],
     "dudf_create": [c_int, c_float, c_float, ctypes.POINTER(c_void_p)],

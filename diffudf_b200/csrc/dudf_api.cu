@@ -467,4 +467,9 @@ int dudf_bench_umma(int variant, int ctas, int iters, float* clk_per_mma_host) {
   return tc_mma_bench(variant, ctas, iters, clk_per_mma_host, 0);
 }
 
+int dudf_debug_set_trace(void* device_buffer) {
+  tc_set_trace((unsigned long long*)device_buffer);
+  return 0;
+}
+
 }  // extern "C"

@@ -16,6 +16,7 @@ struct QueryOut {
   float* packed;   // [P][NCH] raw channels (training path)
   int flags;       // DUDF_Q_*
   float alpha;
+  unsigned long long* trace;   // diagnostics (tools/trace_probe.py): event log of CTA 0, or null
 };
 
 // ---- fp32 CUDA-core path (dudf_simt.cu) ----
@@ -35,6 +36,7 @@ int tc_pack(const NetView& net, void* packed, cudaStream_t st);
 int tc_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN,
                int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
 int tc_selftest(int variant, float* max_err, cudaStream_t st);
+void tc_set_trace(unsigned long long* buf);
 int tc_mma_bench(int variant, int ctas, int iters, float* clk_host, cudaStream_t st);
 
 // ---- loss epilogues, optimiser, utilities (dudf_misc.cu) ----

@@ -106,7 +106,8 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
     if (warp == 8) {
       if (lane == 0) tc_producer<CL, RU>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD, CL > 1 ? cluster_ctarank() : 0u, CL > 1 ? 0 : (int)(out.flags >> 8));
     } else if (warp == 9) {
-      tc_mma_role<CL, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8);
+      tc_mma_role<CL, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8, 0,
+                          (out.trace && blockIdx.x == 0) ? out.trace : nullptr);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -120,10 +121,13 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
     const float bL = net.b[L][0];
     const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
     uint32_t acc_phase = 0;                                 // bit s = parity of acc_ready[s]
+    unsigned long long* etrace = (out.trace && blockIdx.x == 0 && warp == 0) ? out.trace + TC_TRACE_REGION : nullptr;
+    uint32_t en = 0;
 
     for (int64_t rd = 0; rd < rounds; ++rd) {
       const int64_t pair = blockIdx.x + rd * gridDim.x;
       // ---- coordinates of both sub-tiles ----
+      tc_trace(etrace, en, 14, 0);
       tc_epi_bar();
       for (int i = tid; i < 2 * C::PT; i += 256) {
         const int64_t p = pair * 2 * C::PT + i;
@@ -145,6 +149,7 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
             acc_phase ^= 1u << s;
             tc_fence_after();
           }
+          tc_trace(etrace, en, 10 + s, l);
           if (l == 0) {
             // first layer in fp32 on CUDA cores: u0 = w0 (W0 x + b0); derivative channels are w0 W0[:, i]
 #pragma unroll 1
@@ -166,6 +171,7 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
               tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
             }
           }
+          tc_trace(etrace, en, 12 + s, l);
           if (l < L - 1) {
             // publish the activation tile to the MMA issuer
             tc_fence_before();
@@ -351,6 +357,9 @@ static int tc_launch16(const void* packed, const NetView& net, const float* x, i
   return 0;
 }
 
+static unsigned long long* g_tc_trace = nullptr;
+void tc_set_trace(unsigned long long* buf) { g_tc_trace = buf; }
+
 static int g_tc_cluster = -1;      // DUDF_TC_CLUSTER=1|2|4 overrides the cluster size of the query kernel (default 2)
 static int tc_cluster_size() {
   if (g_tc_cluster < 0) {
@@ -384,7 +393,9 @@ static int tc_launch(const void* packed, const NetView& net, const float* x, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DUDF_CUDA_OK(cudaLaunchKernelEx(&cfg, k, (const unsigned char*)packed, net, x, P, gridN, first, out));
+  QueryOut o2 = out;
+  o2.trace = g_tc_trace;
+  DUDF_CUDA_OK(cudaLaunchKernelEx(&cfg, k, (const unsigned char*)packed, net, x, P, gridN, first, o2));
   DUDF_LAUNCH_OK();
   return 0;
 }

@@ -140,6 +140,16 @@ __device__ __forceinline__ void tc_finish_subtile(uint64_t* acc_ready, int s, bo
   umma::mma_commit_warp(&acc_ready[s]);
 }
 
+// event log for tools/trace_probe.py: (tag << 56 | aux << 48 | clock); one writer per region
+constexpr uint32_t TC_TRACE_REGION = 8192;
+__device__ __forceinline__ void tc_trace(unsigned long long* region, uint32_t& n, uint32_t tag, uint32_t aux) {
+  if (region && n < TC_TRACE_REGION) {
+    if ((threadIdx.x & 31) == 0)
+      region[n] = ((unsigned long long)tag << 56) | ((unsigned long long)(aux & 0xff) << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
+    ++n;
+  }
+}
+
 // ---- MMA issuer: the WHOLE warp runs this role in converged, warp-uniform code and one elected lane issues each
 // ---- tcgen05 instruction.  (Issued from a single-lane branch, every tcgen05.mma drags a register -> uniform-register
 // ---- election loop and a recomputed descriptor with it: 107-160 clocks per instruction for 64 clocks of tensor work,
@@ -153,8 +163,10 @@ __device__ __forceinline__ void tc_finish_subtile(uint64_t* acc_ready, int s, bo
 template <int CL = 1, bool REUSE = false>
 __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
                                             uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, unsigned char* img_f,
-                                            unsigned char* img_b, int64_t ncb, int64_t cb0, int dir, int dbg = 0, uint64_t img_policy = 0) {
+                                            unsigned char* img_b, int64_t ncb, int64_t cb0, int dir, int dbg = 0, uint64_t img_policy = 0,
+                                            unsigned long long* trace = nullptr) {
   using namespace umma;
+  uint32_t tn = 0;
   static_assert(TC_STAGES >= 5, "a neuron half (4 chunks) must fit in the ring with one slot to prefetch into");
   constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
   constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
@@ -176,24 +188,21 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
           mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
           act_phase ^= 1u << s;
           tc_fence_after();
+          tc_trace(trace, tn, 1, s);
           tc_copy_subtile(act, s, img, ncb, cb0, pair, layer, img_policy);
           const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
           for (int h = 0; h < 2; ++h) {
             const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
             for (int kb = 0; kb < 4; ++kb) {
-              mbar_wait(&full[stage], phase, 0x300 + stage);
-              tc_fence_after();
-              const uint64_t a_desc = desc_advance(a_desc0, stage * TC_CHUNK_BYTES);
-              if (!skip) {
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                  mma_f16_ss_warp(d_tmem, desc_advance(a_desc, k4 * 32), desc_advance(b_desc, (kb * 8 + k4 * 2) * 1024), idesc, (kb | k4) != 0);
-              }
+              mbar_wait(&full[stage], phase, 0x300 + stage);       // bulk-copy completion: already visible to the async proxy
+              if (!skip)
+                mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(b_desc, kb * 8 * 1024), idesc, kb != 0);
               if constexpr (CL == 1) mma_commit_warp(&empty[stage]);
               else mma_commit_multicast_warp(&empty[stage], mask);
               if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
           }
+          tc_trace(trace, tn, 2, 2 + s);
           tc_finish_subtile(acc_ready, s, img != nullptr);
         }
       } else {
@@ -203,22 +212,16 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
               mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
               act_phase ^= 1u << s;
               tc_fence_after();
+              tc_trace(trace, tn, 1, s);
               tc_copy_subtile(act, s, img, ncb, cb0, pair, layer, img_policy);
             }
             const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
             const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
             uint32_t st = stage, ph = phase;
             for (int kb = 0; kb < 4; ++kb) {
-              if (s == 0) {
-                mbar_wait(&full[st], ph, 0x300 + st);
-                tc_fence_after();
-              }
-              const uint64_t a_desc = desc_advance(a_desc0, st * TC_CHUNK_BYTES);
-              if (!skip) {
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                  mma_f16_ss_warp(d_tmem, desc_advance(a_desc, k4 * 32), desc_advance(b_desc, (kb * 8 + k4 * 2) * 1024), idesc, (kb | k4) != 0);
-              }
+              if (s == 0) mbar_wait(&full[st], ph, 0x300 + st);     // bulk-copy completion: already visible to the async proxy
+              if (!skip)
+                mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, st * TC_CHUNK_BYTES), desc_advance(b_desc, kb * 8 * 1024), idesc, kb != 0);
               if (s == 1) {
                 if constexpr (CL == 1) mma_commit_warp(&empty[st]);
                 else mma_commit_multicast_warp(&empty[st], mask);
@@ -226,6 +229,7 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
               if (++st == TC_STAGES) { st = 0; ph ^= 1; }
             }
             if (s == 1) { stage = st; phase = ph; }
+            tc_trace(trace, tn, 2, h * 2 + s);
             if (h == 1) tc_finish_subtile(acc_ready, s, img != nullptr);
           }
       }

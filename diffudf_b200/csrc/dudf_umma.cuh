@@ -170,6 +170,24 @@ __device__ __forceinline__ void mma_commit_warp(void* bar) {
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+// Four consecutive K = 16 steps of one 64-wide k chunk in ONE elected block: A advances by 32 bytes per step inside its
+// 128-byte swizzle row (descriptor + 2), B (MN-major) by two 1 KB k-groups (descriptor + 128).  `first` = 0 starts a new
+// accumulation with the first step.  One election and no descriptor traffic through general registers per step.
+__device__ __forceinline__ void mma_f16_ss_k64_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t first) {
+  asm volatile(
+      "{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 a3, %1, 6;\n\t"
+      "add.s64 b1, %2, 128;\n\tadd.s64 b2, %2, 256;\n\tadd.s64 b3, %2, 384;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(first)
+      : "memory");
+}
 // descriptor with the start address advanced by `bytes` (no carry out of the 14-bit address field for our tiles)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // all previously issued tcgen05.mma of this thread complete -> one arrival on the mbarrier

@@ -190,6 +190,9 @@ int dudf_selftest_umma(int variant, float* max_err_host);
 /* Tensor-pipe micro-benchmark (tools/umma_bench.py): average clocks per tcgen05.mma (K = 16) over `ctas` CTAs that each
  * issue iters x 16 instructions on resident operands; variants in dudf_tc.cu. */
 int dudf_bench_umma(int variant, int ctas, int iters, float* clk_per_mma_host);
+/* Diagnostics (tools/trace_probe.py): CTA 0 of the tensor-core query kernel logs (tag, clock) events of its MMA warp and of
+ * epilogue warp 0 into device_buffer (2 x 8192 uint64); NULL switches the log off. */
+int dudf_debug_set_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }
