@@ -96,7 +96,7 @@ __device__ __forceinline__ void tc_producer(const unsigned char* packed, unsigne
       const unsigned char* src = packed + (size_t)idx * 8 * TC_CHUNK_BYTES;
       for (int rep = 0; rep < (REUSE ? 1 : 2); ++rep)
         for (int ck = 0; ck < 8; ++ck, ++chunk) {
-          mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
+          mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x100 + stage);
           if ((dbg & 4) && chunk >= (uint32_t)TC_STAGES) {        // pipeline diagnostics: stale weights, no L2 -> SM traffic
             mbar_arrive(&full[stage]);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }

@@ -46,6 +46,21 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity, unsigned c
   }
 }
 
+// the same wait for a role that runs far ahead of its consumer (weight producer): back off between polls instead of spinning
+// at full issue rate next to the epilogue warps (the board is power-capped under this kernel, tools/clock_probe.py)
+__device__ __forceinline__ void mbar_wait_relaxed(void* bar, uint32_t parity, unsigned code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > UMMA_WATCHDOG_CYCLES) {
+      g_watchdog_code = code;
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
