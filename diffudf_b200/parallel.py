@@ -84,3 +84,43 @@ def extract_fields_sharded(model, N, gt_mode, alpha, dp):
     df = dp.gather_rows(df, counts)
     vecs = dp.gather_rows(vecs, counts)
     return df.reshape(N, N, N), vecs.reshape(N, N, N, 3)
+
+
+def propagate_rays_sharded(model, rays, t0, mask_rays, network_config, rendering_config, dp):
+    """Sphere tracing sharded by contiguous ray ranges: every rank marches its range with the device loop of
+    render_st and the hit mask / positions / still-active mask are all-gathered.  Same in-place contract as
+    render_st.propagate_rays on every rank; rays are independent, so the result equals the single-GPU one bit for bit."""
+    import numpy as np
+    from .render_st import _march
+    dev = model._weights_biases()[0][0].device
+    R = t0.shape[0]
+    lo, hi = shard_range(R, dp.rank, dp.world)
+    counts = [shard_range(R, r, dp.world)[1] - shard_range(R, r, dp.world)[0] for r in range(dp.world)]
+    rays_d = torch.from_numpy(np.ascontiguousarray(rays[lo:hi], dtype=np.float64)).to(dev)
+    t0_d = torch.from_numpy(np.ascontiguousarray(t0[lo:hi], dtype=np.float64)).to(dev)
+    idx = torch.nonzero(torch.from_numpy(np.asarray(mask_rays[lo:hi], dtype=bool)).to(dev)).reshape(-1)
+    hits, idx, _ = _march(model, rays_d, t0_d, idx, network_config["gt_mode"], network_config["alpha"],
+                          rendering_config["surface_threshold"], rendering_config["max_iterations"])
+    still = torch.zeros(hi - lo, dtype=torch.bool, device=dev)
+    still[idx] = True
+    packed = torch.cat([t0_d, hits.to(torch.float64)[:, None], still.to(torch.float64)[:, None]], 1)     # one gather
+    full = dp.gather_rows(packed, counts).cpu().numpy()
+    t0[...] = full[:, :3]
+    mask_rays[...] = full[:, 4] != 0
+    hits_np = full[:, 3] != 0
+    if hits_np.sum() == 0:
+        raise ValueError(f"Ray tracing did not converge in {rendering_config['max_iterations']} iterations to any point at "
+                         f"distance {rendering_config['surface_threshold']} or lower from surface.")
+    return hits_np
+
+
+def project_points_sharded(sampler, samples, gt_mode, alpha, num_steps, dp):
+    """NDF projection (render_pc.Sampler.project) sharded by contiguous point ranges, gathered on every rank.
+    samples: (P, 3) float64 CUDA tensor (the same on every rank).  Returns (samples, steps, grads, hessians)."""
+    P = samples.shape[0]
+    lo, hi = shard_range(P, dp.rank, dp.world)
+    counts = [shard_range(P, r, dp.world)[1] - shard_range(P, r, dp.world)[0] for r in range(dp.world)]
+    s, st, g, H = sampler.project(samples[lo:hi].contiguous(), gt_mode, alpha, num_steps)
+    packed = torch.cat([s, st.to(torch.float64)[:, None], g.to(torch.float64), H.reshape(-1, 9).to(torch.float64)], 1)
+    full = dp.gather_rows(packed, counts)
+    return full[:, :3], full[:, 3].to(torch.float32), full[:, 4:7].to(torch.float32), full[:, 7:16].to(torch.float32).reshape(-1, 3, 3)

