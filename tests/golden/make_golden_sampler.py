@@ -21,13 +21,11 @@ sys.path.insert(0, ROOT)
 
 
 def import_dataset():
-    o3d = types.ModuleType("open3d")
-    o3c = types.ModuleType("open3d.core")
+    o3d = sys.modules.setdefault("open3d", types.ModuleType("open3d"))
+    o3c = sys.modules.setdefault("open3d.core", types.ModuleType("open3d.core"))
     o3c.Tensor = object
     o3d.core = o3c
     o3d.t = types.SimpleNamespace(geometry=types.SimpleNamespace(PointCloud=object))
-    sys.modules.setdefault("open3d", o3d)
-    sys.modules.setdefault("open3d.core", o3c)
     sys.path.insert(0, REF)
     import src.dataset as dataset
     return dataset
