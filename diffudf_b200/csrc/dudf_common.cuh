@@ -60,7 +60,9 @@ __device__ __forceinline__ void sincos_precise(float x, float& s, float& c) {
 // an argument in [-pi, pi] (abs. error ~ 4e-7, far below the fp16 operand rounding).
 __device__ __forceinline__ void sincos_fast(float x, float& s, float& c) {
   const float inv2pi = 0.15915494309189535f;
-  float q = rintf(x * inv2pi);
+  // round to nearest even by the 1.5 * 2^23 trick: two FADDs on the FMA pipe (FRND shares the MUFU pipe: 8 clk per warp,
+  // tools/micro/pipe_rates.cu); identical to rintf for |x| < 2^22 * 2 pi
+  float q = (x * inv2pi + 12582912.f) - 12582912.f;
   float r = fmaf(q, -6.2831854820251465f, x);        // 2*pi hi
   r = fmaf(q, 1.7484555e-7f, r);                     // -(2*pi lo): 2pi = 6.28318548 - 1.7484555e-7
   s = __sinf(r);

@@ -37,6 +37,7 @@ int tc_forward(const void* packed, const NetView& net, int nch, const float* x, 
                int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
 int tc_selftest(int variant, float* max_err, cudaStream_t st);
 void tc_set_trace(unsigned long long* buf);
+unsigned long long* tc_get_trace();
 int tc_mma_bench(int variant, int ctas, int iters, float* clk_host, cudaStream_t st);
 
 // ---- loss epilogues, optimiser, utilities (dudf_misc.cu) ----

@@ -359,6 +359,7 @@ static int tc_launch16(const void* packed, const NetView& net, const float* x, i
 
 static unsigned long long* g_tc_trace = nullptr;
 void tc_set_trace(unsigned long long* buf) { g_tc_trace = buf; }
+unsigned long long* tc_get_trace() { return g_tc_trace; }
 
 static int g_tc_cluster = -1;      // DUDF_TC_CLUSTER=1|2|4 overrides the cluster size of the query kernel (default 2)
 static int tc_cluster_size() {

@@ -182,7 +182,7 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
       const bool backward = (dir == TC_DIR_BWD) || (jt >= n_phase);
       const int j = (jt >= n_phase) ? jt - n_phase : jt;
       const int layer = backward ? (n_phase - j) : j;
-      unsigned char* img = backward ? img_b : img_f;
+      unsigned char* img = (dbg & 16) ? nullptr : (backward ? img_b : img_f);     // dbg bit 4: diagnostics, no operand-image copies
       if constexpr (!REUSE) {
         for (int s = 0; s < 2; ++s) {
           mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);

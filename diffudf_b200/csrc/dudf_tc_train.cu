@@ -28,7 +28,21 @@ using namespace umma;
 int tc_train_pair_cols(int nch) { (void)nch; return 256; }
 int tc_train_pair_points(int nch) { return nch == 1 ? 2 * TcCfg<1>::PT : nch == 4 ? 2 * TcCfg<4>::PT : 2 * TcCfg<10>::PT; }
 
-__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
+// fp32 pair -> packed halves, saturating at the largest finite half (one F2FP.SATFINITE.PACK_AB): adjoints that would
+// overflow fp16 clamp instead of becoming inf (the loss scale leaves 29x head-room, so this is a safety net)
+__device__ __forceinline__ uint32_t tt_pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <int GC>
+__device__ __forceinline__ void tt_store_group_sat(const float* v, unsigned char* trow, int chunk0, uint32_t r7) {
+#pragma unroll
+  for (int c8 = 0; c8 < GC / 8; ++c8)
+    *reinterpret_cast<uint4*>(trow + tc_chunk_off(chunk0 + c8, r7)) =
+        make_uint4(tt_pack_h2_sat(v[8 * c8], v[8 * c8 + 1]), tt_pack_h2_sat(v[8 * c8 + 2], v[8 * c8 + 3]),
+                   tt_pack_h2_sat(v[8 * c8 + 4], v[8 * c8 + 5]), tt_pack_h2_sat(v[8 * c8 + 6], v[8 * c8 + 7]));
+}
 
 // ---- thread-major stash of one column group: chunk j of the group lives at dst + j*1024 floats (+ 4*neuron) -------
 // value channels (u0) in fp32 first, then the derivative channels packed as halves (in column order)
@@ -133,6 +147,8 @@ struct EpiCtx {
   uint32_t r7;
   int n, tid, lane;
   uint32_t acc_phase;
+  unsigned long long* trace = nullptr;   // diagnostics (tools/trace_probe.py fused): event log of CTA 0 / warp 0
+  uint32_t tn = 0;
 };
 
 // =============================================================================================
@@ -292,7 +308,8 @@ __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr,
 #pragma unroll
   for (int pp = 0; pp < GC / NCH; ++pp) {
     float sn, cs, ub[NCH];
-    sincos_fast(u[pp * NCH], sn, cs);
+    if constexpr (FIRST) sincos_fast(u[pp * NCH], sn, cs);                    // first layer: arguments up to ~50 rad
+    else { sn = __sinf(u[pp * NCH]); cs = __cosf(u[pp * NCH]); }               // hidden layers: a few rad, MUFU on the raw argument
     tc_adj_point<NCH>(u + pp * NCH, ab + pp * NCH, ub, sn, cs);
     if constexpr (TOP) {
       tc_act_point<NCH>(u + pp * NCH, sn, cs);
@@ -310,9 +327,9 @@ __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr,
       }
     }
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) ab[pp * NCH + ch] = clamp_h(ub[ch]);
+    for (int ch = 0; ch < NCH; ++ch) ab[pp * NCH + ch] = ub[ch];
   }
-  if constexpr (!FIRST) tc_store_group<GC>(ab, trow, chunk0, r7);
+  if constexpr (!FIRST) tt_store_group_sat<GC>(ab, trow, chunk0, r7);
 }
 
 template <int NCH>
@@ -649,6 +666,7 @@ struct FusedDev {
   const float* amax_prev;    // max|stored seed| of the previous step -> loss scale
   float* amax_next;          // this step's (atomicMax)
   int flags;                 // bit 0: discard consumed scratch lines from L2
+  unsigned long long* trace; // diagnostics: event log of CTA 0 (MMA warp, epilogue warp 0) or null
 };
 
 template <int NCH>
@@ -662,6 +680,8 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
   const float ww = net.ww;
   const float invS = 1.0f / S;
   float* sd = e.os;                                               // outputs, then stored seeds, of both sub-tiles [2][256]
+  const bool nostash = ((fd.flags >> 8) & 32) != 0;               // diagnostics: no scratch traffic (results are meaningless)
+  tc_trace(e.trace, e.tn, 14, NCH);
   tc_epi_bar();
   for (int i = e.tid; i < 2 * C::PT; i += 256) {
     const int64_t p = pair * 2 * C::PT + i;
@@ -679,11 +699,13 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
     for (int s = 0; s < 2; ++s) {
       unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
       float* ust = Ucta + ((size_t)l * 256 + s * 128) * 256 + e.n * 4;
+      tc_trace(e.trace, e.tn, 42 + s, l);
       if (l > 0) {
         mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
         e.acc_phase ^= 1u << s;
         tc_fence_after();
       }
+      tc_trace(e.trace, e.tn, 10 + s, l);
       if (l == 0) {
 #pragma unroll 1
         for (int g = 0; g < C::NGRP; ++g) {
@@ -701,10 +723,11 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
           if (g + 1 < C::NGRP) tc_ld_issue<GC>(e.tmem_lane + s * 256 + (g + 1) * GC, nxt);
 #pragma unroll
           for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
-          tt_stash_group<NCH, GC>(u, ust + (size_t)g * GC * 256);
+          if (!nostash) tt_stash_group<NCH, GC>(u, ust + (size_t)g * GC * 256);
           tc_emit_group<NCH, GC, true>(u, trow, g * (GC / 8), e.r7);
         }
       }
+      tc_trace(e.trace, e.tn, 12 + s, l);
       if (l < L - 1) {
         tc_fence_before();
         fence_proxy_async();
@@ -715,8 +738,10 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
   }
   // ---------------- output layer + loss: one thread per point of the pair ----------------
   tc_epi_bar();
+  tc_trace(e.trace, e.tn, 20, 0);
   for (int s = 0; s < 2; ++s) tc_output_dot<C::NV>(e.act + s * TC_ACT_BYTES, e.wl_s, e.os + s * 256, e.tid);
   tc_epi_bar();
+  tc_trace(e.trace, e.tn, 21, 0);
   if ((e.tid & ~31) < 2 * C::PT) {
     double t[4] = {0.0, 0.0, 0.0, 0.0};
     float bl = 0.f, amax = 0.f;
@@ -766,6 +791,7 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
     }
   }
   tc_epi_bar();
+  tc_trace(e.trace, e.tn, 22, 0);
   // ---------------- reverse sweep: layers L-1 .. 1 read the scratch, layer 0 is recomputed from the points ----------------
   for (int l = L - 1; l >= 1; --l) {
     const bool top = (l == L - 1);
@@ -773,12 +799,18 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
       unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
       const float* ust = Ucta + ((size_t)l * 256 + s * 128) * 256 + e.n * 4;
       uint4 nxt[NRAW];
-      tt_stash_load<NCH, GC>(nxt, ust);
+      if (!nostash) tt_stash_load<NCH, GC>(nxt, ust);
+      else {
+#pragma unroll
+        for (int j = 0; j < NRAW; ++j) nxt[j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+      }
+      tc_trace(e.trace, e.tn, 40 + s, l);
       if (!top) {
         mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
         e.acc_phase ^= 1u << s;
         tc_fence_after();
       }
+      tc_trace(e.trace, e.tn, 30 + s, l);
       float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
       TmemRegs<GC> tr;
       if (!top) tc_ld_issue<GC>(e.tmem_lane + s * 256, tr);
@@ -787,7 +819,7 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
         uint4 ug[NRAW];
 #pragma unroll
         for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
-        if (g + 1 < C::NGRP) tt_stash_load<NCH, GC>(nxt, ust + (size_t)(g + 1) * GC * 256);
+        if (g + 1 < C::NGRP && !nostash) tt_stash_load<NCH, GC>(nxt, ust + (size_t)(g + 1) * GC * 256);
         const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * GC : 0u;
         const float* sdg = sd + s * 256 + g * GC;
         const float* pts = e.xs + (s * C::PT + g * (GC / NCH)) * 3;
@@ -799,6 +831,7 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
           for (int j = 0; j < NRAW; ++j) l2_discard_line(ust + (size_t)g * GC * 256 + j * 1024);
         }
       }
+      tc_trace(e.trace, e.tn, 32 + s, l);
       atomicAdd(&grad.b[l][e.n], bsum * ww * invS);
       if (top) atomicAdd(&grad.W[L][e.n], wlsum * invS);
       tc_fence_before();
@@ -808,9 +841,11 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
     }
   }
   for (int s = 0; s < 2; ++s) {
+    tc_trace(e.trace, e.tn, 40 + s, 0);
     mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
     e.acc_phase ^= 1u << s;
     tc_fence_after();
+    tc_trace(e.trace, e.tn, 30 + s, 0);
     float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
     TmemRegs<GC> tr;
     tc_ld_issue<GC>(e.tmem_lane + s * 256, tr);
@@ -820,10 +855,12 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
       const float* pts = e.xs + (s * C::PT + g * (GC / NCH)) * 3;
       tt_bwd_group<NCH, GC, false, true, true>(nullptr, tr, tnext, wl, nullptr, pts, nullptr, 0, e.r7, bsum, wlsum, w0s, &fr);
     }
+    tc_trace(e.trace, e.tn, 32 + s, 0);
     atomicAdd(&grad.b[0][e.n], bsum * net.w0 * invS);
 #pragma unroll
     for (int d = 0; d < 3; ++d) atomicAdd(&grad.W[0][e.n * 3 + d], w0s[d] * net.w0 * invS);
   }
+  tc_trace(e.trace, e.tn, 15, NCH);
 }
 
 template <int NA, int NB>
@@ -865,7 +902,7 @@ tt_fused_kernel(const unsigned char* __restrict__ packed, NetView net, GradView 
       if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BOTH, 0, fd.flags >> 8);
     } else if (warp == 9) {
       tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, Aimg, Zimg, ncb, 0, TC_DIR_BOTH, fd.flags >> 8,
-                       (fd.flags & 2) ? l2_policy_evict_first() : 0ull);
+                       (fd.flags & 2) ? l2_policy_evict_first() : 0ull, (fd.trace && blockIdx.x == 0) ? fd.trace : nullptr);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -876,6 +913,7 @@ tt_fused_kernel(const unsigned char* __restrict__ packed, NetView net, GradView 
     e.n = h * 128 + q * 32 + lane; e.tid = tid; e.lane = lane; e.r7 = e.n & 7;
     e.tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
     e.acc_phase = 0;
+    e.trace = (fd.trace && blockIdx.x == 0 && warp == 0) ? fd.trace + TC_TRACE_REGION : nullptr;
     const float S = loss_scale_from(fd.amax_prev);
     const float wl = net.W[L][e.n];
     FirstRow fr;
@@ -929,6 +967,7 @@ int tc_train_fused(const void* packed, const NetView& net, const GradView& grad,
   fd.loss.mode = fl.mode; fd.loss.alpha = fl.alpha; fd.loss.invP = 1.0f / (float)fl.P_global;
   for (int k = 0; k < 4; ++k) { fd.loss.w[k] = fl.w[k]; fd.loss.up[k] = 1.f; }
   fd.terms = fl.terms; fd.amax_prev = fl.amax_prev; fd.amax_next = fl.amax_next; fd.flags = fl.flags;
+  fd.trace = tc_get_trace();
   if (nb == 0) {
     if (na == 4) return tt_launch_fused<4, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
     if (na == 10) return tt_launch_fused<10, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);

@@ -14,6 +14,11 @@ batches = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x[0]
 for name, fused, flags, w in (("unfused", False, 0, W_S1), ("fused flags=0", True, 0, W_S1), ("fused flags=1", True, 1, W_S1),
                               ("fused flags=2", True, 2, W_S1), ("fused flags=3", True, 3, W_S1), ("fused flags=3, no weight streaming (diagnostic)", True, 3 | (4 << 8), W_S1),
                               ("fused flags=3, no MMA (diagnostic)", True, 3 | (2 << 8), W_S1),
+                              ("fused flags=3, no image copies (diagnostic)", True, 3 | (16 << 8), W_S1),
+                              ("fused flags=3, no scratch traffic (diagnostic)", True, 3 | (32 << 8), W_S1),
+                              ("fused flags=3, no images, no scratch (diagnostic)", True, 3 | (48 << 8), W_S1),
+                              ("fused flags=3, no images/scratch/weights (diag.)", True, 3 | (52 << 8), W_S1),
+                              ("fused flags=3, no images/scratch/weights/MMA", True, 3 | (54 << 8), W_S1),
                               ("unfused, no hessian term", False, 0, [1e4, 1e4, 0, 1e3]), ("fused flags=3, no hessian term", True, 3, [1e4, 1e4, 0, 1e3])):
     torch.manual_seed(123)
     model = SIREN(3, 1, [256] * 8, w0=30).cuda()
