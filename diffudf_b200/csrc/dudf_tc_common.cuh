@@ -237,6 +237,81 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
   }
 }
 
+// ---- skewed schedule (16-warp fused training step): the two sub-tile streams of a CTA run `skew` phases apart, so that one
+// ---- warp set is in its forward sweep (store-heavy: scratch + operand images) while the other is in its reverse sweep
+// ---- (math-heavy).  Slot t serves phase t of stream 0 and phase t - skew of stream 1; a phase index counts the 2 * n_phase
+// ---- phases of every pair of the CTA in order.  Producer and MMA issuer walk the same slot sequence.
+__device__ __forceinline__ void tc_producer_skew(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t rounds,
+                                                 int n_phase, int skew, int dbg = 0) {
+  using namespace umma;
+  uint32_t stage = 0, phase = 0, chunk = 0;
+  const int64_t total = rounds * 2 * n_phase;
+  for (int64_t t = 0; t < total + skew; ++t)
+    for (int s = 0; s < 2; ++s) {
+      const int64_t tt = s ? t - skew : t;
+      if (tt < 0 || tt >= total) continue;
+      const int jt = (int)(tt % (2 * n_phase));
+      const bool backward = jt >= n_phase;
+      const int j = backward ? jt - n_phase : jt;
+      const int idx = backward ? (n_phase + (n_phase - 1 - j)) : j;
+      const unsigned char* src = packed + (size_t)idx * 8 * TC_CHUNK_BYTES;
+      for (int ck = 0; ck < 8; ++ck, ++chunk) {
+        mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x100 + stage);
+        if ((dbg & 4) && chunk >= (uint32_t)TC_STAGES) {
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
+          bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
+        }
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+}
+
+__device__ __forceinline__ void tc_mma_role_skew(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                                 uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, int skew,
+                                                 unsigned char* img_f, unsigned char* img_b, int64_t ncb, int dbg, uint64_t img_policy,
+                                                 unsigned long long* trace) {
+  using namespace umma;
+  uint32_t tn = 0;
+  constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
+  const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
+  const uint64_t b_desc0 = make_desc_sw128(smem_u32(act), 32768, 1024);
+  const bool skip = (dbg & 2) != 0;
+  uint32_t stage = 0, phase = 0, act_phase = 0;
+  const int64_t total = rounds * 2 * n_phase;
+  for (int64_t t = 0; t < total + skew; ++t)
+    for (int s = 0; s < 2; ++s) {
+      const int64_t tt = s ? t - skew : t;
+      if (tt < 0 || tt >= total) continue;
+      const int64_t r = tt / (2 * n_phase);
+      const int jt = (int)(tt - r * 2 * n_phase);
+      const int64_t pair = blockIdx.x + r * gridDim.x;
+      const bool backward = jt >= n_phase;
+      const int j = backward ? jt - n_phase : jt;
+      const int layer = backward ? (n_phase - j) : j;
+      unsigned char* img = (dbg & 16) ? nullptr : (backward ? img_b : img_f);
+      mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
+      act_phase ^= 1u << s;
+      tc_fence_after();
+      tc_trace(trace, tn, 1, s);
+      tc_copy_subtile(act, s, img, ncb, 0, pair, layer, img_policy);
+      const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&full[stage], phase, 0x300 + stage);
+          if (!skip)
+            mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(b_desc, kb * 8 * 1024), idesc, kb != 0);
+          mma_commit_warp(&empty[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      tc_trace(trace, tn, 2, 2 + s);
+      tc_finish_subtile(acc_ready, s, img != nullptr);
+    }
+}
+
 template <int GC>
 __device__ __forceinline__ void tc_load_group(uint32_t taddr, float* u) {
   uint32_t r[32];

@@ -7,6 +7,8 @@ returned terms runs the adjoint-seed kernel, the reverse sweep and the weight-gr
 the Hessian jet (10 channels), all others 4 channels: the alignment term of loss_s1 is masked to
 on-surface rows in the reference too, so results are identical while ~40 % of the work is skipped.
 """
+import os
+
 import torch
 
 from .engine import NCH
@@ -26,7 +28,7 @@ class TrainCore:
         self.precision = precision          # None -> model.train_precision (default 'fp32')
         self.amax = None                    # (2,) fp32: max|stored seed| of the last two tensor-core steps (loss scale source)
         self.amax_key, self.amax_slot = None, 0
-        self.fused_flags = 3
+        self.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "3"))
 
     def _prec(self):
         return self.precision or getattr(self.model, "train_precision", "fp32")

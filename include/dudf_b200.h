@@ -151,6 +151,7 @@ typedef struct dudf_train_segment {
 #define DUDF_FUSED_DISCARD 1      /* drop consumed scratch lines from L2 instead of letting them be written back */
 #define DUDF_FUSED_IMG_EVICT_FIRST 2 /* operand-image stores carry an L2 evict-first hint */
 #define DUDF_FUSED_NO_WGRAD 4     /* stop after the fused launch; the caller runs dudf_jet_wgrad(…, amax_prev, …) itself */
+#define DUDF_FUSED_WARPS16 8      /* two independent sets of 8 epilogue warps (one per sub-tile) instead of one set of 8 */
 int64_t dudf_fused_scratch_bytes(const dudf_ctx* ctx);
 int dudf_train_step_fused(dudf_ctx* ctx, int mode, const dudf_train_segment* segs_host, int nseg, int64_t P_global,
                           const float* w_host, float alpha, double* terms, const float* amax_prev, float* amax_next, void* scratch,

@@ -11,7 +11,8 @@ from diffudf_b200 import SIREN  # noqa: E402
 from diffudf_b200.train import FusedTrainer  # noqa: E402
 
 batches = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x[0], n[0], d[0, :, 0])) for x, n, d in make_batches(4, 0)]
-for name, fused, flags, w in (("unfused", False, 0, W_S1), ("fused flags=0", True, 0, W_S1), ("fused flags=1", True, 1, W_S1),
+for name, fused, flags, w in (("unfused", False, 0, W_S1), ("fused16 flags=11", True, 11, W_S1), ("fused16 flags=11, no hessian term", True, 11, [1e4, 1e4, 0, 1e3]),
+                              ("fused16, no images/scratch/weights/MMA (diag.)", True, 11 | (54 << 8), W_S1), ("fused flags=0", True, 0, W_S1), ("fused flags=1", True, 1, W_S1),
                               ("fused flags=2", True, 2, W_S1), ("fused flags=3", True, 3, W_S1), ("fused flags=3, no weight streaming (diagnostic)", True, 3 | (4 << 8), W_S1),
                               ("fused flags=3, no MMA (diagnostic)", True, 3 | (2 << 8), W_S1),
                               ("fused flags=3, no image copies (diagnostic)", True, 3 | (16 << 8), W_S1),
