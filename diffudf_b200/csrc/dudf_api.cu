@@ -58,7 +58,7 @@ struct dudf_ctx {
   const float* Wp[DUDF_MAX_LAYERS] = {};   // weights in use: the owned copies (dudf_set_weights) or borrowed (dudf_bind_weights)
   const float* bp[DUDF_MAX_LAYERS] = {};
   void* tc_packed = nullptr;
-  dudf::DevBuf ws_out, ws_x64;
+  dudf::DevBuf ws_out, ws_x64, ws_drv;
   NetView view() const {
     NetView v;
     memset(&v, 0, sizeof(v));
@@ -210,6 +210,76 @@ int dudf_curvature(const float* H, const float* T, int64_t P, float* n, float* m
 int dudf_field_vectors(const float* g, const float* H, int64_t P, float* vecs, void* stream) {
   DUDF_REQUIRE(g && H && vecs, "dudf_field_vectors: null argument");
   return field_vectors(g, H, P, vecs, (cudaStream_t)stream);
+}
+
+int dudf_march_rays(dudf_ctx* c, double* pos, const double* dir, unsigned char* active, unsigned char* hit, int64_t R, int gt_mode,
+                    float alpha, float thr, int max_it, int precision, int64_t* queries_host, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_march_rays: weights not set");
+  DUDF_REQUIRE(R >= 0 && R < (int64_t)1 << 31, "dudf_march_rays: R=%lld out of range", (long long)R);
+  DUDF_REQUIRE(gt_mode >= DUDF_GT_TANH && gt_mode <= DUDF_GT_SQUARED, "dudf_march_rays: gt_mode %d", gt_mode);
+  if (queries_host) *queries_host = 0;
+  if (R == 0) return 0;
+  DUDF_REQUIRE(pos && dir && active && hit, "dudf_march_rays: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  // workspace: idx[2][R] int | count int (+pad) | keep[R] bytes | x[R][3] float | f[R] float | cub temp
+  const size_t temp_bytes = drv_select_temp_bytes(R);
+  const size_t off_cnt = 2 * (size_t)R * sizeof(int);
+  const size_t off_keep = off_cnt + 256;
+  const size_t off_x = (off_keep + (size_t)R + 255) / 256 * 256;
+  const size_t off_f = off_x + (size_t)R * 3 * sizeof(float);
+  const size_t off_tmp = (off_f + (size_t)R * sizeof(float) + 255) / 256 * 256;
+  if (c->ws_drv.ensure(off_tmp + temp_bytes)) return 1;
+  unsigned char* ws = (unsigned char*)c->ws_drv.p;
+  int* idx[2] = {(int*)ws, (int*)ws + R};
+  int* d_count = (int*)(ws + off_cnt);
+  unsigned char* keep = ws + off_keep;
+  float* x = (float*)(ws + off_x);
+  float* f = (float*)(ws + off_f);
+  void* temp = ws + off_tmp;
+  int rc = drv_select_initial(temp, temp_bytes, active, R, idx[0], d_count, st);
+  if (rc) return rc;
+  int n = 0;
+  DUDF_CUDA_OK(cudaMemcpyAsync(&n, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DUDF_CUDA_OK(cudaStreamSynchronize(st));
+  int cur = 0;
+  int64_t nq = 0;
+  for (int it = 0; it < max_it && n > 0; ++it) {
+    if ((rc = drv_gather(pos, idx[cur], n, x, st))) return rc;
+    QueryOut o{f, nullptr, nullptr, nullptr, nullptr, 0, 0.f};
+    if ((rc = run_forward(c, 1, x, n, 0, 0, o, precision, st))) return rc;
+    nq += n;
+    if ((rc = drv_advance(pos, dir, idx[cur], f, n, gt_mode, alpha, thr, hit, keep, st))) return rc;
+    if ((rc = drv_select(temp, temp_bytes, idx[cur], keep, n, idx[cur ^ 1], d_count, st))) return rc;
+    cur ^= 1;
+    DUDF_CUDA_OK(cudaMemcpyAsync(&n, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DUDF_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  DUDF_CUDA_OK(cudaMemsetAsync(active, 0, (size_t)R, st));
+  if ((rc = drv_mark(idx[cur], n, active, st))) return rc;
+  if (queries_host) *queries_host = nq;
+  return 0;
+}
+
+int dudf_project_points(dudf_ctx* c, double* x, int64_t P, int num_steps, int gt_mode, float alpha, double* steps, float* g, float* H,
+                        int precision, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_project_points: weights not set");
+  DUDF_REQUIRE(gt_mode >= DUDF_GT_TANH && gt_mode <= DUDF_GT_SQUARED, "dudf_project_points: gt_mode %d", gt_mode);
+  DUDF_REQUIRE(P >= 0 && num_steps >= 0, "dudf_project_points: negative size");
+  if (P == 0 || num_steps == 0) return 0;
+  DUDF_REQUIRE(x && steps && g, "dudf_project_points: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->ws_drv.ensure((size_t)P * 4 * sizeof(float))) return 1;
+  float* x32 = (float*)c->ws_drv.p;
+  float* f = x32 + 3 * P;
+  for (int s = 0; s < num_steps; ++s) {
+    int rc = drv_gather(x, nullptr, P, x32, st);
+    if (rc) return rc;
+    const bool last = (s == num_steps - 1);
+    QueryOut o{f, g, (last ? H : nullptr), nullptr, nullptr, 0, 0.f};
+    if ((rc = run_forward(c, (last && H) ? 10 : 4, x32, P, 0, 0, o, precision, st))) return rc;
+    if ((rc = drv_project(x, f, g, P, gt_mode, alpha, steps, st))) return rc;
+  }
+  return 0;
 }
 
 int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, double* f_host, double* g_host,

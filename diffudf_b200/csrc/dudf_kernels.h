@@ -106,6 +106,16 @@ struct SampleArgs {
 };
 int sample_batch_pc(const SampleArgs& a, int sms, cudaStream_t st);
 int nn_distance(const float* q, int64_t nq, const float* X, int64_t nx, float* dist, int sms, cudaStream_t st);
+// ---- device-resident query drivers (dudf_drivers.cu; src/render_st.py:136-172, src/render_pc.py:43-53) ----
+size_t drv_select_temp_bytes(int64_t R);
+int drv_select_initial(void* temp, size_t temp_bytes, const unsigned char* active, int64_t R, int* idx, int* d_count, cudaStream_t st);
+int drv_select(void* temp, size_t temp_bytes, const int* idx_in, const unsigned char* keep, int64_t n, int* idx_out, int* d_count,
+               cudaStream_t st);
+int drv_gather(const double* pos, const int* idx, int64_t n, float* x, cudaStream_t st);
+int drv_advance(double* pos, const double* dir, const int* idx, const float* f, int64_t n, int gt_mode, float alpha, float thr,
+                unsigned char* hit, unsigned char* keep, cudaStream_t st);
+int drv_mark(const int* idx, int64_t n, unsigned char* mask, cudaStream_t st);
+int drv_project(double* x, const float* f, const float* g, int64_t n, int gt_mode, float alpha, double* steps, cudaStream_t st);
 int loss_seeds(const LossArgs& a, cudaStream_t st);
 int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st);
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);

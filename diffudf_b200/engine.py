@@ -10,6 +10,7 @@ from . import _lib
 
 PRECISIONS = {"fp32": 0, "tc16": 1}
 LOSS_MODES = {"s1": 0, "s2": 1, "siren": 2}
+GT_MODES = {"tanh": 0, "siren": 1, "squared": 2}
 Q_ABS_INV_TANH = 1
 Q_NEG_NORMALIZE = 2
 NCH = {0: 1, 1: 4, 2: 10, 3: 20}
@@ -89,6 +90,38 @@ class Engine:
                                                 _lib.ptr(H), _lib.ptr(T), PRECISIONS[precision], _lib.current_stream()),
                        "dudf_query_points")
         return f, g, H, T
+
+    def march_rays(self, pos, dirs, active, hit, gt_mode, alpha, thr, max_it, precision="fp32"):
+        """Sphere tracing on the device (dudf_march_rays; src/render_st.py:136-172).  pos (R,3) float64 is advanced in place,
+        active / hit (R,) uint8 are updated in place.  Returns the number of value queries."""
+        if gt_mode not in GT_MODES:
+            raise KeyError(gt_mode)
+        for t, dt in ((pos, torch.float64), (dirs, torch.float64), (active, torch.uint8), (hit, torch.uint8)):
+            if t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+                raise RuntimeError("march_rays: contiguous CUDA tensors (float64 positions / directions, uint8 masks) required")
+        nq = ctypes.c_int64(0)
+        with torch.cuda.device(pos.device):
+            _lib.check(self.L.dudf_march_rays(self.h, pos.data_ptr(), dirs.data_ptr(), active.data_ptr(), hit.data_ptr(), pos.shape[0],
+                                              GT_MODES[gt_mode], float(alpha), float(thr), int(max_it), PRECISIONS[precision],
+                                              ctypes.byref(nq), _lib.current_stream()), "dudf_march_rays")
+        return int(nq.value)
+
+    def project_points(self, x, num_steps, gt_mode, alpha, precision="fp32", want_hess=True):
+        """num_steps projection steps on the device (dudf_project_points; src/render_pc.py:43-53).  x (P,3) float64 is updated
+        in place.  Returns (last steps (P,), last gradients (P,3), Hessians of the last step (P,3,3) | None)."""
+        if gt_mode not in GT_MODES:
+            raise KeyError(gt_mode)
+        if x.dtype != torch.float64 or not x.is_cuda or not x.is_contiguous():
+            raise RuntimeError("project_points: contiguous float64 CUDA tensor required")
+        P = x.shape[0]
+        steps = torch.empty(P, device=x.device, dtype=torch.float64)
+        g = torch.empty(P, 3, device=x.device, dtype=torch.float32)
+        H = torch.empty(P, 3, 3, device=x.device, dtype=torch.float32) if want_hess else None
+        with torch.cuda.device(x.device):
+            _lib.check(self.L.dudf_project_points(self.h, x.data_ptr(), P, int(num_steps), GT_MODES[gt_mode], float(alpha), steps.data_ptr(),
+                                                  g.data_ptr(), _lib.ptr(H), PRECISIONS[precision], _lib.current_stream()),
+                       "dudf_project_points")
+        return steps, g, H
 
     def query_grid(self, N, first, count, precision="fp32", flags=0, alpha=0.0, want_vecs=True, want_hess=False, out=None):
         dev = self.device

@@ -25,12 +25,16 @@ def inverse(gt_mode, pred_df, alpha, min_step=0.01):
 
 
 def inverse_torch(gt_mode, f, alpha, min_step=0.01):
-    """Same functions on torch tensors (device resident drivers)."""
+    """Same functions on torch tensors (device resident drivers), with the arithmetic numpy performs on an array of f's dtype:
+    a true division by alpha (torch multiplies a tensor by the reciprocal of a Python scalar divisor, which differs in the last
+    bit), the comparison against 1/alpha rounded to f's dtype."""
     import torch
+    a = torch.tensor(alpha, dtype=f.dtype, device=f.device)
     if gt_mode == "tanh":
-        return torch.where(f < 1 / alpha, torch.sqrt(f / alpha), f)
+        return torch.where(f < 1 / alpha, torch.sqrt(f / a), f)
     if gt_mode == "siren":
         return torch.where(f > 0, f, torch.full_like(f, min_step))
     if gt_mode == "squared":
-        return torch.where(f > 0, torch.sqrt(f.clamp_min(0)), torch.full_like(f, min_step)) / (alpha ** 0.5)
+        r = torch.where(f > 0, torch.sqrt(f.clamp_min(0)), torch.full_like(f, min_step))
+        return (r.to(torch.float64) / (alpha ** 0.5)).to(f.dtype)
     raise KeyError(gt_mode)

@@ -6,7 +6,6 @@ import warnings
 import numpy as np
 import torch
 
-from .inverses import inverse_torch
 from .model import SIREN
 
 
@@ -26,17 +25,10 @@ class Sampler:
         """Inner loop of generate_point_cloud (:43-53) on a float64 CUDA tensor (P,3).
         Returns (samples, last steps (P,), last gradients (P,3), Hessians of the last step (P,3,3))."""
         eng = self.decoder._engine_synced()
-        H = None
-        steps = g = None
-        for step in range(num_steps):
-            x = samples.to(torch.float32).contiguous()
-            if step == num_steps - 1:
-                f, g, H, _ = eng.query(x, 2, self.decoder.precision)
-            else:
-                f, g, _, _ = eng.query(x, 1, self.decoder.precision)
-            steps = inverse_torch(gt_mode, f, alpha, min_step=0)        # no abs(): negative f -> NaN, like the reference
-            gn = g / torch.linalg.norm(g, dim=1, keepdim=True)
-            samples = samples - (steps[:, None] * gn).to(torch.float64)
+        samples = samples.to(torch.float64).contiguous().clone()
+        if num_steps <= 0:
+            return samples, None, None, None
+        steps, g, H = eng.project_points(samples, num_steps, gt_mode, alpha, self.decoder.precision)
         return samples, steps, g, H
 
     def generate_point_cloud(self, gt_mode, alpha, num_steps=5, num_points=20000, surf_thresh=0.01, max_iter=1000):

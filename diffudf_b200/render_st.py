@@ -60,23 +60,15 @@ def compute_curvature(inputs, normals, curvature="mean", device=torch.device(0))
 
 
 def _march(model, rays_d, t0_d, idx, gt_mode, alpha, thr, max_it):
+    """The marching loop of propagate_rays (render_st.py:150-166) through dudf_march_rays: rays_d, t0_d (R,3) float64 CUDA
+    (t0_d advanced in place), idx the rays to march.  Returns (hit mask (R,) bool, indices still marching, value queries)."""
     eng = model._engine_synced()
-    hits = torch.zeros(t0_d.shape[0], dtype=torch.bool, device=t0_d.device)
-    it = 0
-    nq = 0
-    while idx.numel() > 0 and it < max_it:
-        x = t0_d[idx].to(torch.float32).contiguous()
-        f, _, _, _ = eng.query(x, 0, model.precision)
-        nq += x.shape[0]
-        steps = inverse_torch(gt_mode, f.abs(), alpha)
-        pos = t0_d[idx] + rays_d[idx] * steps.to(torch.float64)[:, None]
-        t0_d[idx] = pos
-        below = (f < thr) if gt_mode == "siren" else (steps.abs() < thr)
-        inside = ((pos > -1).all(dim=1)) & ((pos < 1).all(dim=1))
-        hits[idx] |= below & inside
-        idx = idx[(~below) & inside]
-        it += 1
-    return hits, idx, nq
+    R = t0_d.shape[0]
+    active = torch.zeros(R, dtype=torch.uint8, device=t0_d.device)
+    active[idx] = 1
+    hit = torch.zeros(R, dtype=torch.uint8, device=t0_d.device)
+    nq = eng.march_rays(t0_d, rays_d.contiguous(), active, hit, gt_mode, alpha, thr, max_it, model.precision)
+    return hit.bool(), torch.nonzero(active).reshape(-1), nq
 
 
 def propagate_rays(model, rays, t0, mask_rays, network_config, rendering_config, device):

@@ -87,6 +87,29 @@ int dudf_curvature(const float* H, const float* T, int64_t P, float* n, float* m
  * (src/render_mc.py:77-93); g is the already normalised, negated gradient. */
 int dudf_field_vectors(const float* g, const float* H, int64_t P, float* vecs, void* stream);
 
+/* gt_mode of src/inverses.py:3-22 */
+#define DUDF_GT_TANH 0     /* inv_tanh(f) = f < 1/alpha ? sqrt(f/alpha) : f */
+#define DUDF_GT_SIREN 1    /* inv_siren(f) = f > 0 ? f : min_step           */
+#define DUDF_GT_SQUARED 2  /* (f > 0 ? sqrt(f) : min_step) / sqrt(alpha)    */
+
+/* Sphere tracing, the loop of propagate_rays (src/render_st.py:136-172), device resident.  Per iteration: one value query of
+ * the rays still marching, step = inverse(gt_mode, |f|, alpha, min_step 0.01), pos += dir * step in float64; a ray is HIT when
+ * the step (value, for DUDF_GT_SIREN) is below thr and the new position lies strictly inside (-1,1)^3, it is DROPPED when it
+ * leaves the cube, otherwise it keeps marching; at most max_it iterations.
+ * pos: [R][3] float64, updated in place (t0 of the reference); dir: [R][3] float64; active: [R] bytes, in: the rays to march
+ * (mask_rays), out: the rays still marching after max_it; hit: [R] bytes, OR-ed with the rays that hit.  queries_host (may be
+ * NULL) receives the number of value queries.  The stream is synchronised once per iteration (4-byte active count). */
+int dudf_march_rays(dudf_ctx* ctx, double* pos, const double* dir, unsigned char* active, unsigned char* hit, int64_t R,
+                    int gt_mode, float alpha, float thr, int max_it, int precision, int64_t* queries_host, void* stream);
+
+/* Projection onto the zero level set, the inner loop of Sampler.generate_point_cloud (src/render_pc.py:43-53): num_steps
+ * times x -= inverse(gt_mode, f, alpha, min_step 0) * grad f / |grad f| (no abs(), like the reference), in float64 on the widened
+ * fp32 field values exactly as the reference computes on the float64 arrays of evaluate().  x: [P][3] float64, updated in
+ * place; steps: [P] float64, the last step lengths; g: [P][3] the gradients of the last step; H: [P][3][3] the Hessians of the
+ * last step, or NULL.  No host synchronisation. */
+int dudf_project_points(dudf_ctx* ctx, double* x, int64_t P, int num_steps, int gt_mode, float alpha, double* steps, float* g,
+                        float* H, int precision, void* stream);
+
 /* evaluate() of src/evaluate.py:5-37 with HOST buffers: chunks of max_batch points, fp32 compute, results
  * widened to float64 on the device and copied into the caller's arrays (any of them may be NULL). */
 int dudf_evaluate_host(dudf_ctx* ctx, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
