@@ -205,6 +205,16 @@ def aux_full_size_queries(dev):
     sec, _ = timed(lambda: extract_fields(m, None, 512, "tanh", dev, ALPHA))
     out["grid512_extract_fields_tc16_queries_per_s"] = 512 ** 3 / sec
     out["grid512_extract_fields_tc16_s"] = sec
+    # CAP-UDF marching cubes on those 512^3 fields (src/render_mc.py:201-256; classify + scan + emit, HBM-bound).  Algorithmic
+    # bytes: 4 B per grid point (distances; gradients are read for near-surface cells only), 2 B per cell (case byte written and
+    # read back), 72 B per triangle
+    from diffudf_b200.render_mc import cap_triangles
+    u512, g512 = extract_fields(m, None, 512, "tanh", dev, ALPHA)
+    sec, tri = timed(lambda: cap_triangles(u512, g512, 512), reps=3)
+    out["cap_mc_512_ms"] = sec * 1e3
+    out["cap_mc_512_triangles"] = int(tri.shape[0])
+    out["cap_mc_512_algorithmic_gb_per_s"] = (4 * 512 ** 3 + 2 * 511 ** 3 + 72 * int(tri.shape[0])) / sec / 1e9
+    del u512, g512, tri
     # evaluate(): host numpy in, float64 host arrays out (value + gradient), 2 M points
     xs = np.random.default_rng(0).uniform(-1, 1, (2_000_000, 3)).astype(np.float32)
     grads = np.zeros((xs.shape[0], 3))

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
-SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu"]
-HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh",
+SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
+HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh", "dudf_mc_table.h",
            os.path.join(ROOT, "include", "dudf_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
@@ -52,6 +52,7 @@ SIGNATURES = {
     "dudf_march_rays": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_int, c_int,
                         ctypes.POINTER(c_int64), c_void_p],
     "dudf_project_points": [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "dudf_cap_mesh": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int64, ctypes.POINTER(c_int64), c_void_p],
     "dudf_debug_set_trace": [c_void_p],
     "dudf_version": [],
     "dudf_launch_count": [],

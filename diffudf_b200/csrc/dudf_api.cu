@@ -58,7 +58,10 @@ struct dudf_ctx {
   const float* Wp[DUDF_MAX_LAYERS] = {};   // weights in use: the owned copies (dudf_set_weights) or borrowed (dudf_bind_weights)
   const float* bp[DUDF_MAX_LAYERS] = {};
   void* tc_packed = nullptr;
-  dudf::DevBuf ws_out, ws_x64, ws_drv;
+  dudf::DevBuf ws_out, ws_x64, ws_drv, ws_cap;
+  int cap_N = 0;                 // grid size of the classification held in ws_cap (0: none)
+  const float* cap_df = nullptr;
+  int64_t cap_ntris = 0;
   NetView view() const {
     NetView v;
     memset(&v, 0, sizeof(v));
@@ -280,6 +283,41 @@ int dudf_project_points(dudf_ctx* c, double* x, int64_t P, int num_steps, int gt
     if ((rc = drv_project(x, f, g, P, gt_mode, alpha, steps, st))) return rc;
   }
   return 0;
+}
+
+int dudf_cap_mesh(dudf_ctx* c, const float* df, const float* vecs, int N, float threshold, double* tris, int64_t capacity,
+                  int64_t* n_tris_host, void* stream) {
+  DUDF_REQUIRE(c != nullptr, "dudf_cap_mesh: null context");
+  DUDF_REQUIRE(df && vecs && n_tris_host, "dudf_cap_mesh: null argument");
+  DUDF_REQUIRE(N >= 2 && N <= 1290, "dudf_cap_mesh: N=%d out of range (2..1290)", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = N - 1, ncell = M * M * M, nblocks = (ncell + 255) / 256;
+  const size_t off_cnt = ((size_t)ncell + 255) / 256 * 256;
+  const size_t off_off = off_cnt + (size_t)nblocks * sizeof(long long);
+  const size_t off_tmp = off_off + (size_t)nblocks * sizeof(long long);
+  const size_t temp_bytes = cap_scan_temp_bytes(nblocks);
+  if (tris == nullptr) {
+    c->cap_N = 0;
+    if (c->ws_cap.ensure(off_tmp + temp_bytes)) return 1;
+    unsigned char* ws = (unsigned char*)c->ws_cap.p;
+    int rc = cap_classify(df, vecs, N, threshold, ws, (long long*)(ws + off_cnt), (long long*)(ws + off_off), ws + off_tmp, temp_bytes, st);
+    if (rc) return rc;
+    long long last_cnt = 0, last_off = 0;
+    DUDF_CUDA_OK(cudaMemcpyAsync(&last_cnt, (long long*)(ws + off_cnt) + (nblocks - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+    DUDF_CUDA_OK(cudaMemcpyAsync(&last_off, (long long*)(ws + off_off) + (nblocks - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+    DUDF_CUDA_OK(cudaStreamSynchronize(st));
+    c->cap_N = N;
+    c->cap_df = df;
+    c->cap_ntris = last_cnt + last_off;
+    *n_tris_host = c->cap_ntris;
+    return 0;
+  }
+  DUDF_REQUIRE(c->cap_N == N && c->cap_df == df, "dudf_cap_mesh: emit without a matching classification (call with tris == NULL first)");
+  DUDF_REQUIRE(capacity >= c->cap_ntris, "dudf_cap_mesh: buffer holds %lld triangles, %lld needed", (long long)capacity, (long long)c->cap_ntris);
+  *n_tris_host = c->cap_ntris;
+  if (c->cap_ntris == 0) return 0;
+  unsigned char* ws = (unsigned char*)c->ws_cap.p;
+  return cap_emit(df, ws, N, (const long long*)(ws + off_off), tris, st);
 }
 
 int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, double* f_host, double* g_host,

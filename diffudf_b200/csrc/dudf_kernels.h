@@ -116,6 +116,11 @@ int drv_advance(double* pos, const double* dir, const int* idx, const float* f, 
                 unsigned char* hit, unsigned char* keep, cudaStream_t st);
 int drv_mark(const int* idx, int64_t n, unsigned char* mask, cudaStream_t st);
 int drv_project(double* x, const float* f, const float* g, int64_t n, int gt_mode, float alpha, double* steps, cudaStream_t st);
+// ---- CAP-UDF marching cubes (dudf_capmc.cu; src/render_mc.py:201-256) ----
+size_t cap_scan_temp_bytes(int64_t nblocks);
+int cap_classify(const float* df, const float* vecs, int N, float thr, unsigned char* code, long long* block_count, long long* block_offset,
+                 void* temp, size_t temp_bytes, cudaStream_t st);
+int cap_emit(const float* df, const unsigned char* code, int N, const long long* block_offset, double* tris, cudaStream_t st);
 int loss_seeds(const LossArgs& a, cudaStream_t st);
 int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st);
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);

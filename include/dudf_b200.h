@@ -110,6 +110,18 @@ int dudf_march_rays(dudf_ctx* ctx, double* pos, const double* dir, unsigned char
 int dudf_project_points(dudf_ctx* ctx, double* x, int64_t P, int num_steps, int gt_mode, float alpha, double* steps, float* g,
                         float* H, int precision, void* stream);
 
+/* CAP-UDF marching cubes: extract_mesh_CAP(ndf, grad, resolution) of src/render_mc.py:201-256 on the device, fed by the
+ * outputs of dudf_query_grid.  df: [N][N][N] distances, vecs: [N][N][N][3] (negated, normalised) gradients.  A cell whose smallest
+ * corner distance exceeds `threshold` (0.008 in the reference) is skipped; corner c is negative when
+ * dot(vecs[corner 0], vecs[corner c]) < 0; cells with a negative corner are triangulated by marching cubes at iso-value 0 (vertices
+ * at the linear zero crossings, float64, mapped to [-1,1]^3).  Triangles come out in the reference's cell order (i, j, k
+ * lexicographic) as a soup: tris [n][3 vertices][3] float64.  The per-cell triangulation table is generated from the published
+ * algorithm (tools/gen_mc_table.py); PyMCubes' table (mcubes.marching_cubes, render_mc.py:231) is not part of the reference tree.
+ * Call with tris == NULL to classify the cells and get the triangle count in *n_tris_host, then with a buffer of at least that
+ * many triangles (capacity, in triangles) to emit them from the classification the context holds. */
+int dudf_cap_mesh(dudf_ctx* ctx, const float* df, const float* vecs, int N, float threshold, double* tris, int64_t capacity,
+                  int64_t* n_tris_host, void* stream);
+
 /* evaluate() of src/evaluate.py:5-37 with HOST buffers: chunks of max_batch points, fp32 compute, results
  * widened to float64 on the device and copied into the caller's arrays (any of them may be NULL). */
 int dudf_evaluate_host(dudf_ctx* ctx, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
