@@ -291,7 +291,7 @@ int dudf_cap_mesh(dudf_ctx* c, const float* df, const float* vecs, int N, float 
   DUDF_REQUIRE(df && vecs && n_tris_host, "dudf_cap_mesh: null argument");
   DUDF_REQUIRE(N >= 2 && N <= 1290, "dudf_cap_mesh: N=%d out of range (2..1290)", N);
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t M = N - 1, ncell = M * M * M, nblocks = (ncell + 255) / 256;
+  const int64_t M = N - 1, ncell = M * M * M, nblocks = cap_units(ncell);
   const size_t off_cnt = ((size_t)ncell + 255) / 256 * 256;
   const size_t off_off = off_cnt + (size_t)nblocks * sizeof(long long);
   const size_t off_tmp = off_off + (size_t)nblocks * sizeof(long long);

@@ -118,6 +118,7 @@ int drv_mark(const int* idx, int64_t n, unsigned char* mask, cudaStream_t st);
 int drv_project(double* x, const float* f, const float* g, int64_t n, int gt_mode, float alpha, double* steps, cudaStream_t st);
 // ---- CAP-UDF marching cubes (dudf_capmc.cu; src/render_mc.py:201-256) ----
 size_t cap_scan_temp_bytes(int64_t nblocks);
+int cap_units(int64_t ncell);      // blocks of consecutive cells that form the unit of the output order
 int cap_classify(const float* df, const float* vecs, int N, float thr, unsigned char* code, long long* block_count, long long* block_offset,
                  void* temp, size_t temp_bytes, cudaStream_t st);
 int cap_emit(const float* df, const unsigned char* code, int N, const long long* block_offset, double* tris, cudaStream_t st);
