@@ -291,11 +291,15 @@ tt_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev 
 // adjoints of u, written to the B tile (layers > 0); accumulates the thread's gradient partial sums
 // RECOMP0 (with FIRST): the first layer's pre-activations are recomputed from the points instead of read from the stash
 struct FirstRow { float w0, rx, ry, rz, b; };
-template <int NCH, int GC, bool TOP, bool FIRST, bool RECOMP0 = false>
+template <int NCH, int GC, bool TOP, bool FIRST, bool RECOMP0 = false, bool NOW = false>
 __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr, uint32_t next_taddr, float wl, const float* sdg,
                                              const float* pts, unsigned char* trow, int chunk0, uint32_t r7, float& bsum, float& wlsum,
                                              float (&w0s)[3], const FirstRow* fr = nullptr) {
   float u[GC], ab[GC];
+  // NOW (fused kernel): the group's own accumulators are loaded here and used in place — the TMEM load (tens of clocks) hides behind
+  // the scratch conversion below; prefetching them a group ahead made ptxas copy all 32 / 40 staging registers out and back
+  // (64 moves per 8-point group, profiles/r1b_ncu_fused_hot_sass.txt)
+  if constexpr (!TOP && NOW) tc_ld_issue<GC>(next_taddr, tr);
   if constexpr (FIRST && RECOMP0) tc_first_layer_group<NCH, GC>(u, pts, fr->w0, fr->rx, fr->ry, fr->rz, fr->b);
   else tt_unstash_group<NCH, GC>(u, raw);
   if constexpr (TOP) {
@@ -303,7 +307,9 @@ __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr,
     for (int j = 0; j < GC; ++j) ab[j] = wl * sdg[j];
   } else {
     tc_ld_take<GC>(tr, ab);
-    if (next_taddr) tc_ld_issue<GC>(next_taddr, tr);           // next group's accumulators, in flight during the math
+    if constexpr (!NOW) {
+      if (next_taddr) tc_ld_issue<GC>(next_taddr, tr);         // next group's accumulators, in flight during the math
+    }
   }
 #pragma unroll
   for (int pp = 0; pp < GC / NCH; ++pp) {
@@ -813,19 +819,18 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
       tc_trace(e.trace, e.tn, 30 + s, l);
       float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
       TmemRegs<GC> tr;
-      if (!top) tc_ld_issue<GC>(e.tmem_lane + s * 256, tr);
 #pragma unroll 1
       for (int g = 0; g < C::NGRP; ++g) {
         uint4 ug[NRAW];
 #pragma unroll
         for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
         if (g + 1 < C::NGRP && !nostash) tt_stash_load<NCH, GC>(nxt, ust + (size_t)(g + 1) * GC * 256);
-        const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * GC : 0u;
+        const uint32_t tcur = e.tmem_lane + s * 256 + g * GC;
         const float* sdg = sd + s * 256 + g * GC;
         const float* pts = e.xs + (s * C::PT + g * (GC / NCH)) * 3;
         const int c0 = g * (GC / 8);
-        if (top) tt_bwd_group<NCH, GC, true, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else     tt_bwd_group<NCH, GC, false, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        if (top) tt_bwd_group<NCH, GC, true, false, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else     tt_bwd_group<NCH, GC, false, false, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
         if ((fd.flags & 1) && (e.lane & 7) == 0) {
 #pragma unroll
           for (int j = 0; j < NRAW; ++j) l2_discard_line(ust + (size_t)g * GC * 256 + j * 1024);
@@ -848,12 +853,11 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
     tc_trace(e.trace, e.tn, 30 + s, 0);
     float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
     TmemRegs<GC> tr;
-    tc_ld_issue<GC>(e.tmem_lane + s * 256, tr);
 #pragma unroll 1
     for (int g = 0; g < C::NGRP; ++g) {
-      const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * GC : 0u;
+      const uint32_t tcur = e.tmem_lane + s * 256 + g * GC;
       const float* pts = e.xs + (s * C::PT + g * (GC / NCH)) * 3;
-      tt_bwd_group<NCH, GC, false, true, true>(nullptr, tr, tnext, wl, nullptr, pts, nullptr, 0, e.r7, bsum, wlsum, w0s, &fr);
+      tt_bwd_group<NCH, GC, false, true, true, true>(nullptr, tr, tcur, wl, nullptr, pts, nullptr, 0, e.r7, bsum, wlsum, w0s, &fr);
     }
     tc_trace(e.trace, e.tn, 32 + s, 0);
     atomicAdd(&grad.b[0][e.n], bsum * net.w0 * invS);
