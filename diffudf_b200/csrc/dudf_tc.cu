@@ -121,6 +121,7 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
     const float bL = net.b[L][0];
     const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
     uint32_t acc_phase = 0;                                 // bit s = parity of acc_ready[s]
+    const bool inplace = ((out.flags >> 8) & 64) == 0;      // diagnostics bit 6: prefetch the accumulators a group ahead
     unsigned long long* etrace = (out.trace && blockIdx.x == 0 && warp == 0) ? out.trace + TC_TRACE_REGION : nullptr;
     uint32_t en = 0;
 
@@ -160,15 +161,29 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
             }
           } else if (!((out.flags >> 8) & 1)) {       // flags bit 8: pipeline diagnostics — skip the epilogue math
             TmemRegs<C::GC> nxt;
-            tc_ld_issue<C::GC>(tmem_lane + s * 256, nxt);
+            if (inplace) {
+              // accumulators loaded and used in place: a TMEM load takes tens of clocks, while prefetching a group ahead makes
+              // ptxas copy the 32 / 40 staging registers of every group (DUDF_TC_INPLACE=0 restores the prefetch)
 #pragma unroll 1
-            for (int g = 0; g < C::NGRP; ++g) {
-              float u[C::GC];
-              tc_ld_take<C::GC>(nxt, u);
-              if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(tmem_lane + s * 256 + (g + 1) * C::GC, nxt);   // in flight during the math below
+              for (int g = 0; g < C::NGRP; ++g) {
+                float u[C::GC];
+                tc_ld_issue<C::GC>(tmem_lane + s * 256 + g * C::GC, nxt);
+                tc_ld_take<C::GC>(nxt, u);
 #pragma unroll
-              for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
-              tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
+                for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
+                tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
+              }
+            } else {
+              tc_ld_issue<C::GC>(tmem_lane + s * 256, nxt);
+#pragma unroll 1
+              for (int g = 0; g < C::NGRP; ++g) {
+                float u[C::GC];
+                tc_ld_take<C::GC>(nxt, u);
+                if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(tmem_lane + s * 256 + (g + 1) * C::GC, nxt);   // in flight during the math below
+#pragma unroll
+                for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
+                tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
+              }
             }
           }
           tc_trace(etrace, en, 12 + s, l);

@@ -721,12 +721,11 @@ __device__ __forceinline__ void tt_fused_pair(EpiCtx& e, const NetView& net, con
         }
       } else {
         TmemRegs<GC> nxt;
-        tc_ld_issue<GC>(e.tmem_lane + s * 256, nxt);
 #pragma unroll 1
         for (int g = 0; g < C::NGRP; ++g) {
           float u[GC];
+          tc_ld_issue<GC>(e.tmem_lane + s * 256 + g * GC, nxt);      // loaded and used in place (see tt_bwd_group)
           tc_ld_take<GC>(nxt, u);
-          if (g + 1 < C::NGRP) tc_ld_issue<GC>(e.tmem_lane + s * 256 + (g + 1) * GC, nxt);
 #pragma unroll
           for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
           if (!nostash) tt_stash_group<NCH, GC>(u, ust + (size_t)g * GC * 256);

@@ -18,7 +18,7 @@ df = torch.empty(cnt, device="cuda")
 vecs = torch.empty(cnt, 3, device="cuda")
 H = None
 for order_name, want_h in (("f+grad (4 ch)", False), ("f+grad+hess (10 ch)", True)):
-    for name, dbg in (("full", 0), ("no MMA", 2 << 8), ("no epilogue math", 1 << 8), ("neither", 3 << 8),
+    for name, dbg in (("full", 0), ("full, accumulators prefetched a group ahead", 64 << 8), ("no MMA", 2 << 8), ("no epilogue math", 1 << 8), ("neither", 3 << 8),
                       ("no weight streaming", 4 << 8), ("no weights, no epilogue math", 5 << 8),
                       ("no weights, no MMA", 6 << 8), ("no weights, neither", 7 << 8),
                       ("protocol only (no first/output layer either)", 15 << 8), ("full minus first/output layer", 8 << 8)):
@@ -30,4 +30,4 @@ for order_name, want_h in (("f+grad (4 ch)", False), ("f+grad+hess (10 ch)", Tru
             t.record()
             torch.cuda.synchronize()
         ms = s.elapsed_time(t)
-        print(f"{order_name:22s} {name:18s}: {ms:8.3f} ms  {cnt / ms / 1e3:8.1f} M queries/s", flush=True)
+        print(f"{order_name:22s} {name:46s}: {ms:8.3f} ms  {cnt / ms / 1e3:8.1f} M queries/s", flush=True)
