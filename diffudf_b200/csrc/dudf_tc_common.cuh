@@ -390,13 +390,18 @@ __device__ __forceinline__ void tc_first_layer_group(float* u, const float* pts,
 }
 
 // pack GC fp32 values of one thread into halves and store them as GC/8 16-byte chunks of its tile row
+// 16-byte store through a 32-bit shared-memory address (STS.128; a store through the generic pointer costs a 64-bit address
+// add per chunk and goes down the generic path)
+__device__ __forceinline__ void tc_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 template <int GC>
 __device__ __forceinline__ void tc_store_group(const float* v, unsigned char* trow, int chunk0, uint32_t r7) {
+  const uint32_t base = umma::smem_u32(trow);
 #pragma unroll
   for (int c8 = 0; c8 < GC / 8; ++c8)
-    *reinterpret_cast<uint4*>(trow + tc_chunk_off(chunk0 + c8, r7)) =
-        make_uint4(tc_pack_h2(v[8 * c8], v[8 * c8 + 1]), tc_pack_h2(v[8 * c8 + 2], v[8 * c8 + 3]), tc_pack_h2(v[8 * c8 + 4], v[8 * c8 + 5]),
-                   tc_pack_h2(v[8 * c8 + 6], v[8 * c8 + 7]));
+    tc_sts128(base + tc_chunk_off(chunk0 + c8, r7), tc_pack_h2(v[8 * c8], v[8 * c8 + 1]), tc_pack_h2(v[8 * c8 + 2], v[8 * c8 + 3]),
+              tc_pack_h2(v[8 * c8 + 4], v[8 * c8 + 5]), tc_pack_h2(v[8 * c8 + 6], v[8 * c8 + 7]));
 }
 
 // sine-jet of GC/NCH points (in place) and store into the B-operand tile.  PRECISE: explicit 2*pi reduction

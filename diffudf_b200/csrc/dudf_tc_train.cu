@@ -37,11 +37,11 @@ __device__ __forceinline__ uint32_t tt_pack_h2_sat(float lo, float hi) {
 }
 template <int GC>
 __device__ __forceinline__ void tt_store_group_sat(const float* v, unsigned char* trow, int chunk0, uint32_t r7) {
+  const uint32_t base = umma::smem_u32(trow);
 #pragma unroll
   for (int c8 = 0; c8 < GC / 8; ++c8)
-    *reinterpret_cast<uint4*>(trow + tc_chunk_off(chunk0 + c8, r7)) =
-        make_uint4(tt_pack_h2_sat(v[8 * c8], v[8 * c8 + 1]), tt_pack_h2_sat(v[8 * c8 + 2], v[8 * c8 + 3]),
-                   tt_pack_h2_sat(v[8 * c8 + 4], v[8 * c8 + 5]), tt_pack_h2_sat(v[8 * c8 + 6], v[8 * c8 + 7]));
+    tc_sts128(base + tc_chunk_off(chunk0 + c8, r7), tt_pack_h2_sat(v[8 * c8], v[8 * c8 + 1]), tt_pack_h2_sat(v[8 * c8 + 2], v[8 * c8 + 3]),
+              tt_pack_h2_sat(v[8 * c8 + 4], v[8 * c8 + 5]), tt_pack_h2_sat(v[8 * c8 + 6], v[8 * c8 + 7]));
 }
 
 // ---- thread-major stash of one column group: chunk j of the group lives at dst + j*1024 floats (+ 4*neuron) -------
