@@ -312,6 +312,61 @@ __device__ __forceinline__ void tc_mma_role_skew(unsigned char* act, unsigned ch
     }
 }
 
+// ---- forward-only skewed schedule (query kernel, DUDF_TC_SKEW): stream s (sub-tile s of every pair) walks the steps
+// ---- (pair, layer 0 .. n_layer-1); stream 1 runs `lag` steps behind stream 0, so that the layers of one sub-tile that need no MMA
+// ---- (first layer, output layer) fall into the MMA phases of the other.  Step l < n_layer - 1 of a stream is followed by the
+// ---- MMA phase of layer l; slot t serves step t of stream 0 and step t - lag of stream 1.
+__device__ __forceinline__ void tc_producer_fwd_skew(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty,
+                                                     int64_t rounds, int n_layer, int lag) {
+  using namespace umma;
+  uint32_t stage = 0, phase = 0;
+  const int64_t total = rounds * n_layer;
+  for (int64_t t = 0; t < total + lag; ++t)
+    for (int s = 0; s < 2; ++s) {
+      const int64_t st = s ? t - lag : t;
+      if (st < 0 || st >= total) continue;
+      const int l = (int)(st % n_layer);
+      if (l == n_layer - 1) continue;
+      const unsigned char* src = packed + (size_t)l * 8 * TC_CHUNK_BYTES;
+      for (int ck = 0; ck < 8; ++ck) {
+        mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x100 + stage);
+        mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
+        bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+}
+
+__device__ __forceinline__ void tc_mma_role_fwd_skew(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                                     uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_layer, int lag) {
+  using namespace umma;
+  constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
+  const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
+  const uint64_t b_desc0 = make_desc_sw128(smem_u32(act), 32768, 1024);
+  uint32_t stage = 0, phase = 0, act_phase = 0;
+  const int64_t total = rounds * n_layer;
+  for (int64_t t = 0; t < total + lag; ++t)
+    for (int s = 0; s < 2; ++s) {
+      const int64_t st = s ? t - lag : t;
+      if (st < 0 || st >= total) continue;
+      if ((int)(st % n_layer) == n_layer - 1) continue;
+      mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
+      act_phase ^= 1u << s;
+      tc_fence_after();
+      const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&full[stage], phase, 0x300 + stage);
+          mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(b_desc, kb * 8 * 1024), idesc, kb != 0);
+          mma_commit_warp(&empty[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      mma_commit_warp(&acc_ready[s]);
+    }
+}
+
 template <int GC>
 __device__ __forceinline__ void tc_load_group(uint32_t taddr, float* u) {
   uint32_t r[32];
