@@ -175,6 +175,30 @@ def aux_device_sampler(dev, trainer):
     return out
 
 
+def aux_other_losses(dev, batches, n_on):
+    """The other two loss configurations of the training loop on the same batches: loss_s2 (value-only
+    forward, batch statistics, reverse sweep: train.py:174-191) and loss_siren (train.py:23-143), tensor-core path."""
+    import torch
+    from diffudf_b200 import SIREN
+    from diffudf_b200.train import FusedTrainer
+    out = {}
+    for mode, w, key in (("s2", [1e5, 1e5], "loss_s2"), ("siren", [3e3, 1e2, 1e2, 5e1], "loss_siren")):
+        torch.manual_seed(123)
+        tr = FusedTrainer(SIREN(3, 1, [256] * 8, w0=30).to(dev), precision="tc16")
+        for i in range(4):
+            tr.step(mode, *batches[i % len(batches)], n_on, w, ALPHA, LR)
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(20):
+            tr.step(mode, *batches[i % len(batches)], n_on, w, ALPHA, LR)
+        t.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(t) / 20
+        out[f"{key}_step_ms"] = ms
+        out[f"{key}_train_points_per_s"] = batches[0][0].shape[0] / (ms * 1e-3)
+    return out
+
+
 def aux_full_size_queries(dev):
     """BASELINE configs 3-5 at full size on one GPU (tensor-core path, trained fixture weights when present):
     512^3 grid for marching cubes, evaluate() with host buffers, 1024^2 sphere tracing, 2 M-point NDF projection."""
@@ -418,6 +442,7 @@ def run_ours(args, rank, local_rank, world):
         try:
             aux.update(aux_full_size_queries(dev))
             if args.precision == "tc16":
+                aux.update(aux_other_losses(dev, resident, n_on))
                 aux.update(aux_device_sampler(dev, FusedTrainer(SIREN(3, 1, [256] * 8, w0=30).to(dev), precision="tc16")))
         except Exception as exc:          # the secondary numbers must never cost the headline line
             aux["full_size_error"] = repr(exc)[:200]

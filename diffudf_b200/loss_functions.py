@@ -28,7 +28,7 @@ class TrainCore:
         self.precision = precision          # None -> model.train_precision (default 'fp32')
         self.amax = None                    # (2,) fp32: max|stored seed| of the last two tensor-core steps (loss scale source)
         self.amax_key, self.amax_slot = None, 0
-        self.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "3"))
+        self.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "2"))   # evict-first operand images; discarding consumed scratch lines (bit 0) costs 1.5 %
 
     def _prec(self):
         return self.precision or getattr(self.model, "train_precision", "fp32")

@@ -18,7 +18,7 @@ batches = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x[0]
 torch.manual_seed(123)
 model = SIREN(3, 1, [256] * 8, w0=30).cuda()
 tr = FusedTrainer(model, precision="tc16", fused=True)
-tr.core.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "3"))
+tr.core.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "2"))
 for i in range(4):
     tr.step("s1", *batches[i % 2], 9990, W_S1, ALPHA, LR)
 buf = torch.zeros(3 * 8192, dtype=torch.int64, device="cuda")

@@ -19,7 +19,7 @@ prec = sys.argv[3] if len(sys.argv) > 3 else "tc16"
 torch.manual_seed(123)
 model = SIREN(3, 1, [256] * 8, w0=30).cuda()
 tr = FusedTrainer(model, precision=prec, fused=os.environ.get("DUDF_FUSED", "1") != "0")
-tr.core.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "3"))
+tr.core.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "2"))
 x, n, d = make_batches(1, 0)[0]
 x, n, d = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x[0], n[0], d[0, :, 0]))
 for _ in range(steps):
