@@ -898,6 +898,10 @@ tt_fused_kernel(const unsigned char* __restrict__ packed, NetView net, GradView 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (((fd.flags >> 8) & 128) && (blockIdx.x & 1)) {        // diagnostics: odd CTAs start half a pair late (are the store-heavy
+    const long long t0 = clock64();                          // forward sweeps of all CTAs at the same time the problem?  No:
+    while (clock64() - t0 < 120000) {}                       // the per-layer forward time does not change)
+  }
 
   if (warp >= 8) {
     setmaxnreg_dec<TC_REGS_AUX>();
