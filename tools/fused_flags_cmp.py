@@ -6,7 +6,7 @@ from diffudf_b200 import SIREN
 from diffudf_b200.train import FusedTrainer
 batches = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x[0], n[0], d[0, :, 0])) for x, n, d in make_batches(4, 0)]
 for rep in range(3):
-    for flags in (0, 1, 2, 3):
+    for flags in ([int(a) for a in sys.argv[1:]] or [0, 1, 2, 3]):
         torch.manual_seed(123)
         tr = FusedTrainer(SIREN(3, 1, [256] * 8, w0=30).cuda(), precision="tc16", fused=True)
         tr.core.fused_flags = flags
