@@ -34,17 +34,19 @@ def test_beetle_schedule_matches_reference_run(precision, golden, weights):
         # 2 997-row means).  Afterwards Adam's sign-like first update (every parameter moves by +-lr, the sign of a near-zero
         # gradient is rounding noise) makes fp32 trajectories from the SIREN init diverge: 0.7 % in the Hessian term at step 1
         # (tests/test_gpu_losses.py::test_fused_trainer_trajectory): sanity band.
-        # From step 2 on the run is a different sample of a chaotic trajectory: replacing rintf by the equivalent
-        # add-and-subtract rounding in the sine's range reduction (a last-bit change) moved the Hessian term of step 4 from
-        # within 35 % of the reference's to 54 % above it, while the total moved by 10 %.  So: the total within 35 %, every
-        # term within 60 % (+ 2 % of the total for the small ones; the on-surface |f| mean is 2 % of the total).
-        rtol = (1e-4 if precision == "fp32" else 2e-3) if e == 0 else (2e-2 if e == 1 else 0.6)
+        # From step 2 on the run is a different sample of a chaotic trajectory (Adam's first updates move every parameter by +-lr
+        # and the sign of a near-zero gradient is rounding noise; the fp32 step also accumulates with float atomics).  Measured
+        # spread between OUR OWN fp32 runs on identical inputs: on-surface term of step 4 = 61 / 138 / 167 / 173, Hessian term of
+        # steps 4-7 = 1.0x ... 1.95x the reference's, total within 10 %.  So from step 2 on: the total within 35 %, every term
+        # within a factor of 3 (+ 5 % of the total for the small ones); steps 0 and 1 are the parity checks.
         if e < 8:
-            # (the fp32 step accumulates with float atomics: runs differ in the last bit and from step 2 on by as much as two
-            # different trajectories do — the on-surface term of step 4, 2 % of the total, came out at 61 / 138 / 167 / 173 in four
-            # runs — so the small terms are held to 5 % of the total)
-            assert np.allclose(terms[: len(ref)], ref, rtol=rtol, atol=1e-3 if e < 2 else 0.05 * float(ref.sum())), (e, terms, ref)
-            assert abs(float(terms[: len(ref)].sum()) - float(ref.sum())) <= (rtol if e < 2 else 0.35) * float(ref.sum()), (e, terms, ref)
+            if e < 2:
+                rtol = (1e-4 if precision == "fp32" else 2e-3) if e == 0 else 2e-2
+                assert np.allclose(terms[: len(ref)], ref, rtol=rtol, atol=1e-3), (e, terms, ref)
+            else:
+                tot = float(ref.sum())
+                assert abs(float(terms[: len(ref)].sum()) - tot) <= 0.35 * tot, (e, terms, ref)
+                assert np.all(terms[: len(ref)] <= 3.0 * ref + 0.05 * tot) and np.all(terms[: len(ref)] >= ref / 3.0 - 0.05 * tot), (e, terms, ref)
         else:
             # loss_s2 after 8 diverged steps: the spread of the on-surface predictions is comparable, their signed mean
             # (|mean| is the first term) is a cancellation of values of either sign and is only bounded by the spread
