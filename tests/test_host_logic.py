@@ -111,3 +111,25 @@ def test_eigh3_restatement_matches_numpy():
     B[:, 0, 1] += 5.0                                  # upper triangle must be ignored (LAPACK 'L')
     lam2, _ = O.eig_top(B)
     assert np.allclose(lam, lam2)
+
+
+def test_triangle_soup_export_roundtrip(tmp_path):
+    """What extract_mesh_CAP returns in place of trimesh.Trimesh(..., process=False): .vertices / .faces / .export (render_mc.py:253)."""
+    import numpy as np
+    from diffudf_b200.render_mc import TriangleSoup
+    v = np.random.default_rng(0).normal(size=(6, 3))
+    f = np.arange(6, dtype=np.int64).reshape(2, 3)
+    m = TriangleSoup(v, f)
+    for name in ("m.obj", "m.ply"):
+        p = tmp_path / name
+        m.export(str(p))
+        txt = p.read_text().splitlines()
+        if name.endswith(".obj"):
+            vs = np.array([[float(t) for t in l.split()[1:]] for l in txt if l.startswith("v ")])
+            fs = np.array([[int(t) - 1 for t in l.split()[1:]] for l in txt if l.startswith("f ")])
+        else:
+            h = txt.index("end_header")
+            assert f"element vertex {len(v)}" in txt and f"element face {len(f)}" in txt
+            vs = np.array([[float(t) for t in l.split()] for l in txt[h + 1:h + 1 + len(v)]])
+            fs = np.array([[int(t) for t in l.split()[1:]] for l in txt[h + 1 + len(v):]])
+        assert np.array_equal(vs, v) and np.array_equal(fs, f)          # repr() round-trips float64 exactly
