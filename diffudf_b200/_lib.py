@@ -53,6 +53,8 @@ SIGNATURES = {
                         ctypes.POINTER(c_int64), c_void_p],
     "dudf_project_points": [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dudf_cap_mesh": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int64, ctypes.POINTER(c_int64), c_void_p],
+    "dudf_shade_hits": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_double),
+                        ctypes.POINTER(ctypes.c_double), c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p],
     "dudf_debug_set_trace": [c_void_p],
     "dudf_version": [],
     "dudf_launch_count": [],

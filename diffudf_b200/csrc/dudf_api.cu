@@ -285,6 +285,18 @@ int dudf_project_points(dudf_ctx* c, double* x, int64_t P, int num_steps, int gt
   return 0;
 }
 
+int dudf_shade_hits(const long long* rows, int64_t H, const double* samples, const double* normals, const double* pc1, const double* pc2,
+                    const double* color_map, const double* light_host, const double* camera_host, int method, double shininess,
+                    double alpha1, double alpha2, double* colors, void* stream) {
+  DUDF_REQUIRE(H >= 0, "dudf_shade_hits: negative hit count");
+  if (H == 0) return 0;
+  DUDF_REQUIRE(rows && samples && normals && light_host && colors, "dudf_shade_hits: null argument");
+  DUDF_REQUIRE(method == 0 || method == 1, "dudf_shade_hits: method %d (0 Blinn-Phong, 1 Ward)", method);
+  DUDF_REQUIRE(method == 0 || (pc1 && pc2 && camera_host), "dudf_shade_hits: Ward reflectance needs the principal directions and the camera");
+  return drv_shade(rows, H, samples, normals, pc1, pc2, color_map, light_host, camera_host, method, shininess, alpha1, alpha2, colors,
+                   (cudaStream_t)stream);
+}
+
 int dudf_cap_mesh(dudf_ctx* c, const float* df, const float* vecs, int N, float threshold, double* tris, int64_t capacity,
                   int64_t* n_tris_host, void* stream) {
   DUDF_REQUIRE(c != nullptr, "dudf_cap_mesh: null context");

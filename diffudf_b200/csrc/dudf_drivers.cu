@@ -79,6 +79,70 @@ __global__ void __launch_bounds__(256) drv_project_kernel(double* __restrict__ x
   steps[i] = step;
 }
 
+// ---- shading of the hit points: phong_shading / ward_reflectance of src/render_st.py:174-245, one thread per hit, float64 like the
+// ---- reference's numpy arrays; sums of three products in numpy's order, no fused multiply-adds
+struct ShadeArgs {
+  const long long* rows;      // [H] ray index of every hit, ascending (np.nonzero(hits))
+  const double* samples;      // [R][3] ray positions (t0)
+  const double* normals;      // [H][3]
+  const double* pc1;          // [H][3] principal directions (Ward), or null
+  const double* pc2;
+  const double* color_map;    // [H][3] or null (grey 0.7 / 0.7 / 0.2)
+  double light[3], camera[3];
+  double shininess, alpha1, alpha2;
+  int method;                 // 0 Blinn-Phong, 1 Ward
+  double* colors;             // [R][3], rows of rays that did not hit are left as the caller filled them (ones)
+};
+__device__ __forceinline__ double dot3(const double* a, const double* b) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a[0], b[0]), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+}
+__device__ __forceinline__ void normalize3(double* v) {
+  const double n = sqrt(dot3(v, v));
+  v[0] /= n; v[1] /= n; v[2] /= n;
+}
+__global__ void __launch_bounds__(256) drv_shade_kernel(ShadeArgs a, int64_t H) {
+  const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const int64_t r = a.rows[h];
+  const double p[3] = {a.samples[r * 3], a.samples[r * 3 + 1], a.samples[r * 3 + 2]};
+  const double n[3] = {a.normals[h * 3], a.normals[h * 3 + 1], a.normals[h * 3 + 2]};
+  double Ld[3] = {a.light[0] - p[0], a.light[1] - p[1], a.light[2] - p[2]};
+  normalize3(Ld);
+  const double nl = dot3(n, Ld);
+  const double lambertian = fmax(nl, 0.0);
+  double specular = 0.0;
+  if (a.method == 0) {
+    const double I[3] = {-1.0 * Ld[0], -1.0 * Ld[1], -1.0 * Ld[2]};
+    const double k = 2.0 * dot3(n, I);
+    const double Rv[3] = {I[0] - k * n[0], I[1] - k * n[1], I[2] - k * n[2]};
+    double V[3] = {p[0], p[1], p[2]};
+    normalize3(V);
+    const double sa = fmax(dot3(Rv, V), 0.0);
+    if (a.shininess > 0.0 && lambertian > 0.0) specular = pow(sa, a.shininess);
+  } else {
+    double Vd[3] = {a.camera[0] - p[0], a.camera[1] - p[1], a.camera[2] - p[2]};
+    normalize3(Vd);
+    double Hh[3] = {Vd[0] + Ld[0], Vd[1] + Ld[1], Vd[2] + Ld[2]};
+    normalize3(Hh);
+    const double pc1[3] = {a.pc1[h * 3], a.pc1[h * 3 + 1], a.pc1[h * 3 + 2]};
+    const double pc2[3] = {a.pc2[h * 3], a.pc2[h * 3 + 1], a.pc2[h * 3 + 2]};
+    const double weight = 1.0 / (4.0 * 3.141592653589793 * a.alpha1 * a.alpha2 * sqrt(nl * dot3(n, Vd)));
+    const double t1 = dot3(Hh, pc1) / a.alpha1, t2 = dot3(Hh, pc2) / a.alpha2;
+    double sp = weight * exp(-2.0 * (t1 * t1 + t2 * t2) / (1.0 + dot3(n, Hh)));
+    if (isnan(sp)) sp = 0.0;                                    // np.nan_to_num
+    else if (isinf(sp)) sp = sp > 0.0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    specular = sp * 0.1;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double cm = a.color_map ? a.color_map[h * 3 + c] : 1.0;
+    const double dc = a.color_map ? cm * 0.7 : 0.7, am = a.color_map ? cm * 0.2 : 0.2;
+    double v = __dadd_rn(__dadd_rn(__dmul_rn(dc, lambertian), __dmul_rn(dc, specular)), am);
+    v = fmin(fmax(v, 0.0), 0.9);
+    a.colors[r * 3 + c] = v;
+  }
+}
+
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 size_t drv_select_temp_bytes(int64_t R) {
@@ -123,6 +187,19 @@ int drv_mark(const int* idx, int64_t n, unsigned char* mask, cudaStream_t st) {
 int drv_project(double* x, const float* f, const float* g, int64_t n, int gt_mode, float alpha, double* steps, cudaStream_t st) {
   if (n <= 0) return 0;
   drv_project_kernel<<<blocks_for(n), 256, 0, st>>>(x, f, g, n, gt_mode, (double)alpha, steps);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
+int drv_shade(const long long* rows, int64_t H, const double* samples, const double* normals, const double* pc1, const double* pc2,
+              const double* color_map, const double* light, const double* camera, int method, double shininess, double alpha1, double alpha2,
+              double* colors, cudaStream_t st) {
+  if (H <= 0) return 0;
+  ShadeArgs a;
+  a.rows = rows; a.samples = samples; a.normals = normals; a.pc1 = pc1; a.pc2 = pc2; a.color_map = color_map;
+  for (int k = 0; k < 3; ++k) { a.light[k] = light[k]; a.camera[k] = camera ? camera[k] : 0.0; }
+  a.shininess = shininess; a.alpha1 = alpha1; a.alpha2 = alpha2; a.method = method; a.colors = colors;
+  drv_shade_kernel<<<blocks_for(H), 256, 0, st>>>(a, H);
   DUDF_LAUNCH_OK();
   return 0;
 }

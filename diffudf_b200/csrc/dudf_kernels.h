@@ -116,6 +116,9 @@ int drv_advance(double* pos, const double* dir, const int* idx, const float* f, 
                 unsigned char* hit, unsigned char* keep, cudaStream_t st);
 int drv_mark(const int* idx, int64_t n, unsigned char* mask, cudaStream_t st);
 int drv_project(double* x, const float* f, const float* g, int64_t n, int gt_mode, float alpha, double* steps, cudaStream_t st);
+int drv_shade(const long long* rows, int64_t H, const double* samples, const double* normals, const double* pc1, const double* pc2,
+              const double* color_map, const double* light, const double* camera, int method, double shininess, double alpha1, double alpha2,
+              double* colors, cudaStream_t st);
 // ---- CAP-UDF marching cubes (dudf_capmc.cu; src/render_mc.py:201-256) ----
 size_t cap_scan_temp_bytes(int64_t nblocks);
 int cap_units(int64_t ncell);      // blocks of consecutive cells that form the unit of the output order

@@ -1,8 +1,9 @@
 """Sphere tracing field queries: drop-in for the query side of /root/reference/src/render_st.py
 (evaluate :13-36, compute_curvature :42-55, compute_normals_and_cd :57-62, compute_grad :64-65,
-propagate_rays :136-161, grad_descent :163-172).  The march keeps rays on the device (one active-count
-read-back per iteration instead of a full D2H of the values); shading / colour maps are host glue and
-out of scope."""
+propagate_rays :136-161, grad_descent :163-172) and of its shading side (create_projectional_image :67-134,
+phong_shading :174-205, ward_reflectance :207-245).  The march keeps rays on the device (one active-count
+read-back per iteration instead of a full D2H of the values); hit attributes and shading run on the device too
+(dudf_shade_hits, float64 like the reference's numpy arrays)."""
 import numpy as np
 import torch
 
@@ -127,3 +128,94 @@ def hit_attributes(model, points, ray_dirs=None, curvature="mean"):
             out["mean"] = out["mean"] * align[:, 0]
     out["normals"] = n
     return out
+
+
+# ---- shading (src/render_st.py:174-245) -------------------------------------------------------------------------------------
+def _shade(method, light_position, camera_position, hits, samples, normals, shininess=0.0, alpha1=1.0, alpha2=1.0, pc1=None, pc2=None,
+           color_map=None, device=None):
+    import ctypes
+
+    from . import _lib
+    dev = torch.device(device) if device is not None else (samples.device if torch.is_tensor(samples) and samples.is_cuda else torch.device("cuda:0"))
+
+    def f64(a):
+        return None if a is None else torch.as_tensor(a).to(device=dev, dtype=torch.float64).contiguous()
+
+    hits_t = torch.as_tensor(hits).to(dev).bool().reshape(-1)
+    smp, nrm, p1, p2, cm = f64(samples), f64(normals), f64(pc1), f64(pc2), f64(color_map)
+    rows = torch.nonzero(hits_t).reshape(-1).contiguous()
+    H = int(rows.numel())
+    if nrm.shape[0] != H:
+        raise ValueError(f"shading: {H} hits but {nrm.shape[0]} normals")
+    colors = torch.ones_like(smp)
+    light = (ctypes.c_double * 3)(*[float(v) for v in np.asarray(light_position, dtype=np.float64).reshape(3)])
+    cam = None if camera_position is None else (ctypes.c_double * 3)(*[float(v) for v in np.asarray(camera_position, dtype=np.float64).reshape(3)])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dudf_shade_hits(rows.data_ptr(), H, smp.data_ptr(), nrm.data_ptr(), _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(cm), light, cam,
+                                              method, float(shininess), float(alpha1), float(alpha2), colors.data_ptr(), _lib.current_stream()),
+                   "dudf_shade_hits")
+    return colors
+
+
+def phong_shading(light_position, shininess, hits, samples, normals, color_map=None):
+    """src/render_st.py:174-205 with the same arguments (numpy arrays or tensors); returns the (R,3) float64 colours as numpy."""
+    return _shade(0, light_position, None, hits, samples, normals, shininess=shininess, color_map=color_map).cpu().numpy()
+
+
+def ward_reflectance(light_position, camera_position, hits, samples, normals, alpha1, alpha2, pc1, pc2, color_map=None):
+    """src/render_st.py:207-245 with the same arguments; returns the (R,3) float64 colours as numpy."""
+    return _shade(1, light_position, camera_position, hits, samples, normals, alpha1=alpha1, alpha2=alpha2, pc1=pc1, pc2=pc2,
+                  color_map=color_map).cpu().numpy()
+
+
+# the 11 ColorBrewer RdYlBu anchors matplotlib's 'RdYlBu' map interpolates linearly (used only when matplotlib is not installed;
+# matplotlib itself is not part of the reference tree: parity of this fallback is unpinned)
+_RDYLBU = np.array([[165, 0, 38], [215, 48, 39], [244, 109, 67], [253, 174, 97], [254, 224, 144], [255, 255, 191], [224, 243, 248],
+                    [171, 217, 233], [116, 173, 209], [69, 117, 180], [49, 54, 149]], dtype=np.float64) / 255.0
+
+
+def _rdylbu(x):
+    try:
+        from matplotlib import cm
+        return cm.get_cmap("RdYlBu")(x)[:, :3]
+    except Exception:
+        lut_x = np.linspace(0.0, 1.0, 256)
+        lut = np.stack([np.interp(lut_x, np.linspace(0.0, 1.0, 11), _RDYLBU[:, c]) for c in range(3)], 1)
+        idx = np.clip((np.asarray(x, dtype=np.float64) * 256).astype(np.int64), 0, 255)
+        idx[np.asarray(x) == 1.0] = 255
+        return lut[idx]
+
+
+def create_projectional_image(model, rays, t0, mask_rays, network_config, rendering_config, device):
+    """src/render_st.py:67-134 with the same arguments and in-place effects on t0 / mask_rays; returns the (height, width, 3)
+    float64 image.  Marching, the gradient-descent refinement, the hit attributes (eigen-normals, principal directions, curvature)
+    and the shading all run on the device; the percentile clip of the curvature colour map (a global statistic over the hits) and
+    the colour-map lookup are the reference's numpy expressions on the (H,) curvature vector."""
+    dev = torch.device(device)
+    hits = propagate_rays(model, rays, t0, mask_rays, network_config, rendering_config, device)
+    grad_descent(model, t0, hits, network_config, rendering_config, device)
+    pts = torch.from_numpy(np.ascontiguousarray(t0[hits], dtype=np.float64)).to(dev)
+    shape = (rendering_config["height"], rendering_config["width"], 3)
+    if network_config["gt_mode"] == "siren":
+        eng = model._engine_synced()
+        _, g, _, _ = eng.query(pts.to(torch.float32).contiguous(), 1, model.precision)
+        normals = (g / torch.linalg.norm(g, dim=1, keepdim=True)).to(torch.float64)
+        return phong_shading(rendering_config["light_position"], rendering_config["shininess"], hits, t0, normals).reshape(shape)
+    kind = rendering_config["plot_curvatures"] if rendering_config["plot_curvatures"] in ("mean", "gaussian") else None
+    att = hit_attributes(model, pts, torch.from_numpy(np.ascontiguousarray(rays[hits])).to(dev), curvature=kind)
+    normals = att["normals"].to(torch.float64)
+    colours = None
+    if kind is not None:
+        curv = (att["mean"] if kind == "mean" else att["gauss"]).to(torch.float64).cpu().numpy()[:, None]
+        curv = np.clip(curv, np.percentile(curv, rendering_config["curv_low_bound"]), np.percentile(curv, rendering_config["curv_high_bound"]))
+        curv -= np.min(curv)
+        curv /= np.max(curv)
+        colours = _rdylbu(curv.squeeze(1))
+    if rendering_config["reflection_method"] == "blinn-phong":
+        return phong_shading(rendering_config["light_position"], rendering_config["shininess"], hits, t0, normals, color_map=colours).reshape(shape)
+    if rendering_config["reflection_method"] == "ward":
+        dirs = att["dirs"].to(torch.float64)
+        return ward_reflectance(rendering_config["light_position"], rendering_config["camera_position"], hits, t0, normals,
+                                alpha1=rendering_config["alpha1"], alpha2=rendering_config["alpha2"], pc1=dirs[..., 0].contiguous(),
+                                pc2=dirs[..., 1].contiguous(), color_map=colours).reshape(shape)
+    raise KeyError(rendering_config["reflection_method"])

@@ -110,6 +110,15 @@ int dudf_march_rays(dudf_ctx* ctx, double* pos, const double* dir, unsigned char
 int dudf_project_points(dudf_ctx* ctx, double* x, int64_t P, int num_steps, int gt_mode, float alpha, double* steps, float* g,
                         float* H, int precision, void* stream);
 
+/* Shading of the hit points: phong_shading (method 0) / ward_reflectance (method 1) of src/render_st.py:174-245, in float64 like
+ * the reference's numpy arrays.  rows: [H] indices of the rays that hit, ascending (np.nonzero(hits)); samples: [R][3] ray
+ * positions; normals: [H][3]; pc1, pc2: [H][3] principal directions (Ward only, else NULL); color_map: [H][3] or NULL (grey);
+ * light_host / camera_host: 3 HOST doubles (camera: Ward only); colors: [R][3], only the rows of `rows` are written (the caller fills
+ * the array with ones first, like np.ones_like(samples)). */
+int dudf_shade_hits(const long long* rows, int64_t H, const double* samples, const double* normals, const double* pc1, const double* pc2,
+                    const double* color_map, const double* light_host, const double* camera_host, int method, double shininess,
+                    double alpha1, double alpha2, double* colors, void* stream);
+
 /* CAP-UDF marching cubes: extract_mesh_CAP(ndf, grad, resolution) of src/render_mc.py:201-256 on the device, fed by the
  * outputs of dudf_query_grid.  df: [N][N][N] distances, vecs: [N][N][N][3] (negated, normalised) gradients.  A cell whose smallest
  * corner distance exceeds `threshold` (0.008 in the reference) is skipped; corner c is negative when
