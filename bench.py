@@ -275,6 +275,21 @@ def aux_full_size_queries(dev):
     out["sphere_trace_1024_rays_per_s"] = R * R / sec
     out["sphere_trace_1024_value_queries_per_s"] = nq / sec
     out["sphere_trace_1024_hit_fraction"] = float(hits.float().mean())
+    # the whole frame of BASELINE configs[3] through the reference's call (generate_st.py:127): numpy rays in, marching, hit
+    # attributes with the third-order jet (mean curvature), percentile colour map, Blinn-Phong shading, (1024, 1024, 3) image out
+    cfg = {"surface_threshold": 0.004, "max_iterations": 100, "gd_steps": 0, "height": R, "width": R, "light_position": [1, 2.38206, 10],
+           "camera_position": cam.tolist(), "shininess": -1, "plot_curvatures": "mean", "curv_low_bound": 5, "curv_high_bound": 95,
+           "reflection_method": "blinn-phong", "alpha1": 0.2, "alpha2": 0.2}
+    net_cfg = {"gt_mode": "tanh", "alpha": ALPHA}
+    for rep in range(2):
+        t0_np, mask_np = start.copy(), np.ones(R * R, dtype=bool)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        img = render_st.create_projectional_image(m, rays, t0_np, mask_np, net_cfg, cfg, dev)
+        sec = time.perf_counter() - t0
+    out["st_image_1024_mean_curvature_s"] = sec
+    out["st_image_1024_mean_curvature_rays_per_s"] = R * R / sec
+    out["st_image_1024_hit_pixels"] = int((img.reshape(-1, 3) != 1.0).any(axis=1).sum())
     return out
 
 
