@@ -35,24 +35,29 @@ __device__ __forceinline__ void sine_jet(const float* z, float* a, float w, floa
 #pragma unroll
     for (int i = 0; i < 3; ++i) a[1 + i] = wc * z[1 + i];
     if constexpr (NCH >= 10) {
+      // written out channel by channel (xx,xy,xz,yy,yz,zz = 4..9; xxx,xxy,xxz,xyy,xyz,xzz,yyy,yyz,yzz,zzz = 10..19): loops over
+      // symmetric index tuples keep the accumulator tile in local memory (nvcc 12.9 does not scalarise them: 400-byte stack frame)
       const float w2s = w * w * s;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = i; j < 3; ++j)
-          a[4 + sym2(i, j)] = wc * z[4 + sym2(i, j)] - w2s * z[1 + i] * z[1 + j];
+      const float zx = z[1], zy = z[2], zz = z[3];
+      a[4] = wc * z[4] - w2s * zx * zx;
+      a[5] = wc * z[5] - w2s * zx * zy;
+      a[6] = wc * z[6] - w2s * zx * zz;
+      a[7] = wc * z[7] - w2s * zy * zy;
+      a[8] = wc * z[8] - w2s * zy * zz;
+      a[9] = wc * z[9] - w2s * zz * zz;
       if constexpr (NCH >= 20) {
         const float w3c = w * w * w * c;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = i; j < 3; ++j)
-#pragma unroll
-            for (int k = j; k < 3; ++k)
-              a[10 + sym3(i, j, k)] =
-                  wc * z[10 + sym3(i, j, k)] -
-                  w2s * (z[4 + sym2(i, j)] * z[1 + k] + z[4 + sym2(i, k)] * z[1 + j] + z[4 + sym2(j, k)] * z[1 + i]) -
-                  w3c * z[1 + i] * z[1 + j] * z[1 + k];
+        const float xx = z[4], xy = z[5], xz = z[6], yy = z[7], yz = z[8], z2 = z[9];
+        a[10] = wc * z[10] - w2s * (xx * zx + xx * zx + xx * zx) - w3c * zx * zx * zx;
+        a[11] = wc * z[11] - w2s * (xx * zy + xy * zx + xy * zx) - w3c * zx * zx * zy;
+        a[12] = wc * z[12] - w2s * (xx * zz + xz * zx + xz * zx) - w3c * zx * zx * zz;
+        a[13] = wc * z[13] - w2s * (xy * zy + xy * zy + yy * zx) - w3c * zx * zy * zy;
+        a[14] = wc * z[14] - w2s * (xy * zz + xz * zy + yz * zx) - w3c * zx * zy * zz;
+        a[15] = wc * z[15] - w2s * (xz * zz + xz * zz + z2 * zx) - w3c * zx * zz * zz;
+        a[16] = wc * z[16] - w2s * (yy * zy + yy * zy + yy * zy) - w3c * zy * zy * zy;
+        a[17] = wc * z[17] - w2s * (yy * zz + yz * zy + yz * zy) - w3c * zy * zy * zz;
+        a[18] = wc * z[18] - w2s * (yz * zz + yz * zz + z2 * zy) - w3c * zy * zz * zz;
+        a[19] = wc * z[19] - w2s * (z2 * zz + z2 * zz + z2 * zz) - w3c * zz * zz * zz;
       }
     }
   }
