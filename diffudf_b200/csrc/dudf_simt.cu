@@ -78,22 +78,17 @@ __device__ __forceinline__ void sine_jet_adjoint(const float* z, const float* ab
     }
     z0 -= w2s * acc1;
     if constexpr (NCH >= 10) {
+      // channel by channel (xx,xy,xz,yy,yz,zz = 4..9), same operation order as the index loops this replaces (they kept the tile in
+      // local memory, see sine_jet)
       const float w3c = w * w * w * c;
+      const float zx = z[1], zy = z[2], zz = z[3];
       float acc2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = i; j < 3; ++j) {
-          const int q = 4 + sym2(i, j);
-          acc2 += ab[q] * (w2s * z[q] + w3c * z[1 + i] * z[1 + j]);
-          zb[q] = wc * ab[q];
-          if (i == j) {
-            zb[1 + i] -= 2.f * w2s * ab[q] * z[1 + i];
-          } else {
-            zb[1 + i] -= w2s * ab[q] * z[1 + j];
-            zb[1 + j] -= w2s * ab[q] * z[1 + i];
-          }
-        }
+      acc2 += ab[4] * (w2s * z[4] + w3c * zx * zx);  zb[4] = wc * ab[4];  zb[1] -= 2.f * w2s * ab[4] * zx;
+      acc2 += ab[5] * (w2s * z[5] + w3c * zx * zy);  zb[5] = wc * ab[5];  zb[1] -= w2s * ab[5] * zy;  zb[2] -= w2s * ab[5] * zx;
+      acc2 += ab[6] * (w2s * z[6] + w3c * zx * zz);  zb[6] = wc * ab[6];  zb[1] -= w2s * ab[6] * zz;  zb[3] -= w2s * ab[6] * zx;
+      acc2 += ab[7] * (w2s * z[7] + w3c * zy * zy);  zb[7] = wc * ab[7];  zb[2] -= 2.f * w2s * ab[7] * zy;
+      acc2 += ab[8] * (w2s * z[8] + w3c * zy * zz);  zb[8] = wc * ab[8];  zb[2] -= w2s * ab[8] * zz;  zb[3] -= w2s * ab[8] * zy;
+      acc2 += ab[9] * (w2s * z[9] + w3c * zz * zz);  zb[9] = wc * ab[9];  zb[3] -= 2.f * w2s * ab[9] * zz;
       z0 -= acc2;
     }
   }
