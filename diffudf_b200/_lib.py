@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
-SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
+SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_tcx.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
 HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh", "dudf_mc_table.h",
            os.path.join(ROOT, "include", "dudf_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -68,7 +68,7 @@ SIGNATURES = {
     "dudf_eig_normals": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     "dudf_curvature": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "dudf_field_vectors": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
-    "dudf_evaluate_host": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int],
+    "dudf_evaluate_host": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "dudf_stash_columns": [c_int, c_int64, c_int],
     "dudf_jet_forward": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p],
     "dudf_jet_backward": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

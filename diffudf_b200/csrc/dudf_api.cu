@@ -58,6 +58,7 @@ struct dudf_ctx {
   const float* Wp[DUDF_MAX_LAYERS] = {};   // weights in use: the owned copies (dudf_set_weights) or borrowed (dudf_bind_weights)
   const float* bp[DUDF_MAX_LAYERS] = {};
   void* tc_packed = nullptr;
+  void* tcx_packed = nullptr;
   dudf::DevBuf ws_out, ws_x64, ws_drv, ws_cap;
   int cap_N = 0;                 // grid size of the classification held in ws_cap (0: none)
   const float* cap_df = nullptr;
@@ -105,6 +106,7 @@ int dudf_create(int n_hidden, float w0, float ww, dudf_ctx** out) {
     if (i > 0 && i < c->n_lin - 1) DUDF_CUDA_OK(cudaMalloc(&c->Wtd[i], 256 * 256 * sizeof(float)));
   }
   DUDF_CUDA_OK(cudaMalloc(&c->tc_packed, tc_packed_bytes(c->n_lin)));
+  DUDF_CUDA_OK(cudaMalloc(&c->tcx_packed, tcx_packed_bytes(c->n_lin)));
   *out = c;
   return 0;
 }
@@ -117,6 +119,7 @@ int dudf_destroy(dudf_ctx* c) {
     if (c->Wtd[i]) cudaFree(c->Wtd[i]);
   }
   cudaFree(c->tc_packed);
+  cudaFree(c->tcx_packed);
   c->ws_out.release();
   c->ws_x64.release();
   delete c;
@@ -135,6 +138,10 @@ int dudf_refresh_weights(dudf_ctx* c, int what, void* stream) {
   }
   if (what & DUDF_REFRESH_TC16) {
     int rc = tc_pack(c->view(), c->tc_packed, st);
+    if (rc) return rc;
+  }
+  if (what & DUDF_REFRESH_TCX3) {
+    int rc = tcx_pack(c->view(), c->tcx_packed, st);
     if (rc) return rc;
   }
   c->weights_set = true;
@@ -162,7 +169,7 @@ int dudf_set_weights(dudf_ctx* c, const float* const* W, const float* const* b, 
     c->Wp[i] = c->Wd[i];
     c->bp[i] = c->bd[i];
   }
-  return dudf_refresh_weights(c, DUDF_REFRESH_FP32 | DUDF_REFRESH_TC16, stream);
+  return dudf_refresh_weights(c, DUDF_REFRESH_FP32 | DUDF_REFRESH_TC16 | DUDF_REFRESH_TCX3, stream);
 }
 
 static int order_to_nch(int order) { return order == 0 ? 1 : order == 1 ? 4 : order == 2 ? 10 : order == 3 ? 20 : -1; }
@@ -172,6 +179,10 @@ static int run_forward(dudf_ctx* c, int nch, const float* x, int64_t P, int grid
   if (precision == DUDF_PRECISION_TC16) {
     DUDF_REQUIRE(nch != 20, "third-order jets are only available with DUDF_PRECISION_FP32");
     return tc_forward(c->tc_packed, c->view(), nch, x, P, gridN, first, out, c->sms, st);
+  }
+  if (precision == DUDF_PRECISION_TCX3) {
+    DUDF_REQUIRE(nch != 20, "third-order jets are only available with DUDF_PRECISION_FP32");
+    return tcx_forward(c->tcx_packed, c->view(), nch, x, P, gridN, first, out, c->sms, st);
   }
   DUDF_REQUIRE(precision == DUDF_PRECISION_FP32, "unknown precision %d", precision);
   return simt_forward(c->view(), nch, x, P, gridN, first, out, nullptr, nullptr, 0, 0, c->sms, st);
@@ -333,7 +344,7 @@ int dudf_cap_mesh(dudf_ctx* c, const float* df, const float* vecs, int N, float 
 }
 
 int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
-                       double* H_host, int64_t max_batch, int precision) {
+                       double* H_host, int64_t max_batch, int precision, void* stream) {
   DUDF_REQUIRE(c && c->weights_set, "dudf_evaluate_host: weights not set");
   DUDF_REQUIRE(order >= 0 && order <= 2, "dudf_evaluate_host: order %d", order);
   if (N <= 0) return 0;
@@ -350,7 +361,7 @@ int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, d
   double* g64 = f64 + B;
   double* H64 = g64 + 3 * B;
   const int nch = order_to_nch(order);
-  cudaStream_t st = 0;
+  cudaStream_t st = (cudaStream_t)stream;      // the caller's stream: ordered behind its weight refresh / parameter updates
   for (int64_t head = 0; head < N; head += B) {
     const int64_t n = (N - head < B) ? N - head : B;
     DUDF_CUDA_OK(cudaMemcpyAsync(xd, x_host + head * 3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -382,7 +393,7 @@ int dudf_evaluate_host(dudf_ctx* c, const float* x_host, int64_t N, int order, d
 int64_t dudf_stash_columns(int order, int64_t P, int precision) {
   const int nch = order_to_nch(order);
   if (nch < 0 || nch > 10 || P < 0) return -1;
-  if (precision == DUDF_PRECISION_TC16) {
+  if (precision == DUDF_PRECISION_TC16 || precision == DUDF_PRECISION_TCX3) {
     const int pp = tc_train_pair_points(nch), pc = tc_train_pair_cols(nch);
     return (P + pp - 1) / pp * pc;
   }
@@ -403,7 +414,7 @@ static int fill_grad_view(dudf_ctx* c, float* const* gW, float* const* gb, GradV
 // validates a segment list and, for the tensor-core path, that the segments occupy consecutive stash columns
 static int check_segments(const dudf_segment* segs, int nseg, int64_t ld, int precision, bool forward, const char* who) {
   DUDF_REQUIRE(segs && nseg >= 1 && nseg <= 2, "%s: 1 or 2 segments", who);
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "%s: unknown precision %d", who, precision);
+  DUDF_REQUIRE(precision >= DUDF_PRECISION_FP32 && precision <= DUDF_PRECISION_TCX3, "%s: unknown precision %d", who, precision);
   int64_t next = -1;
   for (int i = 0; i < nseg; ++i) {
     const dudf_segment& s = segs[i];
@@ -411,7 +422,7 @@ static int check_segments(const dudf_segment* segs, int nseg, int64_t ld, int pr
     DUDF_REQUIRE(s.rows > 0 && s.x && (forward ? (s.packed != nullptr) : (s.seeds != nullptr)), "%s: empty or null segment", who);
     const int64_t cols = dudf_stash_columns(s.order, s.rows, precision);
     DUDF_REQUIRE(s.col0 % 4 == 0 && s.col0 + cols <= ld, "%s: stash too small", who);
-    if (precision == DUDF_PRECISION_TC16 && i > 0)
+    if (precision != DUDF_PRECISION_FP32 && i > 0)
       DUDF_REQUIRE(s.col0 == next && segs[0].order == 2, "%s: tensor-core segments must be contiguous, Hessian segment first", who);
     next = s.col0 + cols;
   }
@@ -424,9 +435,10 @@ int dudf_jet_forward_multi(dudf_ctx* c, const dudf_segment* segs, int nseg, void
   int rc = check_segments(segs, nseg, ld, precision, true, "dudf_jet_forward");
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == DUDF_PRECISION_TC16) {
+  if (precision != DUDF_PRECISION_FP32) {
     TcSegment ts[2];
     for (int i = 0; i < nseg; ++i) ts[i] = TcSegment{segs[i].x, segs[i].rows, order_to_nch(segs[i].order), segs[i].packed, nullptr};
+    if (precision == DUDF_PRECISION_TCX3) return tcx_train_forward(c->tcx_packed, c->view(), ts, nseg, (float*)Z, A, ld, segs[0].col0, c->sms, st);
     return tc_train_forward(c->tc_packed, c->view(), ts, nseg, (float*)Z, A, ld, segs[0].col0, c->sms, st);
   }
   for (int i = 0; i < nseg; ++i) {
@@ -447,7 +459,7 @@ int dudf_jet_backward_multi(dudf_ctx* c, const dudf_segment* segs, int nseg, con
   rc = fill_grad_view(c, gW, gb, gv, "dudf_jet_backward");
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == DUDF_PRECISION_TC16) {
+  if (precision != DUDF_PRECISION_FP32) {      // TCX3: split forward, single-pass reverse sweep (tools/precision_study.py)
     TcSegment ts[2];
     for (int i = 0; i < nseg; ++i) ts[i] = TcSegment{segs[i].x, segs[i].rows, order_to_nch(segs[i].order), nullptr, segs[i].seeds};
     return tc_train_backward(c->tc_packed, c->view(), gv, ts, nseg, seed_absmax, (const float*)Z, Zb, ld, segs[0].col0, c->sms, st);
@@ -477,11 +489,11 @@ int dudf_jet_backward(dudf_ctx* c, const float* x, int64_t P, int order, const f
 int dudf_jet_wgrad(dudf_ctx* c, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax, float* const* gW,
                    int precision, void* stream) {
   DUDF_REQUIRE(c && Zb && A && gW, "dudf_jet_wgrad: null argument");
-  DUDF_REQUIRE(precision == DUDF_PRECISION_FP32 || precision == DUDF_PRECISION_TC16, "dudf_jet_wgrad: unknown precision %d", precision);
+  DUDF_REQUIRE(precision >= DUDF_PRECISION_FP32 && precision <= DUDF_PRECISION_TCX3, "dudf_jet_wgrad: unknown precision %d", precision);
   GradView gv;
   int rc = fill_grad_view(c, gW, nullptr, gv, "dudf_jet_wgrad");
   if (rc) return rc;
-  if (precision == DUDF_PRECISION_TC16) return tc_train_wgrad(c->view(), gv, Zb, A, ld, seed_absmax, c->sms, (cudaStream_t)stream);
+  if (precision != DUDF_PRECISION_FP32) return tc_train_wgrad(c->view(), gv, Zb, A, ld, seed_absmax, c->sms, (cudaStream_t)stream);
   return simt_wgrad(c->view(), gv, (const float*)Zb, (const float*)A, ld, ncols, c->sms, (cudaStream_t)stream);
 }
 

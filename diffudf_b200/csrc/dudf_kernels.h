@@ -35,6 +35,11 @@ size_t tc_packed_bytes(int n_lin);
 int tc_pack(const NetView& net, void* packed, cudaStream_t st);
 int tc_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN,
                int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
+// ---- split-precision tcgen05 path (dudf_tcx.cu): hi + lo fp16 operands, fp32-grade results ----
+size_t tcx_packed_bytes(int n_lin);
+int tcx_pack(const NetView& net, void* packed, cudaStream_t st);
+int tcx_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN,
+                int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
 int tc_selftest(int variant, float* max_err, cudaStream_t st);
 void tc_set_trace(unsigned long long* buf);
 unsigned long long* tc_get_trace();
@@ -84,6 +89,8 @@ int tc_train_fused(const void* packed, const NetView& net, const GradView& grad,
                    float* scratch, void* Aimg, void* Zimg, int64_t ld, int sms, cudaStream_t st);
 int tc_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld,
                      int64_t col0, int sms, cudaStream_t st);
+int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld,
+                      int64_t col0, int sms, cudaStream_t st);
 int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg,
                       const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st);
 int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,

@@ -219,303 +219,6 @@ tc_forward_kernel(const unsigned char* __restrict__ packed, NetView net, const f
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-// =============================================================================================
-// 16-epilogue-warp variant: the two sub-tiles of a pair are owned by two independent sets of 8 warps (set s = warps
-// 8s..8s+7, one thread per neuron), so four warps per scheduler hide the TMEM / MUFU / shared-memory latencies of the
-// sine-jet instead of two.  Registers: 640 threads start with 96 each (61 440, the CTA's pool); the auxiliary warpgroup
-// drops to 56 and frees 5 120, the epilogue warps rise to 104 and take 4 096.
-// =============================================================================================
-constexpr int TC16_THREADS = 640;
-constexpr int TC16_REGS_EPI = 104;
-constexpr int TC16_REGS_AUX = 56;
-__device__ __forceinline__ void tc_set_bar(int s) { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); }
-
-template <int NCH, bool RU>
-__global__ void __launch_bounds__(TC16_THREADS, 1)
-tc_forward16_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, int gridN,
-                    int64_t grid_first, QueryOut out) {
-  using C = TcCfg<NCH>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* act = smem;
-  unsigned char* ring = smem + C::OFF_RING;
-  float* wl_s = (float*)(smem + C::OFF_WL);
-  float* xs = (float*)(smem + C::OFF_XS);
-  float* os = (float*)(smem + C::OFF_OS);
-  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = net.n_lin - 1;
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-  if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
-    mbar_fence_init();
-  }
-  if (warp == 17) tmem_alloc<512>(tmem_slot);
-  if (tid < 256) wl_s[tid] = net.W[L][tid];
-  if (C::NV < 128 && tid < 256) {
-    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(act + s * TC_ACT_BYTES, tid) + tc_chunk_off(15, tid & 7)) = make_uint4(0, 0, 0, 0);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 16) {
-    setmaxnreg_dec<TC16_REGS_AUX>();
-    if (warp == 16) {
-      if (lane == 0) tc_producer<1, RU>(packed, ring, full, empty, rounds, L - 1, TC_DIR_FWD, 0u, (int)(out.flags >> 8));
-    } else if (warp == 17) {
-      tc_mma_role<1, RU>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, nullptr, 0, 0, TC_DIR_FWD, out.flags >> 8);
-    }
-  } else {
-    setmaxnreg_inc<TC16_REGS_EPI>();
-    const int s = warp >> 3;                                // this warp set's sub-tile
-    const int ts = tid & 255;
-    const int q = warp & 3, h = (warp >> 2) & 1;
-    const int n = h * 128 + q * 32 + lane;
-    const uint32_t r7 = n & 7;
-    const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + s * 256 + h * 128;
-    const float w0 = net.w0, ww = net.ww;
-    const float r0x = net.W[0][n * 3], r0y = net.W[0][n * 3 + 1], r0z = net.W[0][n * 3 + 2], b0 = net.b[0][n];
-    const float bL = net.b[L][0];
-    const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
-    unsigned char* trow = tc_tile_row(act + s * TC_ACT_BYTES, n);
-    float* xss = xs + s * C::PT * 3;
-    float* oss = os + s * 256;
-    uint32_t acc_phase = 0;
-
-    for (int64_t rd = 0; rd < rounds; ++rd) {
-      const int64_t pair = blockIdx.x + rd * gridDim.x;
-      tc_set_bar(s);
-      for (int i = ts; i < C::PT; i += 256) {
-        const int64_t p = (pair * 2 + s) * C::PT + i;
-        float pt[3] = {0.f, 0.f, 0.f};
-        if (p < P) {
-          if (x) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
-          else grid_point(grid_first + p, gridN, vs, pt);
-        }
-        xss[i * 3] = pt[0]; xss[i * 3 + 1] = pt[1]; xss[i * 3 + 2] = pt[2];
-      }
-      tc_set_bar(s);
-      for (int l = 0; l < L; ++l) {
-        const float bias = (l > 0) ? ww * net.b[l][n] : 0.f;
-        if (l > 0) {
-          mbar_wait(&acc_ready[s], acc_phase, 0x400 + s);
-          acc_phase ^= 1u;
-          tc_fence_after();
-        }
-        if (l == 0) {
-#pragma unroll 1
-          for (int g = 0; g < C::NGRP; ++g) {
-            float u[C::GC];
-            tc_first_layer_group<NCH, C::GC>(u, xss + g * (C::GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
-            tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
-          }
-        } else if (!((out.flags >> 8) & 1)) {
-          TmemRegs<C::GC> nxt;
-          tc_ld_issue<C::GC>(tmem_acc, nxt);
-#pragma unroll 1
-          for (int g = 0; g < C::NGRP; ++g) {
-            float u[C::GC];
-            tc_ld_take<C::GC>(nxt, u);
-            if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(tmem_acc + (g + 1) * C::GC, nxt);
-#pragma unroll
-            for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
-            tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
-          }
-        }
-        if (l < L - 1) {
-          tc_fence_before();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&act_ready[s]);
-        } else {
-          tc_set_bar(s);
-          tc_output_dot<C::NV>(act + s * TC_ACT_BYTES, wl_s, oss, ts);
-          tc_set_bar(s);
-          if (ts < C::NV) {
-            const int ch = ts % NCH;
-            const float v = oss[ts] + oss[128 + ts];
-            oss[ts] = (ch == 0) ? v + bL : (ch >= 4 ? v * TC_KAPPA_INV : v);
-          }
-          tc_set_bar(s);
-          if (ts < C::PT) {
-            const int64_t p = (pair * 2 + s) * C::PT + ts;
-            if (p < P) finalize_point<NCH>(out, p, oss + ts * NCH);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) tmem_dealloc<512>(tmem_base);
-}
-
-template <int NCH, bool RU>
-static int tc_launch16(const void* packed, const NetView& net, const float* x, int64_t P, int gridN, int64_t first, const QueryOut& out,
-                       int sms, cudaStream_t st) {
-  using C = TcCfg<NCH>;
-  auto k = tc_forward16_kernel<NCH, RU>;
-  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int grid = (int)std::min<int64_t>(npairs, sms);
-  if (grid < 1) return 0;
-  k<<<grid, TC16_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, x, P, gridN, first, out);
-  DUDF_LAUNCH_OK();
-  return 0;
-}
-
-// =============================================================================================
-// Skewed variant (DUDF_TC_SKEW=lag): the same 8 epilogue warps serve the two sub-tile streams `lag` layers apart, so that the first
-// layer and the output layer of one sub-tile (which need no MMA) overlap the MMAs of the other instead of leaving the tensor pipe
-// idle at every pair boundary (20 % of the lock-step kernel, tools/pipe_probe.py "full minus first/output layer").  Weights are
-// streamed once per sub-tile (no chunk reuse across sub-tiles: they are at different layers).
-// =============================================================================================
-template <int NCH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_forward_skew_kernel(const unsigned char* __restrict__ packed, NetView net, const float* __restrict__ x, int64_t P, int gridN,
-                       int64_t grid_first, QueryOut out, int lag) {
-  using C = TcCfg<NCH>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* act = smem;
-  unsigned char* ring = smem + C::OFF_RING;
-  float* wl_s = (float*)(smem + C::OFF_WL);
-  float* xs = (float*)(smem + C::OFF_XS);
-  float* os = (float*)(smem + C::OFF_OS);
-  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = net.n_lin - 1;
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
-    mbar_fence_init();
-  }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
-  if (tid < 256) wl_s[tid] = net.W[L][tid];
-  if (C::NV < 128 && tid < 256) {
-    for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(act + s * TC_ACT_BYTES, tid) + tc_chunk_off(15, tid & 7)) = make_uint4(0, 0, 0, 0);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 8) {
-    setmaxnreg_dec<TC_REGS_AUX>();
-    if (warp == 8) {
-      if (lane == 0) tc_producer_fwd_skew(packed, ring, full, empty, rounds, L, lag);
-    } else if (warp == 9) {
-      tc_mma_role_fwd_skew(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L, lag);
-    }
-  } else {
-    setmaxnreg_inc<TC_REGS_EPI>();
-    const int q = warp & 3, h = warp >> 2;
-    const int n = h * 128 + q * 32 + lane;
-    const uint32_t r7 = n & 7;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * 128;
-    const float w0 = net.w0, ww = net.ww;
-    const float r0x = net.W[0][n * 3], r0y = net.W[0][n * 3 + 1], r0z = net.W[0][n * 3 + 2], b0 = net.b[0][n];
-    const float bL = net.b[L][0];
-    const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
-    uint32_t acc_phase = 0;
-    const int64_t total = rounds * L;
-    for (int64_t t = 0; t < total + lag; ++t) {
-#pragma unroll 1
-      for (int s = 0; s < 2; ++s) {
-        const int64_t st = s ? t - lag : t;
-        if (st < 0 || st >= total) continue;                 // uniform over the 8 warps
-        const int64_t rd = st / L;
-        const int l = (int)(st - rd * L);
-        const int64_t pair = blockIdx.x + rd * gridDim.x;
-        unsigned char* trow = tc_tile_row(act + s * TC_ACT_BYTES, n);
-        float* xss = xs + s * 128 * 3;
-        if (l == 0) {
-          tc_epi_bar();
-          for (int i = tid; i < C::PT; i += 256) {
-            const int64_t p = (pair * 2 + s) * C::PT + i;
-            float pt[3] = {0.f, 0.f, 0.f};
-            if (p < P) {
-              if (x) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
-              else grid_point(grid_first + p, gridN, vs, pt);
-            }
-            xss[i * 3] = pt[0]; xss[i * 3 + 1] = pt[1]; xss[i * 3 + 2] = pt[2];
-          }
-          tc_epi_bar();
-#pragma unroll 1
-          for (int g = 0; g < C::NGRP; ++g) {
-            float u[C::GC];
-            tc_first_layer_group<NCH, C::GC>(u, xss + g * (C::GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
-            tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), r7);
-          }
-        } else {
-          const float bias = ww * net.b[l][n];
-          mbar_wait(&acc_ready[s], (acc_phase >> s) & 1u, 0x400 + s);
-          acc_phase ^= 1u << s;
-          tc_fence_after();
-          TmemRegs<C::GC> nxt;
-#pragma unroll 1
-          for (int g = 0; g < C::NGRP; ++g) {
-            float u[C::GC];
-            tc_ld_issue<C::GC>(tmem_lane + s * 256 + g * C::GC, nxt);
-            tc_ld_take<C::GC>(nxt, u);
-#pragma unroll
-            for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
-            tc_emit_group<NCH, C::GC, false>(u, trow, g * (C::GC / 8), r7);
-          }
-        }
-        if (l < L - 1) {
-          tc_fence_before();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&act_ready[s]);
-        } else {
-          tc_epi_bar();
-          tc_output_dot<C::NV>(act + s * TC_ACT_BYTES, wl_s, os + s * 256, tid);
-          tc_epi_bar();
-          if (tid < C::NV) {
-            const int ch = tid % NCH;
-            const float v = os[s * 256 + tid] + os[s * 256 + 128 + tid];
-            os[s * 256 + tid] = (ch == 0) ? v + bL : (ch >= 4 ? v * TC_KAPPA_INV : v);
-          }
-          tc_epi_bar();
-          if (tid < C::PT) {
-            const int64_t p = (pair * 2 + s) * C::PT + tid;
-            if (p < P) finalize_point<NCH>(out, p, os + s * 256 + tid * NCH);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
-}
-
-template <int NCH>
-static int tc_launch_skew(const void* packed, const NetView& net, const float* x, int64_t P, int gridN, int64_t first, const QueryOut& out,
-                          int sms, int lag, cudaStream_t st) {
-  using C = TcCfg<NCH>;
-  auto k = tc_forward_skew_kernel<NCH>;
-  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  const int grid = (int)std::min<int64_t>(npairs, sms);
-  if (grid < 1) return 0;
-  k<<<grid, TC_THREADS, C::SMEM, st>>>((const unsigned char*)packed, net, x, P, gridN, first, out, lag);
-  DUDF_LAUNCH_OK();
-  return 0;
-}
-
 static unsigned long long* g_tc_trace = nullptr;
 void tc_set_trace(unsigned long long* buf) { g_tc_trace = buf; }
 unsigned long long* tc_get_trace() { return g_tc_trace; }
@@ -565,11 +268,6 @@ static int tc_launch_cl(const void* packed, const NetView& net, const float* x, 
                         int sms, cudaStream_t st) {
   using C = TcCfg<NCH>;
   const int64_t npairs = (P + 2 * C::PT - 1) / (2 * C::PT);
-  static const int skew = getenv("DUDF_TC_SKEW") ? atoi(getenv("DUDF_TC_SKEW")) : 0;         // lag of sub-tile stream 1 in layers
-  if (skew > 0 && skew < net.n_lin - 1) return tc_launch_skew<NCH>(packed, net, x, P, gridN, first, out, sms, skew, st);
-  static const int w16 = getenv("DUDF_TC_WARPS16") ? atoi(getenv("DUDF_TC_WARPS16")) : 0;   // 1: ping-pong order, 2: chunk-reuse order
-  if (w16 == 1) return tc_launch16<NCH, false>(packed, net, x, P, gridN, first, out, sms, st);
-  if (w16 == 2) return tc_launch16<NCH, true>(packed, net, x, P, gridN, first, out, sms, st);
   int cl = tc_cluster_size();
   while (cl > 1 && npairs < 2 * cl) cl >>= 1;              // tiny queries: no point in pairing CTAs
   static const bool no_reuse = getenv("DUDF_TC_REUSE") && atoi(getenv("DUDF_TC_REUSE")) == 0;   // ping-pong order instead of chunk reuse

@@ -237,136 +237,6 @@ __device__ __forceinline__ void tc_mma_role(unsigned char* act, unsigned char* r
   }
 }
 
-// ---- skewed schedule (16-warp fused training step): the two sub-tile streams of a CTA run `skew` phases apart, so that one
-// ---- warp set is in its forward sweep (store-heavy: scratch + operand images) while the other is in its reverse sweep
-// ---- (math-heavy).  Slot t serves phase t of stream 0 and phase t - skew of stream 1; a phase index counts the 2 * n_phase
-// ---- phases of every pair of the CTA in order.  Producer and MMA issuer walk the same slot sequence.
-__device__ __forceinline__ void tc_producer_skew(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t rounds,
-                                                 int n_phase, int skew, int dbg = 0) {
-  using namespace umma;
-  uint32_t stage = 0, phase = 0, chunk = 0;
-  const int64_t total = rounds * 2 * n_phase;
-  for (int64_t t = 0; t < total + skew; ++t)
-    for (int s = 0; s < 2; ++s) {
-      const int64_t tt = s ? t - skew : t;
-      if (tt < 0 || tt >= total) continue;
-      const int jt = (int)(tt % (2 * n_phase));
-      const bool backward = jt >= n_phase;
-      const int j = backward ? jt - n_phase : jt;
-      const int idx = backward ? (n_phase + (n_phase - 1 - j)) : j;
-      const unsigned char* src = packed + (size_t)idx * 8 * TC_CHUNK_BYTES;
-      for (int ck = 0; ck < 8; ++ck, ++chunk) {
-        mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x100 + stage);
-        if ((dbg & 4) && chunk >= (uint32_t)TC_STAGES) {
-          mbar_arrive(&full[stage]);
-        } else {
-          mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
-          bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
-        }
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-}
-
-__device__ __forceinline__ void tc_mma_role_skew(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
-                                                 uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, int skew,
-                                                 unsigned char* img_f, unsigned char* img_b, int64_t ncb, int dbg, uint64_t img_policy,
-                                                 unsigned long long* trace) {
-  using namespace umma;
-  uint32_t tn = 0;
-  constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
-  const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
-  const uint64_t b_desc0 = make_desc_sw128(smem_u32(act), 32768, 1024);
-  const bool skip = (dbg & 2) != 0;
-  uint32_t stage = 0, phase = 0, act_phase = 0;
-  const int64_t total = rounds * 2 * n_phase;
-  for (int64_t t = 0; t < total + skew; ++t)
-    for (int s = 0; s < 2; ++s) {
-      const int64_t tt = s ? t - skew : t;
-      if (tt < 0 || tt >= total) continue;
-      const int64_t r = tt / (2 * n_phase);
-      const int jt = (int)(tt - r * 2 * n_phase);
-      const int64_t pair = blockIdx.x + r * gridDim.x;
-      const bool backward = jt >= n_phase;
-      const int j = backward ? jt - n_phase : jt;
-      const int layer = backward ? (n_phase - j) : j;
-      unsigned char* img = (dbg & 16) ? nullptr : (backward ? img_b : img_f);
-      mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
-      act_phase ^= 1u << s;
-      tc_fence_after();
-      tc_trace(trace, tn, 1, s);
-      tc_copy_subtile(act, s, img, ncb, 0, pair, layer, img_policy);
-      const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&full[stage], phase, 0x300 + stage);
-          if (!skip)
-            mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(b_desc, kb * 8 * 1024), idesc, kb != 0);
-          mma_commit_warp(&empty[stage]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-      tc_trace(trace, tn, 2, 2 + s);
-      tc_finish_subtile(acc_ready, s, img != nullptr);
-    }
-}
-
-// ---- forward-only skewed schedule (query kernel, DUDF_TC_SKEW): stream s (sub-tile s of every pair) walks the steps
-// ---- (pair, layer 0 .. n_layer-1); stream 1 runs `lag` steps behind stream 0, so that the layers of one sub-tile that need no MMA
-// ---- (first layer, output layer) fall into the MMA phases of the other.  Step l < n_layer - 1 of a stream is followed by the
-// ---- MMA phase of layer l; slot t serves step t of stream 0 and step t - lag of stream 1.
-__device__ __forceinline__ void tc_producer_fwd_skew(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty,
-                                                     int64_t rounds, int n_layer, int lag) {
-  using namespace umma;
-  uint32_t stage = 0, phase = 0;
-  const int64_t total = rounds * n_layer;
-  for (int64_t t = 0; t < total + lag; ++t)
-    for (int s = 0; s < 2; ++s) {
-      const int64_t st = s ? t - lag : t;
-      if (st < 0 || st >= total) continue;
-      const int l = (int)(st % n_layer);
-      if (l == n_layer - 1) continue;
-      const unsigned char* src = packed + (size_t)l * 8 * TC_CHUNK_BYTES;
-      for (int ck = 0; ck < 8; ++ck) {
-        mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x100 + stage);
-        mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
-        bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-}
-
-__device__ __forceinline__ void tc_mma_role_fwd_skew(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
-                                                     uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_layer, int lag) {
-  using namespace umma;
-  constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
-  const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
-  const uint64_t b_desc0 = make_desc_sw128(smem_u32(act), 32768, 1024);
-  uint32_t stage = 0, phase = 0, act_phase = 0;
-  const int64_t total = rounds * n_layer;
-  for (int64_t t = 0; t < total + lag; ++t)
-    for (int s = 0; s < 2; ++s) {
-      const int64_t st = s ? t - lag : t;
-      if (st < 0 || st >= total) continue;
-      if ((int)(st % n_layer) == n_layer - 1) continue;
-      mbar_wait(&act_ready[s], (act_phase >> s) & 1u, 0x200 + s);
-      act_phase ^= 1u << s;
-      tc_fence_after();
-      const uint64_t b_desc = desc_advance(b_desc0, s * TC_ACT_BYTES);
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&full[stage], phase, 0x300 + stage);
-          mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(b_desc, kb * 8 * 1024), idesc, kb != 0);
-          mma_commit_warp(&empty[stage]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-      mma_commit_warp(&acc_ready[s]);
-    }
-}
-
 template <int GC>
 __device__ __forceinline__ void tc_load_group(uint32_t taddr, float* u) {
   uint32_t r[32];
@@ -520,5 +390,97 @@ __device__ __forceinline__ void tc_output_dot(const unsigned char* tile, const f
     os[half * 128 + j] = sum;
   }
 }
+
+// ---- thread-major stash of one column group: chunk j of the group lives at dst + j*1024 floats (+ 4*neuron) -------
+// value channels (u0) in fp32 first, then the derivative channels packed as halves (in column order)
+template <int NCH, int GC>
+struct Stash {
+  static constexpr int NP = GC / NCH;                      // points per group
+  static constexpr int NF4 = NP / 4;                       // float4 chunks of u0
+  static constexpr int ND = GC - NP;                       // derivative values
+  static constexpr int NH8 = (ND + 7) / 8;                 // uint4 chunks of halves
+  static constexpr int CHUNKS = (NCH == 1) ? GC / 4 : NF4 + NH8;
+};
+
+template <int NCH, int GC>
+__device__ __forceinline__ void tt_stash_group(const float* u, float* dst) {
+  using S = Stash<NCH, GC>;
+  if constexpr (NCH == 1) {
+#pragma unroll
+    for (int j4 = 0; j4 < GC / 4; ++j4)
+      *reinterpret_cast<float4*>(dst + j4 * 1024) = make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
+  } else {
+#pragma unroll
+    for (int j4 = 0; j4 < S::NF4; ++j4)
+      *reinterpret_cast<float4*>(dst + j4 * 1024) =
+          make_float4(u[(j4 * 4) * NCH], u[(j4 * 4 + 1) * NCH], u[(j4 * 4 + 2) * NCH], u[(j4 * 4 + 3) * NCH]);
+    float d[S::NH8 * 8];
+#pragma unroll
+    for (int pp = 0; pp < S::NP; ++pp)
+#pragma unroll
+      for (int ch = 1; ch < NCH; ++ch) d[pp * (NCH - 1) + ch - 1] = u[pp * NCH + ch];
+#pragma unroll
+    for (int j = S::ND; j < S::NH8 * 8; ++j) d[j] = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < S::NH8; ++c8)
+      *reinterpret_cast<uint4*>(dst + (S::NF4 + c8) * 1024) =
+          make_uint4(tc_pack_h2(d[8 * c8], d[8 * c8 + 1]), tc_pack_h2(d[8 * c8 + 2], d[8 * c8 + 3]),
+                     tc_pack_h2(d[8 * c8 + 4], d[8 * c8 + 5]), tc_pack_h2(d[8 * c8 + 6], d[8 * c8 + 7]));
+  }
+}
+
+// the reverse sweep issues the loads of the NEXT group before it works on the current one (raw 16-byte registers)
+template <int NCH, int GC>
+__device__ __forceinline__ void tt_stash_load(uint4* raw, const float* src) {
+#pragma unroll
+  for (int j = 0; j < Stash<NCH, GC>::CHUNKS; ++j) raw[j] = __ldcs(reinterpret_cast<const uint4*>(src + j * 1024));
+}
+
+template <int NCH, int GC>
+__device__ __forceinline__ void tt_unstash_group(float* u, const uint4* raw) {
+  using S = Stash<NCH, GC>;
+  if constexpr (NCH == 1) {
+#pragma unroll
+    for (int j4 = 0; j4 < GC / 4; ++j4) {
+      const uint4 t = raw[j4];
+      u[j4 * 4] = __uint_as_float(t.x); u[j4 * 4 + 1] = __uint_as_float(t.y);
+      u[j4 * 4 + 2] = __uint_as_float(t.z); u[j4 * 4 + 3] = __uint_as_float(t.w);
+    }
+  } else {
+#pragma unroll
+    for (int j4 = 0; j4 < S::NF4; ++j4) {
+      const uint4 t = raw[j4];
+      u[(j4 * 4) * NCH] = __uint_as_float(t.x); u[(j4 * 4 + 1) * NCH] = __uint_as_float(t.y);
+      u[(j4 * 4 + 2) * NCH] = __uint_as_float(t.z); u[(j4 * 4 + 3) * NCH] = __uint_as_float(t.w);
+    }
+    float d[S::NH8 * 8];
+#pragma unroll
+    for (int c8 = 0; c8 < S::NH8; ++c8) {
+      const uint4 t = raw[S::NF4 + c8];
+      const __half2* hv = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f2 = __half22float2(hv[e]);
+        d[8 * c8 + 2 * e] = f2.x;
+        d[8 * c8 + 2 * e + 1] = f2.y;
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < S::NP; ++pp)
+#pragma unroll
+      for (int ch = 1; ch < NCH; ++ch) u[pp * NCH + ch] = d[pp * (NCH - 1) + ch - 1];
+  }
+}
+
+// one row segment of a training batch as the kernels see it
+struct SegDev {
+  const float* x;        // [P][3]
+  float* outp;           // forward: [P][NCH] raw channels
+  const float* seeds;    // backward: [P][NCH]
+  const float* normals;  // fused step: [P][3] ground-truth normals
+  const float* dist;     // fused step: [P] ground-truth distances
+  int64_t P;
+  int64_t npairs;
+};
 
 }  // namespace dudf

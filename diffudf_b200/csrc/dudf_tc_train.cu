@@ -44,98 +44,6 @@ __device__ __forceinline__ void tt_store_group_sat(const float* v, unsigned char
               tt_pack_h2_sat(v[8 * c8 + 4], v[8 * c8 + 5]), tt_pack_h2_sat(v[8 * c8 + 6], v[8 * c8 + 7]));
 }
 
-// ---- thread-major stash of one column group: chunk j of the group lives at dst + j*1024 floats (+ 4*neuron) -------
-// value channels (u0) in fp32 first, then the derivative channels packed as halves (in column order)
-template <int NCH, int GC>
-struct Stash {
-  static constexpr int NP = GC / NCH;                      // points per group
-  static constexpr int NF4 = NP / 4;                       // float4 chunks of u0
-  static constexpr int ND = GC - NP;                       // derivative values
-  static constexpr int NH8 = (ND + 7) / 8;                 // uint4 chunks of halves
-  static constexpr int CHUNKS = (NCH == 1) ? GC / 4 : NF4 + NH8;
-};
-
-template <int NCH, int GC>
-__device__ __forceinline__ void tt_stash_group(const float* u, float* dst) {
-  using S = Stash<NCH, GC>;
-  if constexpr (NCH == 1) {
-#pragma unroll
-    for (int j4 = 0; j4 < GC / 4; ++j4)
-      *reinterpret_cast<float4*>(dst + j4 * 1024) = make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
-  } else {
-#pragma unroll
-    for (int j4 = 0; j4 < S::NF4; ++j4)
-      *reinterpret_cast<float4*>(dst + j4 * 1024) =
-          make_float4(u[(j4 * 4) * NCH], u[(j4 * 4 + 1) * NCH], u[(j4 * 4 + 2) * NCH], u[(j4 * 4 + 3) * NCH]);
-    float d[S::NH8 * 8];
-#pragma unroll
-    for (int pp = 0; pp < S::NP; ++pp)
-#pragma unroll
-      for (int ch = 1; ch < NCH; ++ch) d[pp * (NCH - 1) + ch - 1] = u[pp * NCH + ch];
-#pragma unroll
-    for (int j = S::ND; j < S::NH8 * 8; ++j) d[j] = 0.f;
-#pragma unroll
-    for (int c8 = 0; c8 < S::NH8; ++c8)
-      *reinterpret_cast<uint4*>(dst + (S::NF4 + c8) * 1024) =
-          make_uint4(tc_pack_h2(d[8 * c8], d[8 * c8 + 1]), tc_pack_h2(d[8 * c8 + 2], d[8 * c8 + 3]),
-                     tc_pack_h2(d[8 * c8 + 4], d[8 * c8 + 5]), tc_pack_h2(d[8 * c8 + 6], d[8 * c8 + 7]));
-  }
-}
-
-// the reverse sweep issues the loads of the NEXT group before it works on the current one (raw 16-byte registers)
-template <int NCH, int GC>
-__device__ __forceinline__ void tt_stash_load(uint4* raw, const float* src) {
-#pragma unroll
-  for (int j = 0; j < Stash<NCH, GC>::CHUNKS; ++j) raw[j] = __ldcs(reinterpret_cast<const uint4*>(src + j * 1024));
-}
-
-template <int NCH, int GC>
-__device__ __forceinline__ void tt_unstash_group(float* u, const uint4* raw) {
-  using S = Stash<NCH, GC>;
-  if constexpr (NCH == 1) {
-#pragma unroll
-    for (int j4 = 0; j4 < GC / 4; ++j4) {
-      const uint4 t = raw[j4];
-      u[j4 * 4] = __uint_as_float(t.x); u[j4 * 4 + 1] = __uint_as_float(t.y);
-      u[j4 * 4 + 2] = __uint_as_float(t.z); u[j4 * 4 + 3] = __uint_as_float(t.w);
-    }
-  } else {
-#pragma unroll
-    for (int j4 = 0; j4 < S::NF4; ++j4) {
-      const uint4 t = raw[j4];
-      u[(j4 * 4) * NCH] = __uint_as_float(t.x); u[(j4 * 4 + 1) * NCH] = __uint_as_float(t.y);
-      u[(j4 * 4 + 2) * NCH] = __uint_as_float(t.z); u[(j4 * 4 + 3) * NCH] = __uint_as_float(t.w);
-    }
-    float d[S::NH8 * 8];
-#pragma unroll
-    for (int c8 = 0; c8 < S::NH8; ++c8) {
-      const uint4 t = raw[S::NF4 + c8];
-      const __half2* hv = reinterpret_cast<const __half2*>(&t);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f2 = __half22float2(hv[e]);
-        d[8 * c8 + 2 * e] = f2.x;
-        d[8 * c8 + 2 * e + 1] = f2.y;
-      }
-    }
-#pragma unroll
-    for (int pp = 0; pp < S::NP; ++pp)
-#pragma unroll
-      for (int ch = 1; ch < NCH; ++ch) u[pp * NCH + ch] = d[pp * (NCH - 1) + ch - 1];
-  }
-}
-
-// one row segment of a training batch as the kernels see it
-struct SegDev {
-  const float* x;        // [P][3]
-  float* outp;           // forward: [P][NCH] raw channels
-  const float* seeds;    // backward: [P][NCH]
-  const float* normals;  // fused step: [P][3] ground-truth normals
-  const float* dist;     // fused step: [P] ground-truth distances
-  int64_t P;
-  int64_t npairs;
-};
-
 struct EpiCtx {
   unsigned char* act;
   float* xs;
@@ -943,455 +851,6 @@ tt_fused_kernel(const unsigned char* __restrict__ packed, NetView net, GradView 
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-// =============================================================================================
-// 16-epilogue-warp fused step.  The two sub-tiles of a pair are owned by two independent sets of 8 warps (set s = warps
-// 8s .. 8s+7, one thread per neuron): four warps per scheduler instead of two hide the TMEM-load, scratch-load and MUFU
-// latencies that bound the 8-warp kernel (tools/fused_trace.py: a sub-tile epilogue takes 2 700 clk alone and 5 800 next to
-// the other sub-tile's MMAs, against 2 048 clk of tensor work).  The register budget drops to 104 per thread
-// (512 x 104 + 128 x 56), so a step covers 16 columns (4 points x 4 channels) or 20 columns (2 points x 10 channels)
-// instead of 32 / 40; a 20-column step ends in the middle of a 16-byte chunk of the B tile, which the two steps sharing
-// the chunk fill with 8-byte stores.  The sets never synchronise with each other: coordinates, output layer, loss rows
-// and seeds of a sub-tile are handled inside its set (named barriers 1 + s).
-// Scratch of one step, thread-major: 32-bit words [u0 fp32 x NP | derivative channels as packed halves], in 16-byte chunks
-// (chunk j of a step at +j * 1024 floats, 16 bytes per thread; a trailing half chunk is stored as 8 bytes per thread).
-// =============================================================================================
-constexpr int T16_THREADS = 640;
-constexpr int T16_REGS_EPI = 104;
-constexpr int T16_REGS_AUX = 56;
-
-template <int NCH>
-struct Cfg16 {
-  static constexpr int GC = (NCH == 10) ? 20 : 16;      // columns per step
-  static constexpr int NP = GC / NCH;                   // points per step
-  static constexpr int PT = TcCfg<NCH>::PT;
-  static constexpr int NV = TcCfg<NCH>::NV;
-  static constexpr int NSTEP = NV / GC;                 // 8 (jet-4) or 6 (jet-10)
-  static constexpr int NW = NP + (GC - NP) / 2;         // scratch words per step: 10 or 11
-  static constexpr int NFULL = NW / 4;                  // full 16-byte chunks: 2
-  static constexpr int TAIL = NW - 4 * NFULL;           // 2 (8-byte tail) or 3 (stored as a padded 16-byte chunk)
-  static constexpr int NCHUNK = NFULL + (TAIL ? 1 : 0);
-  static constexpr int NWP = (TAIL == 2) ? NW : 4 * NCHUNK;   // words held in registers (padded)
-};
-constexpr int T16_STEP_FLOATS = 3 * 1024;               // scratch floats reserved per step (3 chunk slots)
-constexpr int T16_SUB_FLOATS = 8 * T16_STEP_FLOATS;     // per (layer, set)
-
-__device__ __forceinline__ void t16_bar(int s) { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); }
-
-template <int NCH>
-__device__ __forceinline__ void t16_stash_store(const float* u, float* dst, int n) {
-  using K = Cfg16<NCH>;
-  uint32_t w[K::NWP];
-#pragma unroll
-  for (int p = 0; p < K::NP; ++p) w[p] = __float_as_uint(u[p * NCH]);
-  float d[K::GC - K::NP + 1];
-#pragma unroll
-  for (int p = 0; p < K::NP; ++p)
-#pragma unroll
-    for (int ch = 1; ch < NCH; ++ch) d[p * (NCH - 1) + ch - 1] = u[p * NCH + ch];
-#pragma unroll
-  for (int j = 0; j < (K::GC - K::NP) / 2; ++j) w[K::NP + j] = tc_pack_h2(d[2 * j], d[2 * j + 1]);
-#pragma unroll
-  for (int j = K::NW; j < K::NWP; ++j) w[j] = 0u;
-#pragma unroll
-  for (int c = 0; c < K::NWP / 4; ++c) *reinterpret_cast<uint4*>(dst + c * 1024 + n * 4) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-  if constexpr (K::TAIL == 2) *reinterpret_cast<uint2*>(dst + K::NFULL * 1024 + n * 2) = make_uint2(w[4 * K::NFULL], w[4 * K::NFULL + 1]);
-}
-template <int NCH>
-__device__ __forceinline__ void t16_stash_load(uint32_t* w, const float* src, int n) {
-  using K = Cfg16<NCH>;
-#pragma unroll
-  for (int c = 0; c < K::NWP / 4; ++c) {
-    const uint4 t = __ldcs(reinterpret_cast<const uint4*>(src + c * 1024 + n * 4));
-    w[4 * c] = t.x; w[4 * c + 1] = t.y; w[4 * c + 2] = t.z; w[4 * c + 3] = t.w;
-  }
-  if constexpr (K::TAIL == 2) {
-    const uint2 t = __ldcs(reinterpret_cast<const uint2*>(src + K::NFULL * 1024 + n * 2));
-    w[4 * K::NFULL] = t.x; w[4 * K::NFULL + 1] = t.y;
-  }
-}
-template <int NCH>
-__device__ __forceinline__ void t16_unstash(float* u, const uint32_t* w) {
-  using K = Cfg16<NCH>;
-#pragma unroll
-  for (int p = 0; p < K::NP; ++p) u[p * NCH] = __uint_as_float(w[p]);
-  float d[K::GC - K::NP + 1];
-#pragma unroll
-  for (int j = 0; j < (K::GC - K::NP) / 2; ++j) {
-    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w[K::NP + j]));
-    d[2 * j] = f2.x; d[2 * j + 1] = f2.y;
-  }
-#pragma unroll
-  for (int p = 0; p < K::NP; ++p)
-#pragma unroll
-    for (int ch = 1; ch < NCH; ++ch) u[p * NCH + ch] = d[p * (NCH - 1) + ch - 1];
-}
-
-// GC fp32 values of step `step` -> halves in the thread's tile row (columns step * GC ...)
-template <int NCH, bool SAT>
-__device__ __forceinline__ void t16_store_step(const float* v, unsigned char* trow, int step, uint32_t r7) {
-  using K = Cfg16<NCH>;
-  uint32_t h[K::GC / 2];
-#pragma unroll
-  for (int j = 0; j < K::GC / 2; ++j) h[j] = SAT ? tt_pack_h2_sat(v[2 * j], v[2 * j + 1]) : tc_pack_h2(v[2 * j], v[2 * j + 1]);
-  if constexpr (K::GC == 16) {
-    *reinterpret_cast<uint4*>(trow + tc_chunk_off(2 * step, r7)) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(trow + tc_chunk_off(2 * step + 1, r7)) = make_uint4(h[4], h[5], h[6], h[7]);
-  } else {                                              // 20 columns = 2.5 chunks: steps 2k / 2k+1 share chunk 5k+2
-    const int c = 5 * (step >> 1);
-    if ((step & 1) == 0) {
-      *reinterpret_cast<uint4*>(trow + tc_chunk_off(c, r7)) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(trow + tc_chunk_off(c + 1, r7)) = make_uint4(h[4], h[5], h[6], h[7]);
-      *reinterpret_cast<uint2*>(trow + tc_chunk_off(c + 2, r7)) = make_uint2(h[8], h[9]);
-    } else {
-      *reinterpret_cast<uint2*>(trow + tc_chunk_off(c + 2, r7) + 8) = make_uint2(h[0], h[1]);
-      *reinterpret_cast<uint4*>(trow + tc_chunk_off(c + 3, r7)) = make_uint4(h[2], h[3], h[4], h[5]);
-      *reinterpret_cast<uint4*>(trow + tc_chunk_off(c + 4, r7)) = make_uint4(h[6], h[7], h[8], h[9]);
-    }
-  }
-}
-
-template <int GC>
-__device__ __forceinline__ void t16_ld_issue(uint32_t taddr, uint32_t* r) {
-  umma::tmem_ld_x16(taddr, r);
-  if constexpr (GC == 20) umma::tmem_ld_x4(taddr + 16, r + 16);
-}
-
-struct Set16 {
-  unsigned char* tile;     // this set's B tile
-  unsigned char* trow;     // the thread's row of it
-  float* xs;               // [PT][3] coordinates of the sub-tile
-  float* os;               // [256] output-layer partial sums / stored seeds
-  const float* wl_s;
-  uint64_t* act_ready;     // this set's barriers
-  uint64_t* acc_ready;
-  uint32_t tmem_acc;       // accumulator of (sub-tile, neuron half, lane quarter)
-  uint32_t r7, acc_phase;
-  int s, n, ts, lane;
-  unsigned long long* trace;
-  uint32_t tn;
-};
-
-template <int NCH>
-__device__ __forceinline__ void t16_pair(Set16& e, const NetView& net, const GradView& grad, const SegDev& sg, const FusedDev& fd, int64_t pair,
-                                         float* Uset, float S, float wl, const FirstRow& fr, double* acc_terms, float* acc_misc) {
-  using K = Cfg16<NCH>;
-  constexpr int GC = K::GC;
-  const int L = net.n_lin - 1;
-  const float ww = net.ww;
-  const float invS = 1.0f / S;
-  const bool nostash = ((fd.flags >> 8) & 32) != 0;
-  const int64_t p0 = (pair * 2 + e.s) * K::PT;          // first point of this set's sub-tile
-  tc_trace(e.trace, e.tn, 14, NCH);
-  t16_bar(e.s);
-  for (int i = e.ts; i < K::PT; i += 256) {
-    const int64_t p = p0 + i;
-    float pt[3] = {0.f, 0.f, 0.f};
-    if (p < sg.P) { pt[0] = sg.x[p * 3]; pt[1] = sg.x[p * 3 + 1]; pt[2] = sg.x[p * 3 + 2]; }
-    e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
-  }
-  if (K::NV < 128) *reinterpret_cast<uint4*>(e.trow + tc_chunk_off(15, e.r7)) = make_uint4(0, 0, 0, 0);
-  t16_bar(e.s);
-  // ---------------- forward ----------------
-  for (int l = 0; l < L; ++l) {
-    const float bias = (l > 0) ? ww * net.b[l][e.n] : 0.f;
-    float* ust = Uset + (size_t)l * 2 * T16_SUB_FLOATS;
-    tc_trace(e.trace, e.tn, 42 + e.s, l);
-    if (l > 0) {
-      mbar_wait(e.acc_ready, e.acc_phase, 0x400 + e.s);
-      e.acc_phase ^= 1u;
-      tc_fence_after();
-    }
-    tc_trace(e.trace, e.tn, 10 + e.s, l);
-    if (l == 0) {
-#pragma unroll 1
-      for (int g = 0; g < K::NSTEP; ++g) {
-        float u[GC];
-        tc_first_layer_group<NCH, GC>(u, e.xs + g * K::NP * 3, fr.w0, fr.rx, fr.ry, fr.rz, fr.b);
-#pragma unroll
-        for (int pp = 0; pp < K::NP; ++pp) {
-          float sn, cs;
-          sincos_fast(u[pp * NCH], sn, cs);
-          tc_act_point<NCH>(u + pp * NCH, sn, cs);
-        }
-        t16_store_step<NCH, false>(u, e.trow, g, e.r7);
-      }
-    } else {
-      uint32_t nxt[GC];
-      t16_ld_issue<GC>(e.tmem_acc, nxt);
-#pragma unroll 1
-      for (int g = 0; g < K::NSTEP; ++g) {
-        float u[GC];
-        umma::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < GC; ++j) u[j] = __uint_as_float(nxt[j]);
-        if (g + 1 < K::NSTEP) t16_ld_issue<GC>(e.tmem_acc + (g + 1) * GC, nxt);
-#pragma unroll
-        for (int pp = 0; pp < K::NP; ++pp) u[pp * NCH] += bias;
-        if (!nostash) t16_stash_store<NCH>(u, ust + g * T16_STEP_FLOATS, e.n);
-#pragma unroll
-        for (int pp = 0; pp < K::NP; ++pp) {
-          float sn, cs;
-          sincos_fast(u[pp * NCH], sn, cs);
-          tc_act_point<NCH>(u + pp * NCH, sn, cs);
-        }
-        t16_store_step<NCH, false>(u, e.trow, g, e.r7);
-      }
-    }
-    tc_trace(e.trace, e.tn, 12 + e.s, l);
-    if (l < L - 1) {
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (e.lane == 0) mbar_arrive(e.act_ready);
-    }
-  }
-  // ---------------- output layer + loss rows of this sub-tile ----------------
-  t16_bar(e.s);
-  tc_trace(e.trace, e.tn, 20, 0);
-  tc_output_dot<K::NV>(e.tile, e.wl_s, e.os, e.ts);
-  t16_bar(e.s);
-  tc_trace(e.trace, e.tn, 21, 0);
-  if ((e.ts & ~31) < K::PT) {
-    double t[4] = {0.0, 0.0, 0.0, 0.0};
-    float bl = 0.f, amax = 0.f;
-    if (e.ts < K::PT) {
-      const int64_t p = p0 + e.ts;
-      float* col = e.os + e.ts * NCH;
-      float v[10], sv[10];
-#pragma unroll
-      for (int ch = 0; ch < 10; ++ch) {
-        v[ch] = 0.f;
-        if (ch < NCH) {
-          const float r = col[ch] + col[128 + ch];
-          v[ch] = (ch == 0) ? r + net.b[L][0] : (ch >= 4 ? r * TC_KAPPA_INV : r);
-        }
-      }
-#pragma unroll
-      for (int ch = 0; ch < 10; ++ch) sv[ch] = 0.f;
-      if (p < sg.P) {
-        loss_row(fd.loss, NCH, v, sg.dist[p], sg.normals + p * 3, t, sv);
-        if (sg.outp) {
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) sg.outp[p * NCH + ch] = v[ch];
-        }
-      }
-      bl = sv[0];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const float st = sv[ch] * (ch >= 4 ? TC_KAPPA_INV : 1.f);
-        amax = fmaxf(amax, fabsf(st));
-        col[ch] = st * S;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
-      bl += __shfl_xor_sync(0xffffffffu, bl, o);
-      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    }
-    if (e.lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (t[k] != 0.0) atomicAdd(&acc_terms[k], t[k]);
-      if (bl != 0.f) atomicAdd(&acc_misc[0], bl);
-      if (amax > 0.f && isfinite(amax)) atomicMax(reinterpret_cast<int*>(&acc_misc[1]), __float_as_int(amax));
-    }
-  }
-  t16_bar(e.s);
-  tc_trace(e.trace, e.tn, 22, 0);
-  // ---------------- reverse sweep ----------------
-  const float* sd = e.os;
-  for (int l = L - 1; l >= 1; --l) {
-    const bool top = (l == L - 1);
-    const float* ust = Uset + (size_t)l * 2 * T16_SUB_FLOATS;
-    uint32_t wn[K::NWP];
-    if (!nostash) t16_stash_load<NCH>(wn, ust, e.n);
-    else {
-#pragma unroll
-      for (int j = 0; j < K::NWP; ++j) wn[j] = 0x3c003c00u;
-    }
-    tc_trace(e.trace, e.tn, 40 + e.s, l);
-    if (!top) {
-      mbar_wait(e.acc_ready, e.acc_phase, 0x400 + e.s);
-      e.acc_phase ^= 1u;
-      tc_fence_after();
-    }
-    tc_trace(e.trace, e.tn, 30 + e.s, l);
-    float bsum = 0.f, wlsum = 0.f;
-    uint32_t tr[GC];
-    if (!top) t16_ld_issue<GC>(e.tmem_acc, tr);
-#pragma unroll 1
-    for (int g = 0; g < K::NSTEP; ++g) {
-      float u[GC], ab[GC];
-      t16_unstash<NCH>(u, wn);
-      if (g + 1 < K::NSTEP && !nostash) t16_stash_load<NCH>(wn, ust + (g + 1) * T16_STEP_FLOATS, e.n);
-      if (top) {
-#pragma unroll
-        for (int j = 0; j < GC; ++j) ab[j] = wl * sd[g * GC + j];
-      } else {
-        umma::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < GC; ++j) ab[j] = __uint_as_float(tr[j]);
-        if (g + 1 < K::NSTEP) t16_ld_issue<GC>(e.tmem_acc + (g + 1) * GC, tr);
-      }
-#pragma unroll
-      for (int pp = 0; pp < K::NP; ++pp) {
-        float ub[NCH];
-        const float sn = __sinf(u[pp * NCH]), cs = __cosf(u[pp * NCH]);
-        tc_adj_point<NCH>(u + pp * NCH, ab + pp * NCH, ub, sn, cs);
-        if (top) {
-          tc_act_point<NCH>(u + pp * NCH, sn, cs);
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) wlsum = fmaf(sd[g * GC + pp * NCH + ch], u[pp * NCH + ch], wlsum);
-        }
-        bsum += ub[0];
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) ab[pp * NCH + ch] = ub[ch];
-      }
-      t16_store_step<NCH, true>(ab, e.trow, g, e.r7);
-      if ((fd.flags & 1) && (e.lane & 7) == 0) {
-#pragma unroll
-        for (int c = 0; c < K::NFULL; ++c) l2_discard_line(ust + g * T16_STEP_FLOATS + c * 1024 + e.n * 4);
-      }
-    }
-    tc_trace(e.trace, e.tn, 32 + e.s, l);
-    atomicAdd(&grad.b[l][e.n], bsum * ww * invS);
-    if (top) atomicAdd(&grad.W[L][e.n], wlsum * invS);
-    tc_fence_before();
-    fence_proxy_async();
-    __syncwarp();
-    if (e.lane == 0) mbar_arrive(e.act_ready);
-  }
-  {
-    tc_trace(e.trace, e.tn, 40 + e.s, 0);
-    mbar_wait(e.acc_ready, e.acc_phase, 0x400 + e.s);
-    e.acc_phase ^= 1u;
-    tc_fence_after();
-    tc_trace(e.trace, e.tn, 30 + e.s, 0);
-    float bsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
-    uint32_t tr[GC];
-    t16_ld_issue<GC>(e.tmem_acc, tr);
-#pragma unroll 1
-    for (int g = 0; g < K::NSTEP; ++g) {
-      float u[GC], ab[GC];
-      const float* pts = e.xs + g * K::NP * 3;
-      tc_first_layer_group<NCH, GC>(u, pts, fr.w0, fr.rx, fr.ry, fr.rz, fr.b);
-      umma::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < GC; ++j) ab[j] = __uint_as_float(tr[j]);
-      if (g + 1 < K::NSTEP) t16_ld_issue<GC>(e.tmem_acc + (g + 1) * GC, tr);
-#pragma unroll
-      for (int pp = 0; pp < K::NP; ++pp) {
-        float sn, cs, ub[NCH];
-        sincos_fast(u[pp * NCH], sn, cs);
-        tc_adj_point<NCH>(u + pp * NCH, ab + pp * NCH, ub, sn, cs);
-        bsum += ub[0];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) w0s[d] += ub[0] * pts[pp * 3 + d] + ub[1 + d];
-      }
-    }
-    tc_trace(e.trace, e.tn, 32 + e.s, 0);
-    atomicAdd(&grad.b[0][e.n], bsum * net.w0 * invS);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) atomicAdd(&grad.W[0][e.n * 3 + d], w0s[d] * net.w0 * invS);
-  }
-  tc_trace(e.trace, e.tn, 15, NCH);
-}
-
-template <int NA, int NB>
-__global__ void __launch_bounds__(T16_THREADS, 1)
-tt_fused16_kernel(const unsigned char* __restrict__ packed, NetView net, GradView grad, SegDev sa, SegDev sb, FusedDev fd,
-                  float* __restrict__ scratch, unsigned char* __restrict__ Aimg, unsigned char* __restrict__ Zimg, int64_t ncb) {
-  using C = TcCfg<NA>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* act = smem;
-  unsigned char* ring = smem + C::OFF_RING;
-  float* wl_s = (float*)(smem + C::OFF_WL);
-  uint64_t* bars = (uint64_t*)(smem + C::OFF_BAR);
-  uint64_t *full = bars, *empty = bars + TC_STAGES, *act_ready = bars + 2 * TC_STAGES, *acc_ready = bars + 2 * TC_STAGES + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
-  double* acc_terms = (double*)(smem + C::OFF_BAR + 128);
-  float* acc_misc = (float*)(smem + C::OFF_BAR + 160);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = net.n_lin - 1;
-  const int64_t npairs = sa.npairs + sb.npairs;
-  const int64_t rounds = ((int64_t)blockIdx.x < npairs) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
-    mbar_fence_init();
-    for (int k = 0; k < 4; ++k) acc_terms[k] = 0.0;
-    acc_misc[0] = 0.f; acc_misc[1] = 0.f;
-  }
-  if (warp == 17) tmem_alloc<512>(tmem_slot);
-  if (tid < 256) wl_s[tid] = net.W[L][tid];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 16) {
-    setmaxnreg_dec<T16_REGS_AUX>();
-    const int skew = (fd.flags & 16) ? 0 : L - 1;          // flags bit 4 (diagnostics): both streams in lockstep
-    if (warp == 16) {
-      if (lane == 0) tc_producer_skew(packed, ring, full, empty, rounds, L - 1, skew, fd.flags >> 8);
-    } else if (warp == 17) {
-      tc_mma_role_skew(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, skew, Aimg, Zimg, ncb, fd.flags >> 8,
-                       (fd.flags & 2) ? l2_policy_evict_first() : 0ull, (fd.trace && blockIdx.x == 0) ? fd.trace : nullptr);
-    }
-  } else {
-    setmaxnreg_inc<T16_REGS_EPI>();
-    const int s = warp >> 3, q = warp & 3, h = (warp >> 2) & 1;
-    Set16 e;
-    e.s = s; e.ts = tid & 255; e.lane = lane;
-    e.n = h * 128 + q * 32 + lane; e.r7 = e.n & 7;
-    e.tile = act + s * TC_ACT_BYTES;
-    e.trow = tc_tile_row(e.tile, e.n);
-    e.xs = (float*)(smem + C::OFF_XS) + s * 128 * 3;
-    e.os = (float*)(smem + C::OFF_OS) + s * 256;
-    e.wl_s = wl_s;
-    e.act_ready = &act_ready[s]; e.acc_ready = &acc_ready[s];
-    e.tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + s * 256 + h * 128;
-    e.acc_phase = 0;
-    e.trace = (fd.trace && blockIdx.x == 0 && (warp & 7) == 0) ? fd.trace + TC_TRACE_REGION * (1 + s) : nullptr;
-    e.tn = 0;
-    const float S = loss_scale_from(fd.amax_prev);
-    const float wl = net.W[L][e.n];
-    FirstRow fr;
-    fr.w0 = net.w0; fr.rx = net.W[0][e.n * 3]; fr.ry = net.W[0][e.n * 3 + 1]; fr.rz = net.W[0][e.n * 3 + 2]; fr.b = net.b[0][e.n];
-    float* Uset = scratch + (size_t)blockIdx.x * L * 256 * 256 + (size_t)s * T16_SUB_FLOATS;
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      if (pair < sa.npairs) {
-        t16_pair<NA>(e, net, grad, sa, fd, pair, Uset, S, wl, fr, acc_terms, acc_misc);
-      } else {
-        if constexpr (NB > 0) t16_pair<NB>(e, net, grad, sb, fd, pair - sa.npairs, Uset, S, wl, fr, acc_terms, acc_misc);
-      }
-    }
-    asm volatile("bar.sync 3, 512;" ::: "memory");
-    if (tid < 4 && acc_terms[tid] != 0.0) atomicAdd(&fd.terms[tid], acc_terms[tid]);
-    if (tid == 4 && acc_misc[0] != 0.f) atomicAdd(&grad.b[L][0], acc_misc[0]);
-    if (tid == 5 && acc_misc[1] > 0.f) atomicMax(reinterpret_cast<int*>(fd.amax_next), __float_as_int(acc_misc[1]));
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) tmem_dealloc<512>(tmem_base);
-}
-
-template <int NA, int NB>
-static int tt_launch_fused16(const void* packed, const NetView& net, const GradView& grad, const SegDev& a, const SegDev& b, const FusedDev& fd,
-                             float* scratch, void* Aimg, void* Zimg, int64_t ld, int sms, cudaStream_t st) {
-  auto k = tt_fused16_kernel<NA, NB>;
-  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
-  const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
-  if (grid < 1) return 0;
-  k<<<grid, T16_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, fd, scratch, (unsigned char*)Aimg,
-                                                (unsigned char*)Zimg, ld >> 6);
-  DUDF_LAUNCH_OK();
-  return 0;
-}
-
 size_t tc_fused_scratch_bytes(const NetView& net, int sms) { return (size_t)sms * (net.n_lin - 1) * 256 * 256 * sizeof(float); }
 
 template <int NA, int NB>
@@ -1424,11 +883,6 @@ int tc_train_fused(const void* packed, const NetView& net, const GradView& grad,
   for (int k = 0; k < 4; ++k) { fd.loss.w[k] = fl.w[k]; fd.loss.up[k] = 1.f; }
   fd.terms = fl.terms; fd.amax_prev = fl.amax_prev; fd.amax_next = fl.amax_next; fd.flags = fl.flags;
   fd.trace = tc_get_trace();
-  if (fl.flags & DUDF_FUSED_WARPS16) {
-    if (nb == 0 && na == 4) return tt_launch_fused16<4, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
-    if (nb == 0 && na == 10) return tt_launch_fused16<10, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
-    if (na == 10 && nb == 4) return tt_launch_fused16<10, 4>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
-  }
   if (nb == 0) {
     if (na == 4) return tt_launch_fused<4, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);
     if (na == 10) return tt_launch_fused<10, 0>(packed, net, grad, a, b, fd, scratch, Aimg, Zimg, ld, sms, st);

@@ -1,0 +1,512 @@
+// Split-precision ("TCX3") forward chain on tcgen05: fp32-grade jets from fp16 tensor-core operands.
+//
+// Every hidden-layer product  (w W) a  is evaluated as three fp16 MMAs into one fp32 TMEM accumulator,
+//     Wh*Ah + Wh*Al + Wl*Ah        with   X = Xh + Xl,  Xh = fp16(X),  Xl = fp16(X - Xh)   (the Wl*Al term is 2^-22 relative),
+// which restores the 22+ significand bits the reference's fp32 nn.Linear works with (src/model.py:29-30,116-135); the
+// single-pass fp16 chain (dudf_tc.cu) keeps 11.  tools/precision_study.py (operand roundings emulated on the CPU) puts the
+// jets of this scheme at 1e-7..5e-7 of fp64 and — with the reverse sweep and the weight-gradient GEMM left single-pass —
+// the parameter gradients of loss_s1 / loss_s2 / loss_siren at 5e-4..1e-3, inside north_star's 1e-3 for tensor-core paths.
+//
+// Same orientation as dudf_tc.cu (D[neuron][column], weights = UMMA A operand, activations = B operand, lane = neuron), but a
+// different schedule, because the activation tile now exists twice (hi and lo, 2 x 64 KB for 128 columns): ONE 128-column
+// tile per CTA, updated IN PLACE, with the k range of every layer split in two halves.  Per layer the MMA warp issues the groups
+//     G(h=0,kh=0) G(1,0) | G(0,1) G(1,1)          (h = output-neuron half / accumulator, kh = input-neuron half = tile rows)
+// so that after the first two groups the rows of k-half 0 are dead.  The epilogue of neuron half 0 (all 8 warps: 128 neurons x
+// two column halves) starts when G(0,1) retires and overwrites exactly those rows with the next layer's activations while
+// G(1,1) still runs; the epilogue of half 1 overlaps the next layer's G(.,0) groups, which only read rows of k-half 0.  The
+// tensor pipe stays busy as long as an epilogue half fits under 1 536 clk (one group = 24 MMAs of 64 clk); the four
+// accumulators (2 halves x 2 layer parities) fill the 512 TMEM columns.  Weights are scaled by 64 before the split so that
+// their lo parts stay out of the fp16 subnormal range; the epilogue folds the 1/64 back in.
+//
+// The same kernel serves the training forward (TRAIN): it additionally stashes the pre-activations for the reverse sweep and
+// lets the MMA warp bulk-copy the hi tile as the operand image of the weight-gradient GEMM — the layouts of dudf_tc_train.cu,
+// whose (single-pass) reverse sweep and weight-gradient kernels consume them unchanged.
+#include <cuda_fp16.h>
+#include <cstdlib>
+#include <cstring>
+#include "dudf_common.cuh"
+#include "dudf_kernels.h"
+#include "dudf_device.cuh"
+#include "dudf_umma.cuh"
+#include "dudf_tc_common.cuh"
+
+namespace dudf {
+
+using namespace umma;
+
+constexpr int TCX_STAGES = 5;
+constexpr float TCX_WSCALE = 64.f;
+constexpr float TCX_WSCALE_INV = 1.f / 64.f;
+constexpr int TCX_LAYER_CHUNKS = 16;           // 4 groups x 2 k-blocks x (hi, lo) chunks of 128 neurons x 64 k
+constexpr int TCX_OFF_LO = TC_ACT_BYTES;       // lo tile behind the hi tile
+constexpr int TCX_OFF_RING = 2 * TC_ACT_BYTES;
+constexpr int TCX_OFF_WL = TCX_OFF_RING + TCX_STAGES * TC_CHUNK_BYTES;
+constexpr int TCX_OFF_XS = TCX_OFF_WL + 256 * 4;
+constexpr int TCX_OFF_OS = TCX_OFF_XS + 128 * 3 * 4;
+constexpr int TCX_OFF_BAR = TCX_OFF_OS + 8 * 128 * 4;        // os: [8 = neuron half x lane quarter][128 columns] partial sums
+constexpr int TCX_SMEM = TCX_OFF_BAR + 256 + 1024;
+static_assert(TCX_SMEM <= 232448, "shared memory budget");
+
+size_t tcx_packed_bytes(int n_lin) { return (size_t)((n_lin > 2) ? (n_lin - 2) : 1) * TCX_LAYER_CHUNKS * TC_CHUNK_BYTES; }
+
+// fp16 hi / lo images of 64 w W in the order the MMA warp consumes them: [layer][kh][h][kb][hi | lo], 16 KB swizzled chunks
+__global__ void __launch_bounds__(256) tcx_pack_kernel(NetView net, unsigned char* packed) {
+  const int l = blockIdx.y + 1;
+  const int n = blockIdx.x;
+  const int k = threadIdx.x;
+  const float v = TCX_WSCALE * (net.ww * net.W[l][n * 256 + k]);
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const int h = n >> 7, r = n & 127, kh = k >> 7, kb = (k >> 6) & 1, kk = k & 63;
+  unsigned char* chunk = packed + ((size_t)(l - 1) * TCX_LAYER_CHUNKS + ((kh * 2 + h) * 2 + kb) * 2) * TC_CHUNK_BYTES;
+  *reinterpret_cast<__half*>(chunk + sw128_offset(r, kk)) = hi;
+  *reinterpret_cast<__half*>(chunk + TC_CHUNK_BYTES + sw128_offset(r, kk)) = lo;
+}
+
+int tcx_pack(const NetView& net, void* packed, cudaStream_t st) {
+  if (net.n_lin <= 2) return 0;
+  tcx_pack_kernel<<<dim3(256, net.n_lin - 2), 256, 0, st>>>(net, (unsigned char*)packed);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
+template <int NCH>
+struct TcxCfg {
+  using B = TcCfg<NCH>;
+  static constexpr int PT = B::PT, NV = B::NV, GC = B::GC, NGRP = B::NGRP;
+  static constexpr int G0 = (NCH == 10) ? 2 : NGRP / 2;      // column groups of warps 0-3; warps 4-7 take the rest
+};
+
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// ---- producer: 16 chunks per layer, in consumption order ----
+template <int CL>
+__device__ __forceinline__ void tcx_producer(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t rounds,
+                                             int n_phase, uint32_t cta_rank) {
+  uint32_t stage = 0, phase = 0, chunk = 0;
+  for (int64_t r = 0; r < rounds; ++r)
+    for (int j = 0; j < n_phase; ++j) {
+      const unsigned char* src = packed + (size_t)j * TCX_LAYER_CHUNKS * TC_CHUNK_BYTES;
+      for (int ck = 0; ck < TCX_LAYER_CHUNKS; ++ck, ++chunk) {
+        mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x1100 + stage);
+        mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
+        if constexpr (CL == 1) {
+          bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
+        } else {
+          if (chunk % CL == cta_rank)
+            bulk_g2s_multicast(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage],
+                               (uint16_t)((1u << CL) - 1));
+        }
+        if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+}
+
+// ---- MMA issuer (whole warp, warp-uniform, one elected lane per instruction; see tc_mma_role) ----
+// img != null (training forward): each k-half of the hi tile is bulk-copied to the operand images of the weight-gradient GEMM
+// as soon as it is published; its shared-memory reads are complete before the accumulator whose epilogue overwrites those rows
+// is handed over.
+template <int CL>
+__device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                             uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, int64_t ntiles,
+                                             unsigned char* img, int64_t ncb, int64_t cb0, uint64_t img_policy) {
+  constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
+  constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
+  const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
+  const uint64_t bh_desc0 = make_desc_sw128(smem_u32(act), 32768, 1024);
+  const uint64_t bl_desc0 = desc_advance(bh_desc0, TCX_OFF_LO);
+  uint32_t stage = 0, phase = 0, act_phase = 0, jg = 0;
+  auto release = [&](uint32_t st) {
+    if constexpr (CL == 1) mma_commit_warp(&empty[st]);
+    else mma_commit_multicast_warp(&empty[st], mask);
+  };
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t tile = blockIdx.x + r * gridDim.x;
+    const bool copy = img != nullptr && tile < ntiles;
+    for (int j = 0; j < n_phase; ++j, ++jg) {
+      const uint32_t acc = tmem_base + (jg & 1u) * 256;
+      for (int kh = 0; kh < 2; ++kh) {
+        mbar_wait(&act_ready[kh], (act_phase >> kh) & 1u, 0x1200 + kh);
+        act_phase ^= 1u << kh;
+        tc_fence_after();
+        if (copy) {
+          if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+              unsigned char* dst = img + ((size_t)j * ncb + cb0 + tile * 2 + nb) * TC_IMG_BYTES + kh * (TC_IMG_BYTES / 2);
+              const unsigned char* src = act + nb * TC_IMG_BYTES + kh * (TC_IMG_BYTES / 2);
+              if (img_policy) bulk_s2g_hint(dst, src, TC_IMG_BYTES / 2, img_policy);
+              else bulk_s2g(dst, src, TC_IMG_BYTES / 2);
+            }
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t d_tmem = acc + h * 128;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t koff = (uint32_t)(kh * 2 + kb) * 8192u;
+            mbar_wait(&full[stage], phase, 0x1300 + stage);                    // hi chunk: against the hi and the lo tile
+            const uint64_t a_hi = desc_advance(a_desc0, stage * TC_CHUNK_BYTES);
+            mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), idesc, (kh | kb) != 0);
+            mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bl_desc0, koff), idesc, 1);
+            release(stage);
+            if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait(&full[stage], phase, 0x1300 + stage);                    // lo chunk: against the hi tile
+            mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(bh_desc0, koff), idesc, 1);
+            release(stage);
+            if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (kh == 1) {
+            if (copy) {
+              if ((threadIdx.x & 31) == 0) {
+                if (h == 0) bulk_wait_read1();        // the copy of k-half 0 has left shared memory
+                else bulk_wait_read0();
+              }
+              __syncwarp();
+            }
+            mma_commit_warp(&acc_ready[h]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// hi / lo split of GC fp32 values of one thread into the two B tiles (saturating: an overflowing activation clamps instead of inf)
+__device__ __forceinline__ uint32_t tcx_pack_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <int GC>
+__device__ __forceinline__ void tcx_store_group(const float* v, uint32_t row_hi, int chunk0, uint32_t r7) {
+#pragma unroll
+  for (int c8 = 0; c8 < GC / 8; ++c8) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = v[8 * c8 + 2 * e], b = v[8 * c8 + 2 * e + 1];
+      hi[e] = tcx_pack_sat(a, b);
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+      lo[e] = tcx_pack_sat(a - hf.x, b - hf.y);
+    }
+    const uint32_t off = tc_chunk_off(chunk0 + c8, r7);
+    tc_sts128(row_hi + off, hi[0], hi[1], hi[2], hi[3]);
+    tc_sts128(row_hi + TCX_OFF_LO + off, lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// column sums over the 32 lanes of a warp: v[0..M-1] of every lane -> v[0] of lane L = sum over lanes of column (L % M)
+template <int M>
+__device__ __forceinline__ void tcx_colsum(float* v, int lane) {
+#pragma unroll
+  for (int o = 16; o >= M; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+#pragma unroll
+  for (int o = M / 2; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? v[i + o] : v[i];
+      const float send = up ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+
+struct TcxEpi {
+  unsigned char* act;
+  float* xs;
+  float* os;
+  const float* wl_s;
+  uint64_t* act_ready;
+  uint64_t* acc_ready;
+  uint32_t tmem_q;        // accumulator base of this warp's lane quarter
+  uint32_t acc_phase;     // bit h = parity of acc_ready[h]
+  uint32_t jg;            // layer phases completed so far (accumulator parity)
+  int q, cw, lane, tid;
+};
+
+struct TcxTrain {         // training forward: stash + operand images (null for queries)
+  float* Ust;
+  unsigned char* Aimg;
+  int64_t ld, col0;
+};
+
+// all layers of one 128-column tile.  x == null: grid points (first + p).  TRAIN: stash the pre-activations, write raw channels.
+template <int NCH, bool TRAIN>
+__device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const float* __restrict__ x, int64_t P, int gridN, int64_t grid_first,
+                                         float vs, int64_t tile, bool valid, const QueryOut& out, float* outp, float* Ust, int64_t ld, int64_t colt) {
+  using C = TcxCfg<NCH>;
+  constexpr int GC = C::GC;
+  const int L = net.n_lin - 1;
+  const float w0 = net.w0, ww = net.ww;
+  tc_epi_bar();
+  for (int i = e.tid; i < C::PT; i += 256) {
+    const int64_t p = tile * C::PT + i;
+    float pt[3] = {0.f, 0.f, 0.f};
+    if (valid && p < P) {
+      if (x) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
+      else grid_point(grid_first + p, gridN, vs, pt);
+    }
+    e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
+  }
+  if (C::NV < 128) {       // idle columns of both tiles are zero for this tile's math (a launch may mix jet orders)
+    *reinterpret_cast<uint4*>(tc_tile_row(e.act, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(tc_tile_row(e.act + TCX_OFF_LO, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_epi_bar();
+  const int g_begin = e.cw ? C::G0 : 0, g_end = e.cw ? C::NGRP : C::G0;
+  for (int l = 0; l < L; ++l) {
+    for (int h = 0; h < 2; ++h) {
+      const int n = h * 128 + e.q * 32 + e.lane;               // this thread's neuron in this half = its row of the B operand
+      const uint32_t r7 = n & 7;
+      const uint32_t row_hi = smem_u32(tc_tile_row(e.act, n));
+      float r0x = 0.f, r0y = 0.f, r0z = 0.f, b0 = 0.f, bias = 0.f;
+      if (l == 0) { r0x = net.W[0][n * 3]; r0y = net.W[0][n * 3 + 1]; r0z = net.W[0][n * 3 + 2]; b0 = net.b[0][n]; }
+      else bias = ww * net.b[l][n];
+      const float wl = (l == L - 1) ? e.wl_s[n] : 0.f;
+      if (l > 0) {
+        mbar_wait(&e.acc_ready[h], (e.acc_phase >> h) & 1u, 0x1400 + h);
+        e.acc_phase ^= 1u << h;
+        tc_fence_after();
+      }
+      const uint32_t taddr = e.tmem_q + ((e.jg + (uint32_t)l - 1u) & 1u) * 256 + h * 128;
+#pragma unroll 1
+      for (int g = g_begin; g < g_end; ++g) {
+        float u[GC];
+        if (l == 0) {
+          tc_first_layer_group<NCH, GC>(u, e.xs + g * (GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
+        } else {
+          TmemRegs<GC> tr;
+          tc_ld_issue<GC>(taddr + g * GC, tr);
+          tc_ld_take<GC>(tr, u);
+#pragma unroll
+          for (int j = 0; j < GC; ++j) u[j] *= TCX_WSCALE_INV;
+#pragma unroll
+          for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
+        }
+        if constexpr (TRAIN) {
+          if (valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + colt) * 256 + n * 4 + (size_t)g * GC * 256);
+        }
+#pragma unroll
+        for (int pp = 0; pp < GC / NCH; ++pp) {
+          float sn, cs;
+          sincos_fast(u[pp * NCH], sn, cs);
+          tc_act_point<NCH>(u + pp * NCH, sn, cs);
+        }
+        if (l < L - 1) {
+          tcx_store_group<GC>(u, row_hi, g * (GC / 8), r7);
+        } else {
+          // output layer (256 -> 1 per channel) on the fp32 activations: this warp's 32 neurons, reduced over its lanes
+#pragma unroll
+          for (int j = 0; j < GC; ++j) u[j] *= wl;
+          float* dst = e.os + (h * 4 + e.q) * 128 + g * GC;
+          tcx_colsum<32>(u, e.lane);
+          dst[e.lane] = u[0];
+          if constexpr (GC == 40) {
+            tcx_colsum<8>(u + 32, e.lane);
+            if (e.lane < 8) dst[32 + e.lane] = u[32];
+          }
+        }
+      }
+      if (l < L - 1) {
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (e.lane == 0) mbar_arrive(&e.act_ready[h]);
+      }
+    }
+  }
+  e.jg += (uint32_t)(L - 1);
+  tc_epi_bar();
+  if (e.tid < C::NV) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += e.os[k * 128 + e.tid];
+    const int ch = e.tid % NCH;
+    e.os[e.tid] = (ch == 0) ? v + net.b[L][0] : (ch >= 4 ? v * TC_KAPPA_INV : v);
+  }
+  tc_epi_bar();
+  if (e.tid < C::PT) {
+    const int64_t p = tile * C::PT + e.tid;
+    if (valid && p < P) {
+      if constexpr (TRAIN) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) outp[p * NCH + ch] = e.os[e.tid * NCH + ch];
+      } else {
+        finalize_point<NCH>(out, p, e.os + e.tid * NCH);
+      }
+    }
+  }
+}
+
+// One launch serves up to two row segments with different jet orders (training: on-surface rows carry the Hessian jet).
+// Queries use segment a only (x == null: grid points).
+template <int NA, int NB, int CL, bool TRAIN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev sa, SegDev sb, int64_t tiles_a, int64_t tiles_b, int gridN,
+                   int64_t grid_first, QueryOut out, TcxTrain tr) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* act = smem;
+  unsigned char* ring = smem + TCX_OFF_RING;
+  float* wl_s = (float*)(smem + TCX_OFF_WL);
+  uint64_t* bars = (uint64_t*)(smem + TCX_OFF_BAR);
+  uint64_t *full = bars, *empty = bars + TCX_STAGES, *act_ready = bars + 2 * TCX_STAGES, *acc_ready = bars + 2 * TCX_STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TCX_STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = net.n_lin - 1;
+  const int64_t ntiles = tiles_a + tiles_b;
+  // every CTA of a cluster runs the same number of rounds (a round past the end works on a fully masked tile)
+  const int64_t rounds = (CL > 1) ? (ntiles + gridDim.x - 1) / gridDim.x
+                                  : (((int64_t)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  if (tid == 0) {
+    for (int i = 0; i < TCX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (tid < 256) wl_s[tid] = net.W[L][tid];
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    setmaxnreg_dec<TC_REGS_AUX>();
+    if (warp == 8) {
+      if (lane == 0) tcx_producer<CL>(packed, ring, full, empty, rounds, L - 1, CL > 1 ? cluster_ctarank() : 0u);
+    } else if (warp == 9) {
+      tcx_mma_role<CL>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, ntiles, TRAIN ? tr.Aimg : nullptr,
+                       tr.ld >> 6, tr.col0 >> 6, TRAIN ? l2_policy_evict_first() : 0ull);
+    }
+  } else {
+    setmaxnreg_inc<TC_REGS_EPI>();
+    TcxEpi e;
+    e.act = act; e.xs = (float*)(smem + TCX_OFF_XS); e.os = (float*)(smem + TCX_OFF_OS); e.wl_s = wl_s;
+    e.act_ready = act_ready; e.acc_ready = acc_ready;
+    e.q = warp & 3; e.cw = warp >> 2; e.lane = lane; e.tid = tid;
+    e.tmem_q = tmem_base + ((uint32_t)(e.q * 32) << 16);
+    e.acc_phase = 0; e.jg = 0;
+    const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+      const int64_t tile = blockIdx.x + rd * gridDim.x;
+      const bool valid = tile < ntiles;
+      const int64_t colt = tr.col0 + tile * 128;
+      if (!valid || tile < tiles_a) {
+        tcx_tile<NA, TRAIN>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt);
+      } else {
+        if constexpr (NB > 0) tcx_tile<NB, TRAIN>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                 // nobody exits while a peer may still multicast into its ring
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+static int tcx_cluster_size() {
+  static int v = -1;            // DUDF_TCX_CLUSTER=1|2|4 overrides the cluster size (default 2: halves the L2 reads of the weight stream)
+  if (v < 0) {
+    const char* e = getenv("DUDF_TCX_CLUSTER");
+    const int c = e ? atoi(e) : 2;
+    v = (c == 1 || c == 2 || c == 4) ? c : 2;
+  }
+  return v;
+}
+
+template <int NA, int NB, int CL, bool TRAIN>
+static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
+                      const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
+  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN>;
+  DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
+  const int64_t ntiles = ta + tb;
+  int grid = (int)std::min<int64_t>(ntiles, sms);
+  if (grid < 1) return 0;
+  if (CL > 1) grid = std::max(CL, (std::min<int>(sms, (int)((ntiles + CL - 1) / CL * CL)) / CL) * CL);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TCX_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DUDF_CUDA_OK(cudaLaunchKernelEx(&cfg, k, (const unsigned char*)packed, net, a, b, ta, tb, gridN, first, out, tr));
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
+template <int NA, int NB, bool TRAIN>
+static int tcx_launch_cl(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
+                         const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
+  int cl = tcx_cluster_size();
+  while (cl > 1 && ta + tb < 2 * cl) cl >>= 1;
+  if (cl == 4) return tcx_launch<NA, NB, 4, TRAIN>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  if (cl == 2) return tcx_launch<NA, NB, 2, TRAIN>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  return tcx_launch<NA, NB, 1, TRAIN>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+}
+
+int tcx_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN, int64_t grid_first, const QueryOut& out,
+                int sms, cudaStream_t st) {
+  SegDev a, b;
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  a.x = x;
+  a.P = P;
+  TcxTrain tr;
+  memset(&tr, 0, sizeof(tr));
+  switch (nch) {
+    case 1: return tcx_launch_cl<1, 0, false>(packed, net, a, b, (P + TcxCfg<1>::PT - 1) / TcxCfg<1>::PT, 0, gridN, grid_first, out, tr, sms, st);
+    case 4: return tcx_launch_cl<4, 0, false>(packed, net, a, b, (P + TcxCfg<4>::PT - 1) / TcxCfg<4>::PT, 0, gridN, grid_first, out, tr, sms, st);
+    case 10: return tcx_launch_cl<10, 0, false>(packed, net, a, b, (P + TcxCfg<10>::PT - 1) / TcxCfg<10>::PT, 0, gridN, grid_first, out, tr, sms, st);
+  }
+  DUDF_REQUIRE(false, "split tensor-core path: unsupported channel count %d", nch);
+}
+
+// training forward: same stash / operand-image layout and column allocation (256 columns per sub-tile pair) as tc_train_forward
+int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld, int64_t col0,
+                      int sms, cudaStream_t st) {
+  DUDF_REQUIRE(ld % 64 == 0 && col0 % 128 == 0, "tensor-core stash: ld must be a multiple of 64 and col0 of 128");
+  DUDF_REQUIRE(nseg == 1 || nseg == 2, "tensor-core training: 1 or 2 segments per launch");
+  SegDev a, b;
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  auto fill = [](SegDev& d, const TcSegment& s) {
+    d.x = s.x; d.outp = s.packed; d.P = s.rows;
+    const int pp = tc_train_pair_points(s.nch);
+    d.npairs = (s.rows + pp - 1) / pp;
+  };
+  fill(a, segs[0]);
+  if (nseg == 2) fill(b, segs[1]);
+  const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
+  const int64_t ta = 2 * a.npairs, tb = 2 * b.npairs;       // whole pairs: the reverse sweep reads the stash of a padding sub-tile too
+  DUDF_REQUIRE(col0 + (ta + tb) * 128 <= ld, "tensor-core stash too small");
+  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0};
+  QueryOut out;
+  memset(&out, 0, sizeof(out));
+  if (nb == 0) {
+    if (na == 1) return tcx_launch_cl<1, 0, true>(packed, net, a, b, ta, tb, 0, 0, out, tr, sms, st);
+    if (na == 4) return tcx_launch_cl<4, 0, true>(packed, net, a, b, ta, tb, 0, 0, out, tr, sms, st);
+    if (na == 10) return tcx_launch_cl<10, 0, true>(packed, net, a, b, ta, tb, 0, 0, out, tr, sms, st);
+  } else if (na == 10) {
+    if (nb == 4) return tcx_launch_cl<10, 4, true>(packed, net, a, b, ta, tb, 0, 0, out, tr, sms, st);
+    if (nb == 1) return tcx_launch_cl<10, 1, true>(packed, net, a, b, ta, tb, 0, 0, out, tr, sms, st);
+  }
+  DUDF_REQUIRE(false, "split tensor-core training: unsupported segment channel counts (%d, %d)", na, nb);
+}
+
+}  // namespace dudf

@@ -8,7 +8,11 @@ import torch
 
 from . import _lib
 
-PRECISIONS = {"fp32": 0, "tc16": 1}
+PRECISIONS = {"fp32": 0, "tc16": 1, "tcx3": 2}
+TC_PRECISIONS = ("tc16", "tcx3")          # tensor-core arithmetics (share the stash / operand-image layouts)
+# weight images a precision needs (dudf_refresh_weights bits): fp32 transposes 1, single-pass fp16 images 2 (the reverse
+# sweep of both tensor-core modes), hi + lo fp16 images 4
+NEED = {"fp32": 1, "tc16": 2, "tcx3": 6}
 LOSS_MODES = {"s1": 0, "s2": 1, "siren": 2}
 GT_MODES = {"tanh": 0, "siren": 1, "squared": 2}
 Q_ABS_INV_TANH = 1
@@ -55,11 +59,17 @@ class Engine:
             pass
 
     # ---- weights ----
-    def sync_weights(self, weights, biases, need=3):
+    def sync_weights(self, weights, biases, need=7, reuse=False):
         """Bind the parameter tensors (zero copy) and rebuild the derived operand images that `need` asks for
-        (bit 1: fp32 transposes, bit 2: tensor-core fp16 images) when any parameter changed since they were built
-        (torch version counters / storage pointers; in-place updates behind torch's back must reset `_sig`)."""
+        (bit 1: fp32 transposes, bit 2: single-pass fp16 images, bit 4: hi + lo fp16 images).
+
+        torch's version counters do not see writes through `.data` (EMA, clipping, manual re-initialisation), so the
+        images are rebuilt on EVERY call (three small kernels, ~15 us of device time, no host synchronisation) unless the
+        caller passes reuse=True — which is what the loss backward does after checking that the signature it recorded in
+        its forward is unchanged.  `invalidate()` forces a rebuild explicitly."""
         sig = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+        if sig != self._sig or not reuse:
+            self._fresh = 0
         if sig != self._sig:
             ws = [w.detach() for w in weights]
             bs = [b.detach() for b in biases]
@@ -69,12 +79,16 @@ class Engine:
             _lib.check(self.L.dudf_bind_weights(self.h, _ptr_array(ws), _ptr_array(bs)), "dudf_bind_weights")
             self._bound = (ws, bs)               # keep the storages alive while the library holds their pointers
             self._sig = sig
-            self._fresh = 0
         todo = need & ~self._fresh
         if todo:
             with torch.cuda.device(self.device):
                 _lib.check(self.L.dudf_refresh_weights(self.h, todo, _lib.current_stream()), "dudf_refresh_weights")
             self._fresh |= todo
+
+    def invalidate(self):
+        """Forget the derived weight images: the next use rebuilds them from the bound parameters."""
+        self._sig = None
+        self._fresh = 0
 
     # ---- queries ----
     def query(self, x, order, precision="fp32", flags=0, alpha=0.0):
@@ -167,7 +181,8 @@ class Engine:
     def evaluate_host(self, x_host, order, f_host, g_host, H_host, max_batch, precision="fp32"):
         with torch.cuda.device(self.device):
             _lib.check(self.L.dudf_evaluate_host(self.h, x_host.ctypes.data, x_host.shape[0], order, _lib.ptr(f_host), _lib.ptr(g_host),
-                                                 _lib.ptr(H_host), max_batch, PRECISIONS[precision]), "dudf_evaluate_host")
+                                                 _lib.ptr(H_host), max_batch, PRECISIONS[precision], _lib.current_stream()),
+                       "dudf_evaluate_host")
 
     # ---- training primitives ----
     def stash_columns(self, order, P, precision="fp32"):

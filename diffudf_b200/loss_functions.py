@@ -11,7 +11,7 @@ import os
 
 import torch
 
-from .engine import NCH
+from .engine import NCH, NEED, TC_PRECISIONS
 
 S1_KEYS = ("sdf_on_surf", "sdf_off_surf", "hessian_constraint", "grad_constraint")
 S2_KEYS = ("sdf_on_surf", "std_on_surf")
@@ -45,7 +45,7 @@ class TrainCore:
         return t
 
     def plan(self, mode, P, n_on, w, prec):
-        eng = self.model._engine_synced(2 if prec == "tc16" else 1)
+        eng = self.model._engine_synced(NEED[prec], reuse=True)
         if mode == "s1":
             base = 1 if (w[3] != 0 or w[2] != 0) else 0
             nh = n_on if w[2] != 0 else 0
@@ -61,12 +61,12 @@ class TrainCore:
             segs.append(dict(row0=row0, rows=rows, order=order, col0=col, cols=cols, off=off))
             col += cols
             off += rows * NCH[order]
-        ld = (col + 63) // 64 * 64 if prec == "tc16" else (col + 3) // 4 * 4
+        ld = (col + 63) // 64 * 64 if prec in TC_PRECISIONS else (col + 3) // 4 * 4
         return segs, ld, off
 
     def _stashes(self, L, ld, prec, need_z=True):
         Z = self._buf("Z", (L, 256, ld)) if need_z else None
-        if prec == "tc16":       # fp16 operand images [layer][column block of 64][256 neurons][64 columns]; zero tails are part of the contract
+        if prec in TC_PRECISIONS:       # fp16 operand images [layer][column block of 64][256 neurons][64 columns]; zero tails are part of the contract
             A = self._buf("A", (L, 4, ld, 64), torch.float16, zero=True)
             Zb = self._buf("Zb", (L, 4, ld, 64), torch.float16, zero=True)
         else:
@@ -78,7 +78,7 @@ class TrainCore:
         """Returns a (4,) float64 device tensor with this rank's share of the loss terms."""
         m = self.model
         prec = self._prec()
-        eng = m._engine_synced(2 if prec == "tc16" else 1)
+        eng = m._engine_synced(NEED[prec])
         P = x.shape[0]
         P_global = P if P_global is None else P_global
         segs, ld, nout = self.plan(mode, P, n_on, w, prec)
@@ -115,16 +115,16 @@ class TrainCore:
         key = (mode, tuple(float(v) for v in w), float(alpha), int(P_global), int(n_on), int(P))
         if self.amax is None:
             self.amax = torch.zeros(2, device=x.device, dtype=torch.float32)
-        if prec != "tc16" or mode == "s2" or self.amax_key != key:
+        if prec != "tc16" or mode == "s2" or self.amax_key != key:     # (tcx3 has no single-launch kernel yet)
             terms = self.forward(mode, x, normals, d, n_on, w, alpha, P_global, None)
             slot = 1 - self.amax_slot
             self.amax[slot:slot + 1].zero_()
-            self.backward(None, gW, gB, absmax=self.amax[slot:slot + 1] if prec == "tc16" else None)
+            self.backward(None, gW, gB, absmax=self.amax[slot:slot + 1] if prec in TC_PRECISIONS else None)
             if prec == "tc16" and mode != "s2":
                 self.amax_key, self.amax_slot = key, slot
             return terms
         m = self.model
-        eng = m._engine_synced(2)
+        eng = m._engine_synced(NEED[prec])
         segs, ld, _ = self.plan(mode, P, n_on, w, prec)
         _, A, Zb = self._stashes(m.n_hidden, ld, prec, need_z=False)
         scratch = self._buf("fused_scratch", (eng.fused_scratch_bytes() // 4,))
@@ -146,11 +146,11 @@ class TrainCore:
             raise RuntimeError("TrainCore.backward without a pending forward")
         m = self.model
         prec = p["prec"]
-        eng = m._engine_synced(2 if prec == "tc16" else 1)
+        eng = m._engine_synced(NEED[prec], reuse=True)
         if eng._sig != p["sig"]:
             raise RuntimeError("SIREN parameters changed between the loss forward and backward")
         seeds = self._buf("seeds", tuple(p["packed"].shape))
-        if absmax is None and prec == "tc16":
+        if absmax is None and prec in TC_PRECISIONS:
             absmax = torch.zeros(1, device=p["x"].device, dtype=torch.float32)
         for s in p["segs"]:                 # all seeds (and their magnitude) before the first reverse sweep
             r0, r1 = s["row0"], s["row0"] + s["rows"]

@@ -92,7 +92,7 @@ class _JetFn(torch.autograd.Function):
     def backward(ctx, fb, gb, Hb):
         model, order, ld = ctx.model, ctx.order, ctx.ld
         x, Z, A = ctx.saved_tensors
-        eng = model._engine_synced()
+        eng = model._engine_synced(1, reuse=True)
         if eng._sig != ctx.sig:
             raise RuntimeError("SIREN parameters changed between forward and backward")
         P = x.shape[0]
@@ -127,8 +127,8 @@ class FieldRecord:
 
     def __init__(self, model, coords):
         self.model = model
-        self.coords = coords
-        self.lead = tuple(coords.shape[:-1])
+        self.lead = tuple(coords.shape[:-1])          # (the record does not keep `coords`: it is attached TO coords, and a
+                                                      #  back-reference would leave the stashes to the cyclic collector)
         self.x = coords.detach().reshape(-1, 3).to(torch.float32).contiguous()
         self.cache = {}
         self.train = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
@@ -163,8 +163,8 @@ class SIREN(nn.Module):
     """SIREN(n_in_features, n_out_features, hidden_layer_config, w0=30, ww=None, delay_init=False,
     activation='sine') — see /root/reference/src/model.py:48-113 for the parameter docs.
 
-    Extras (not in the reference): `precision` ('fp32' CUDA-core path, 'tc16' tcgen05 path; used for
-    queries) and `jet_order` (a hint: evaluate this derivative order already in forward so that a
+    Extras (not in the reference): `precision` ('fp32' CUDA-core path, 'tcx3' split-precision tcgen05 path with
+    fp32-grade results, 'tc16' single-pass tcgen05 path with 1e-3-class results; used for queries) and `jet_order` (a hint: evaluate this derivative order already in forward so that a
     following gradient()/hessian() costs nothing more)."""
 
     def __init__(self, n_in_features, n_out_features, hidden_layer_config=[], w0=30, ww=None, delay_init=False,
@@ -190,8 +190,8 @@ class SIREN(nn.Module):
             self.net[0].apply(first_layer_sine_init)
             self.net[1:].apply(lambda module: sine_init(module, self.ww))
         self.n_hidden = len(hidden_layer_config)
-        self.precision = "fp32"           # arithmetic of field queries: 'fp32' | 'tc16'
-        self.train_precision = "fp32"     # arithmetic of the fused losses / trainer
+        self.precision = "fp32"           # arithmetic of field queries: 'fp32' | 'tcx3' (split tensor-core, fp32-grade) | 'tc16'
+        self.train_precision = "fp32"     # arithmetic of the fused losses / trainer (same choices)
         self.jet_order = 0
         self._engine = None
 
@@ -207,16 +207,24 @@ class SIREN(nn.Module):
             out += [self.net[i][0].weight, self.net[i][0].bias]
         return out
 
-    def _engine_synced(self, need=3):
-        """The native engine with the weight images `need`ed up to date (1: fp32 path, 2: tensor-core path, 3: both)."""
+    def _engine_synced(self, need=7, reuse=False):
+        """The native engine with the weight images `need`ed up to date (bit 1: fp32 path, 2: single-pass tensor-core
+        images, 4: split tensor-core images; engine.NEED maps a precision to its bits).  reuse=True keeps images that were
+        built for the same parameter signature (see Engine.sync_weights)."""
         ws, bs = self._weights_biases()
         dev = ws[0].device
         if dev.type != "cuda":
             raise RuntimeError("diffudf_b200.SIREN has no CPU path: move the module to a CUDA (sm_100) device")
         if self._engine is None or self._engine.device != dev:
             self._engine = Engine(self.n_hidden, self.w0, self.ww, dev)
-        self._engine.sync_weights(ws, bs, need)
+        self._engine.sync_weights(ws, bs, need, reuse)
         return self._engine
+
+    def invalidate_weights(self):
+        """Call after writing parameters behind torch's back (`p.data.copy_()` and friends) while a loss forward is
+        pending; queries and new forwards re-read the parameters on their own."""
+        if self._engine is not None:
+            self._engine.invalidate()
 
     def forward(self, x):
         """x: (..., 3) coordinates.  Returns {'model_in': leaf copy of x, 'model_out': f(x) (..., 1)}

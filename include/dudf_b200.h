@@ -23,7 +23,9 @@ typedef struct dudf_ctx dudf_ctx;
 
 /* arithmetic of the hidden-layer contractions */
 #define DUDF_PRECISION_FP32 0  /* fp32 FFMA on CUDA cores; tolerance 1e-5 vs the fp64 oracle          */
-#define DUDF_PRECISION_TC16 1  /* tcgen05 MMA, fp16 operands, fp32 TMEM accumulation; tolerance 1e-3  */
+#define DUDF_PRECISION_TC16 1  /* tcgen05 MMA, fp16 operands, fp32 TMEM accumulation; 1e-3 class (f), 2e-3 (derivatives) */
+#define DUDF_PRECISION_TCX3 2  /* tcgen05 MMA, hi+lo fp16 operand split (3 MMAs per product), fp32-grade jets (1e-5);
+                                  training: split forward, single-pass reverse sweep / weight gradient (gradients 1e-3) */
 
 /* post-processing flags of the field queries */
 #define DUDF_Q_ABS_INV_TANH 1  /* f <- inv_tanh(|f|, alpha)            src/inverses.py:18-19, render_mc.py:71 */
@@ -51,6 +53,7 @@ int dudf_set_weights(dudf_ctx* ctx, const float* const* W_host, const float* con
  * (optimizer.step()): the fp32 transposes used by the CUDA-core forward and / or the fp16 tensor-core images. */
 #define DUDF_REFRESH_FP32 1
 #define DUDF_REFRESH_TC16 2
+#define DUDF_REFRESH_TCX3 4
 int dudf_bind_weights(dudf_ctx* ctx, const float* const* W_host, const float* const* b_host);
 int dudf_refresh_weights(dudf_ctx* ctx, int what, void* stream);
 
@@ -134,7 +137,7 @@ int dudf_cap_mesh(dudf_ctx* ctx, const float* df, const float* vecs, int N, floa
 /* evaluate() of src/evaluate.py:5-37 with HOST buffers: chunks of max_batch points, fp32 compute, results
  * widened to float64 on the device and copied into the caller's arrays (any of them may be NULL). */
 int dudf_evaluate_host(dudf_ctx* ctx, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
-                       double* H_host, int64_t max_batch, int precision);
+                       double* H_host, int64_t max_batch, int precision, void* stream);
 
 /* Training primitives.  loss_s1 / loss_s2 / loss_siren (src/loss_functions.py:82-155) followed by
  * train_loss.backward() (train.py:221) decompose into
@@ -195,7 +198,6 @@ typedef struct dudf_train_segment {
 #define DUDF_FUSED_DISCARD 1      /* drop consumed scratch lines from L2 instead of letting them be written back */
 #define DUDF_FUSED_IMG_EVICT_FIRST 2 /* operand-image stores carry an L2 evict-first hint */
 #define DUDF_FUSED_NO_WGRAD 4     /* stop after the fused launch; the caller runs dudf_jet_wgrad(…, amax_prev, …) itself */
-#define DUDF_FUSED_WARPS16 8      /* two independent sets of 8 epilogue warps (one per sub-tile) instead of one set of 8 */
 int64_t dudf_fused_scratch_bytes(const dudf_ctx* ctx);
 int dudf_train_step_fused(dudf_ctx* ctx, int mode, const dudf_train_segment* segs_host, int nseg, int64_t P_global,
                           const float* w_host, float alpha, double* terms, const float* amax_prev, float* amax_next, void* scratch,

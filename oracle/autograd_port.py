@@ -15,11 +15,13 @@ import numpy as np
 import torch
 
 
-def make_params(params_np, dtype=torch.float32, requires_grad=True):
+def make_params(params_np, dtype=torch.float32, requires_grad=True, device="cpu"):
+    """device="cuda:0" runs the same operation sequence as stock eager PyTorch on the GPU (bench.py's "reference on the same
+    B200" figure, SURVEY 8d last row); tests and the CPU baseline use the default."""
     out = []
     for W, b in params_np:
-        out.append((torch.tensor(np.asarray(W), dtype=dtype, requires_grad=requires_grad),
-                    torch.tensor(np.asarray(b), dtype=dtype, requires_grad=requires_grad)))
+        out.append((torch.tensor(np.asarray(W), dtype=dtype, requires_grad=requires_grad, device=device),
+                    torch.tensor(np.asarray(b), dtype=dtype, requires_grad=requires_grad, device=device)))
     return out
 
 
@@ -60,13 +62,13 @@ def loss_s1(params, x, normals, d, w, alpha):
         on = (d == 0).flatten()
         out["hessian_constraint"] = torch.where(on, 1 - cosv.abs(), torch.zeros_like(cosv)).mean() * w[2]
     else:
-        out["hessian_constraint"] = torch.zeros(1)[0]
+        out["hessian_constraint"] = torch.zeros(1, device=f.device)[0]
     if w[3] != 0:
         g = grad_of(f, coords)
         tgt = (t + d * alpha * (1 - t ** 2)).abs().squeeze(-1)
         out["grad_constraint"] = (torch.linalg.norm(g.squeeze(0), dim=-1) - tgt).abs().mean() * w[3]
     else:
-        out["grad_constraint"] = torch.zeros(1)[0]
+        out["grad_constraint"] = torch.zeros(1, device=f.device)[0]
     return out
 
 
@@ -77,7 +79,8 @@ def loss_s2(params, x, normals, d, w, alpha=None):
 
 
 def train_step(params, opt, x, normals, d, mode, w, alpha):
-    """optim.zero_grad(); loss; backward; optim.step() — returns the loss terms as floats."""
+    """optim.zero_grad(); loss; backward; optim.step() — returns the loss terms as floats (one host read-back each, as the
+    reference's .item() calls, train.py:227-233)."""
     opt.zero_grad()
     loss = loss_s1(params, x, normals, d, w, alpha) if mode == "s1" else loss_s2(params, x, normals, d, w, alpha)
     total = 0
@@ -98,17 +101,18 @@ def make_optimizer(params, lr):
 def evaluate(params, samples, want_grad=True, want_hess=False, max_batch=64 ** 2):
     """Chunked f / grad / Hessian query (src/evaluate.py) returning float64 numpy arrays."""
     n = samples.shape[0]
+    dev = params[0][0].device
     f_out = np.zeros((n, 1))
     g_out = np.zeros((n, 3)) if want_grad else None
     h_out = np.zeros((n, 3, 3)) if want_hess else None
     head = 0
     while head < n:
-        xs = torch.from_numpy(samples[head:head + max_batch]).float().unsqueeze(0)
+        xs = torch.from_numpy(samples[head:head + max_batch]).float().unsqueeze(0).to(dev)
         coords, f = field(params, xs)
         if want_grad:
-            g_out[head:head + max_batch] = grad_of(f, coords).squeeze(0).detach().numpy()
+            g_out[head:head + max_batch] = grad_of(f, coords).squeeze(0).detach().cpu().numpy()
         if want_hess:
-            h_out[head:head + max_batch] = hessian_of(f.squeeze(-1), coords)[0].detach().numpy()
-        f_out[head:head + max_batch] = f.squeeze(0).detach().numpy()
+            h_out[head:head + max_batch] = hessian_of(f.squeeze(-1), coords)[0].detach().cpu().numpy()
+        f_out[head:head + max_batch] = f.squeeze(0).detach().cpu().numpy()
         head += max_batch
     return f_out, g_out, h_out
