@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
-SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_tcx.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
+SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_tcx.cu", "dudf_mesh.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
 HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh", "dudf_mc_table.h",
            os.path.join(ROOT, "include", "dudf_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -48,6 +48,11 @@ SIGNATURES = {
     "dudf_sample_batch_pc": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, ctypes.POINTER(c_float),
                              ctypes.POINTER(c_float), ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p],
+    "dudf_mesh_distance": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
+    "dudf_sample_batch_mesh": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, ctypes.POINTER(c_float),
+                               ctypes.POINTER(c_float), ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p],
+    "dudf_mesh_sample_surface": [c_void_p, c_void_p, c_int64, c_int64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p],
     "dudf_nearest_distance": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
     "dudf_march_rays": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_int, c_int,
                         ctypes.POINTER(c_int64), c_void_p],

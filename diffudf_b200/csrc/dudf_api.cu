@@ -577,6 +577,36 @@ int dudf_sample_batch_pc(const float* surf_pts, const float* surf_normals, int64
   return sample_batch_pc(a, device_sms(), (cudaStream_t)stream);
 }
 
+int dudf_mesh_distance(const float* queries, int64_t n_q, const float* triangles, int64_t n_tri, float* dist, void* stream) {
+  DUDF_REQUIRE(queries && triangles && dist, "dudf_mesh_distance: null argument");
+  return mesh_distance(queries, n_q, triangles, n_tri, dist, device_sms(), (cudaStream_t)stream);
+}
+
+int dudf_sample_batch_mesh(const float* surf_pts, const float* surf_normals, int64_t n_surf, const float* triangles, int64_t n_tri,
+                           int64_t n_on, int64_t n_far, int64_t n_near, float sigma, const float* lo_host, const float* hi_host,
+                           uint64_t seed, uint64_t batch_index, const int64_t* on_idx, const float* far_pts, const int64_t* near_idx,
+                           const float* near_off, float* coords, float* normals, float* dist, void* stream) {
+  DUDF_REQUIRE(surf_pts && surf_normals && triangles && coords && normals && dist, "dudf_sample_batch_mesh: null argument");
+  DUDF_REQUIRE(n_surf > 0 && n_tri > 0 && n_on >= 0 && n_far >= 0 && n_near >= 0, "dudf_sample_batch_mesh: bad sizes");
+  DUDF_REQUIRE(n_near == 0 || n_on > 0, "dudf_sample_batch_mesh: near rows are displaced ON rows; n_on must be positive");
+  SampleArgs a;
+  a.surf_pts = surf_pts; a.surf_nrm = surf_normals; a.n_surf = n_surf; a.n_on = n_on; a.n_far = n_far; a.n_near = n_near;
+  a.sigma = sigma; a.seed = seed; a.batch = batch_index;
+  for (int k = 0; k < 3; ++k) { a.lo[k] = lo_host ? lo_host[k] : -1.f; a.hi[k] = hi_host ? hi_host[k] : 1.f; }
+  a.on_idx = on_idx; a.far_pts = far_pts; a.near_idx = near_idx; a.near_off = near_off;
+  a.coords = coords; a.normals = normals; a.dist = dist;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = sample_rows(a, st);
+  if (rc) return rc;
+  return mesh_distance(coords + n_on * 3, n_far + n_near, triangles, n_tri, dist + n_on, device_sms(), st);
+}
+
+int dudf_mesh_sample_surface(const float* triangles, const float* cdf, int64_t n_tri, int64_t n, uint64_t seed, const float* draws,
+                             float* points, float* normals, void* stream) {
+  DUDF_REQUIRE(triangles && cdf && points && normals, "dudf_mesh_sample_surface: null argument");
+  return mesh_sample_surface(triangles, cdf, n_tri, n, seed, draws, points, normals, (cudaStream_t)stream);
+}
+
 int dudf_nearest_distance(const float* queries, int64_t n_q, const float* cloud, int64_t n_x, float* dist, void* stream) {
   DUDF_REQUIRE(queries && cloud && dist, "dudf_nearest_distance: null argument");
   return nn_distance(queries, n_q, cloud, n_x, dist, device_sms(), (cudaStream_t)stream);

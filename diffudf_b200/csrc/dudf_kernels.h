@@ -112,6 +112,11 @@ struct SampleArgs {
   float* dist;              // out [P]
 };
 int sample_batch_pc(const SampleArgs& a, int sms, cudaStream_t st);
+int sample_rows(const SampleArgs& a, cudaStream_t st);       // positions / normals / |offset| only
+// ---- mesh half of the sampler (dudf_mesh.cu; src/dataset.py:14-70, src/preprocess_mesh.py:29-40) ----
+int mesh_distance(const float* q, int64_t nq, const float* tri, int64_t nt, float* dist, int sms, cudaStream_t st);
+int mesh_sample_surface(const float* tri, const float* cdf, int64_t nt, int64_t n, uint64_t seed, const float* draws, float* pts, float* nrm,
+                        cudaStream_t st);
 int nn_distance(const float* q, int64_t nq, const float* X, int64_t nx, float* dist, int sms, cudaStream_t st);
 // ---- device-resident query drivers (dudf_drivers.cu; src/render_st.py:136-172, src/render_pc.py:43-53) ----
 size_t drv_select_temp_bytes(int64_t R);

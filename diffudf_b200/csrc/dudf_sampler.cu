@@ -185,11 +185,19 @@ int nn_distance(const float* q, int64_t nq, const float* X, int64_t nx, float* d
   return 0;
 }
 
-int sample_batch_pc(const SampleArgs& a, int sms, cudaStream_t st) {
+int sample_rows(const SampleArgs& a, cudaStream_t st) {
   const int64_t P = a.n_on + a.n_far + a.n_near;
   if (P <= 0) return 0;
   sample_rows_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a);
   DUDF_LAUNCH_OK();
+  return 0;
+}
+
+int sample_batch_pc(const SampleArgs& a, int sms, cudaStream_t st) {
+  const int64_t P = a.n_on + a.n_far + a.n_near;
+  if (P <= 0) return 0;
+  int rc = sample_rows(a, st);
+  if (rc) return rc;
   return nn_distance(a.coords + a.n_on * 3, a.n_far, a.surf_pts, a.n_surf, a.dist + a.n_on, sms, st);
 }
 

@@ -1,9 +1,12 @@
-"""Drop-in for the point-cloud half of /root/reference/src/dataset.py: `PointCloud(onlyPCloud=True)` (:134-185),
-`sampleTrainingDataPC` (:80-131) and `shortestDistance` (:72-78), produced on the device by
-`dudf_sample_batch_pc` / `dudf_nearest_distance` (include/dudf_b200.h) — no host sampling, no host->device copy.
+"""Drop-in for /root/reference/src/dataset.py: `PointCloud` (:134-185) in both its modes, `sampleTrainingDataPC` (:80-131),
+`sampleTrainingData` (:14-70) and `shortestDistance` (:72-78), produced on the device by `dudf_sample_batch_pc` /
+`dudf_sample_batch_mesh` / `dudf_nearest_distance` / `dudf_mesh_distance` (include/dudf_b200.h) — no host sampling, no
+host->device copy.
 
-The mesh half (`sampleTrainingData`, Open3D RaycastingScene signed distances, :14-70) and `.ply` IO are not rebuilt
-(Open3D is a third-party consumer): construct from arrays.  Iterating yields the reference's triple
+Open3D (`.ply` IO, RaycastingScene) is a third-party consumer that is not rebuilt: construct from arrays (points + normals,
+and the triangle list for the mesh mode).  The mesh mode measures the UNSIGNED distance of every off-surface row to the
+triangles by brute force; Open3D's ray-parity sign is not reproduced (the losses are even in the distance, and the sign is
+undefined for the open surfaces DUDF targets).  Iterating yields the reference's triple
 `(coords (1, P, 3), normals (1, P, 3), sdf (1, P, 1))`, fp32, as CUDA tensors ordered [on | far | near]."""
 import ctypes
 
@@ -30,6 +33,65 @@ def shortestDistance(P, X):
         _lib.check(_lib.lib().dudf_nearest_distance(P.data_ptr(), P.shape[0], X.data_ptr(), X.shape[0], out.data_ptr(),
                                                     _lib.current_stream()), "dudf_nearest_distance")
     return out
+
+
+def _triangles(triangles, device):
+    """(n_tri, 3, 3) float32 CUDA tensor from a (n_tri, 3, 3) array or a (vertices (n,3), faces (m,3)) pair."""
+    if isinstance(triangles, (tuple, list)) and len(triangles) == 2:
+        V, F = triangles
+        V = torch.as_tensor(np.asarray(V) if not torch.is_tensor(V) else V)
+        F = torch.as_tensor(np.asarray(F) if not torch.is_tensor(F) else F).long()
+        triangles = V[F]
+    t = _as_dev(np.asarray(triangles) if not torch.is_tensor(triangles) else triangles, device)
+    if t.ndim != 3 or t.shape[1:] != (3, 3):
+        raise ValueError("triangles must have shape (n_tri, 3, 3)")
+    return t
+
+
+def meshDistance(P, triangles):
+    """Unsigned distance from each row of P (n, 3) to the triangle mesh (what |scene.compute_signed_distance| returns,
+    src/dataset.py:35,50) -> (n,) fp32."""
+    if P.device.type != "cuda":
+        raise RuntimeError("diffudf_b200.dataset.meshDistance needs CUDA (sm_100) tensors; there is no CPU fallback")
+    P = P.detach().to(torch.float32).contiguous()
+    T = _triangles(triangles, P.device)
+    out = torch.empty(P.shape[0], device=P.device, dtype=torch.float32)
+    if P.shape[0] == 0:
+        return out
+    with torch.cuda.device(P.device):
+        _lib.check(_lib.lib().dudf_mesh_distance(P.data_ptr(), P.shape[0], T.data_ptr(), T.shape[0], out.data_ptr(),
+                                                 _lib.current_stream()), "dudf_mesh_distance")
+    return out
+
+
+def sampleTrainingData(surface_pc, surface_normals, samplesOnSurface, samplesOffSurface, triangles, domainBounds=([-1, -1, -1], [1, 1, 1]),
+                       seed=0, batch_index=0, draws=None, sigma=0.01):
+    """One batch of the mesh mode (reference :14-70; `scene` becomes the triangle list): like sampleTrainingDataPC, with the
+    distance of the far AND the near rows measured to the mesh."""
+    dev = surface_pc.device
+    if dev.type != "cuda":
+        raise RuntimeError("diffudf_b200.dataset.sampleTrainingData needs the cloud on a CUDA (sm_100) device; there is no CPU fallback")
+    X = surface_pc.detach().to(torch.float32).contiguous()
+    N = surface_normals.detach().to(device=dev, dtype=torch.float32).contiguous()
+    T = _triangles(triangles, dev)
+    n_on, n_off = int(samplesOnSurface), int(samplesOffSurface)
+    n_far = n_off // 2
+    n_near = n_off - n_far
+    P = n_on + n_off
+    coords = torch.empty(1, P, 3, device=dev, dtype=torch.float32)
+    normals = torch.empty(1, P, 3, device=dev, dtype=torch.float32)
+    sdf = torch.empty(1, P, 1, device=dev, dtype=torch.float32)
+    d = draws or {}
+    keep = [_as_dev(d[k], dev, torch.int64 if k.endswith("idx") else torch.float32) if d.get(k) is not None else None
+            for k in ("on_idx", "far", "near_idx", "near_off")]
+    lo = (ctypes.c_float * 3)(*[float(v) for v in domainBounds[0]])
+    hi = (ctypes.c_float * 3)(*[float(v) for v in domainBounds[1]])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dudf_sample_batch_mesh(X.data_ptr(), N.data_ptr(), X.shape[0], T.data_ptr(), T.shape[0], n_on, n_far, n_near,
+                                                     float(sigma), lo, hi, int(seed) & (2 ** 64 - 1), int(batch_index), _lib.ptr(keep[0]),
+                                                     _lib.ptr(keep[1]), _lib.ptr(keep[2]), _lib.ptr(keep[3]), coords.data_ptr(),
+                                                     normals.data_ptr(), sdf.data_ptr(), _lib.current_stream()), "dudf_sample_batch_mesh")
+    return coords, normals, sdf
 
 
 def sampleTrainingDataPC(surface_pc, surface_normals, samplesOnSurface, samplesOffSurface, domainBounds=([-1, -1, -1], [1, 1, 1]),
@@ -65,9 +127,13 @@ class PointCloud(torch.utils.data.IterableDataset):
     """Iterable of device-generated batches; same attributes as the reference dataset (`batchesPerEpoch`,
     `samplesOnSurface`, `samplesFarSurface`) so the training loops take it unchanged."""
 
-    def __init__(self, points, normals, batchSize, samplingPercentiles, batchesPerEpoch, device, seed=0):
+    def __init__(self, points, normals, batchSize, samplingPercentiles, batchesPerEpoch, device, seed=0, triangles=None):
+        """triangles=None is the reference's onlyPCloud=True mode (distances to the cloud); with a triangle list
+        ((n_tri,3,3) or (vertices, faces)) the off-surface distances are measured to the mesh (onlyPCloud=False)."""
         super().__init__()
         self.device = torch.device(device)
+        self.onlyPCloud = triangles is None
+        self.triangles = None if triangles is None else _triangles(triangles, self.device)
         self.surface_pc = _as_dev(np.asarray(points) if not torch.is_tensor(points) else points, self.device)
         self.surface_normals = _as_dev(np.asarray(normals) if not torch.is_tensor(normals) else normals, self.device)
         if self.surface_pc.ndim != 2 or self.surface_pc.shape[1] != 3 or self.surface_pc.shape != self.surface_normals.shape:
@@ -81,7 +147,11 @@ class PointCloud(torch.utils.data.IterableDataset):
 
     def __iter__(self):
         for _ in range(self.batchesPerEpoch):
-            out = sampleTrainingDataPC(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
-                                       seed=self.seed, batch_index=self.batches_drawn)
+            if self.onlyPCloud:
+                out = sampleTrainingDataPC(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
+                                           seed=self.seed, batch_index=self.batches_drawn)
+            else:
+                out = sampleTrainingData(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
+                                         self.triangles, seed=self.seed, batch_index=self.batches_drawn)
             self.batches_drawn += 1
             yield out

@@ -227,6 +227,22 @@ int dudf_sample_batch_pc(const float* surf_pts, const float* surf_normals, int64
                          const int64_t* on_idx, const float* far_pts, const int64_t* near_idx, const float* near_off, float* coords,
                          float* normals, float* dist, void* stream);
 int dudf_nearest_distance(const float* queries, int64_t n_q, const float* cloud, int64_t n_x, float* dist, void* stream);
+/* ---- Mesh half of the batch sampler (src/dataset.py:14-70, PointCloud(onlyPCloud=False); src/preprocess_mesh.py:29-40) ----
+ * dudf_mesh_distance replaces scene.compute_signed_distance (Open3D RaycastingScene, :35,50) by the UNSIGNED distance
+ * dist[i] = min_t |q_i - triangle_t| (brute force; the losses are even in the distance and the ray-parity sign is undefined
+ * for open surfaces).  triangles: [n_tri][3 vertices][3] fp32, device.
+ * dudf_sample_batch_mesh writes one [n_on | n_far | n_near] batch like dudf_sample_batch_pc, with the distance of ALL
+ * off-surface rows (far and near) measured to the mesh, as sampleTrainingData does.
+ * dudf_mesh_sample_surface replaces mesh.sample_points_uniformly(n, use_triangle_normal=True): triangle by inverse CDF of the
+ * areas (cdf: [n_tri] inclusive prefix sums / total, device), barycentric (1 - sqrt r1, sqrt r1 (1 - r2), sqrt r1 r2), triangle
+ * normal.  draws ([n][3] = u_triangle, r1, r2 in [0,1)) may be NULL (Philox keyed by seed). */
+int dudf_mesh_distance(const float* queries, int64_t n_q, const float* triangles, int64_t n_tri, float* dist, void* stream);
+int dudf_sample_batch_mesh(const float* surf_pts, const float* surf_normals, int64_t n_surf, const float* triangles, int64_t n_tri,
+                           int64_t n_on, int64_t n_far, int64_t n_near, float sigma, const float* lo_host, const float* hi_host,
+                           uint64_t seed, uint64_t batch_index, const int64_t* on_idx, const float* far_pts, const int64_t* near_idx,
+                           const float* near_off, float* coords, float* normals, float* dist, void* stream);
+int dudf_mesh_sample_surface(const float* triangles, const float* cdf, int64_t n_tri, int64_t n, uint64_t seed, const float* draws,
+                             float* points, float* normals, void* stream);
 /* torch.optim.Adam.step as configured in train.py:334-337 (betas, eps given explicitly, no weight decay);
  * t is the 1-based step count.  Flat fp32 arrays of n elements. */
 int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
