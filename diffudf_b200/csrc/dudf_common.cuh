@@ -69,6 +69,28 @@ __device__ __forceinline__ void sincos_fast(float x, float& s, float& c) {
   c = __cosf(r);
 }
 
+// fp32-grade variant without MUFU (split-precision tensor-core path): Cody-Waite reduction by pi/2 (FMA, two-term), the
+// published single-precision minimax polynomials on [-pi/4, pi/4] (Cephes sinf / cosf coefficients), quadrant by the low
+// bits of the rounded quotient.  ~1 ulp for |x| < 1e3; ~22 FMA-pipe / ALU instructions.
+__device__ __forceinline__ void sincos_poly(float x, float& s, float& c) {
+  const float t = fmaf(x, 0.63661977236758134f, 12582912.f);       // 1.5 * 2^23: the quotient rounded to nearest in the low bits
+  const int qi = __float_as_int(t);
+  const float q = t - 12582912.f;
+  float r = fmaf(q, -1.57079637050628662109375f, x);
+  r = fmaf(q, 4.37113882867379e-8f, r);                              // pi/2 = 1.5707963705062866 - 4.37113882867379e-8
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  const float sr = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  const float cr = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const bool swap = (qi & 1) != 0;
+  const float ss = swap ? cr : sr, cc = swap ? sr : cr;
+  s = __int_as_float(__float_as_int(ss) ^ ((qi & 2) << 30));
+  c = __int_as_float(__float_as_int(cc) ^ (((qi + 1) & 2) << 30));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Symmetric 3x3 eigen-decomposition by cyclic Jacobi rotations (ascending eigenvalues, like
 // torch.linalg.eigh / np.linalg.eigh used at src/loss_functions.py:142, src/render_st.py:59,

@@ -82,13 +82,18 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 // ---- producer: 16 chunks per layer, in consumption order ----
 template <int CL>
 __device__ __forceinline__ void tcx_producer(const unsigned char* packed, unsigned char* ring, uint64_t* full, uint64_t* empty, int64_t rounds,
-                                             int n_phase, uint32_t cta_rank) {
+                                             int n_phase, uint32_t cta_rank, int dbg) {
   uint32_t stage = 0, phase = 0, chunk = 0;
   for (int64_t r = 0; r < rounds; ++r)
     for (int j = 0; j < n_phase; ++j) {
       const unsigned char* src = packed + (size_t)j * TCX_LAYER_CHUNKS * TC_CHUNK_BYTES;
       for (int ck = 0; ck < TCX_LAYER_CHUNKS; ++ck, ++chunk) {
         mbar_wait_relaxed(&empty[stage], phase ^ 1, 0x1100 + stage);
+        if ((dbg & 4) && chunk >= (uint32_t)TCX_STAGES) {          // diagnostics: stale weights, no L2 -> SM traffic
+          mbar_arrive(&full[stage]);
+          if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_arrive_expect_tx(&full[stage], TC_CHUNK_BYTES);
         if constexpr (CL == 1) {
           bulk_g2s(ring + stage * TC_CHUNK_BYTES, src + (size_t)ck * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full[stage]);
@@ -109,7 +114,8 @@ __device__ __forceinline__ void tcx_producer(const unsigned char* packed, unsign
 template <int CL>
 __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
                                              uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, int64_t ntiles,
-                                             unsigned char* img, int64_t ncb, int64_t cb0, uint64_t img_policy) {
+                                             unsigned char* img, int64_t ncb, int64_t cb0, uint64_t img_policy, int dbg) {
+  const bool skip = (dbg & 2) != 0;
   constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
   constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
   const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
@@ -149,12 +155,14 @@ __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* 
             const uint32_t koff = (uint32_t)(kh * 2 + kb) * 8192u;
             mbar_wait(&full[stage], phase, 0x1300 + stage);                    // hi chunk: against the hi and the lo tile
             const uint64_t a_hi = desc_advance(a_desc0, stage * TC_CHUNK_BYTES);
-            mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), idesc, (kh | kb) != 0);
-            mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bl_desc0, koff), idesc, 1);
+            if (!skip) {
+              mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), idesc, (kh | kb) != 0);
+              mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bl_desc0, koff), idesc, 1);
+            }
             release(stage);
             if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
             mbar_wait(&full[stage], phase, 0x1300 + stage);                    // lo chunk: against the hi tile
-            mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(bh_desc0, koff), idesc, 1);
+            if (!skip) mma_f16_ss_k64_warp(d_tmem, desc_advance(a_desc0, stage * TC_CHUNK_BYTES), desc_advance(bh_desc0, koff), idesc, 1);
             release(stage);
             if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -235,12 +243,14 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   float* Ust;
   unsigned char* Aimg;
   int64_t ld, col0;
-};
+  int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
+};                        //   8 no tile stores
 
 // all layers of one 128-column tile.  x == null: grid points (first + p).  TRAIN: stash the pre-activations, write raw channels.
-template <int NCH, bool TRAIN>
+template <int NCH, bool TRAIN, int SC>
 __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const float* __restrict__ x, int64_t P, int gridN, int64_t grid_first,
-                                         float vs, int64_t tile, bool valid, const QueryOut& out, float* outp, float* Ust, int64_t ld, int64_t colt) {
+                                         float vs, int64_t tile, bool valid, const QueryOut& out, float* outp, float* Ust, int64_t ld, int64_t colt,
+                                         int dbg) {
   using C = TcxCfg<NCH>;
   constexpr int GC = C::GC;
   const int L = net.n_lin - 1;
@@ -293,14 +303,17 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
         if constexpr (TRAIN) {
           if (valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + colt) * 256 + n * 4 + (size_t)g * GC * 256);
         }
+        if (!(dbg & 1)) {
 #pragma unroll
-        for (int pp = 0; pp < GC / NCH; ++pp) {
-          float sn, cs;
-          sincos_fast(u[pp * NCH], sn, cs);
-          tc_act_point<NCH>(u + pp * NCH, sn, cs);
+          for (int pp = 0; pp < GC / NCH; ++pp) {
+            float sn, cs;
+            if constexpr (SC == 1) sincos_poly(u[pp * NCH], sn, cs);
+            else sincos_fast(u[pp * NCH], sn, cs);
+            tc_act_point<NCH>(u + pp * NCH, sn, cs);
+          }
         }
         if (l < L - 1) {
-          tcx_store_group<GC>(u, row_hi, g * (GC / 8), r7);
+          if (!(dbg & 8)) tcx_store_group<GC>(u, row_hi, g * (GC / 8), r7);
         } else {
           // output layer (256 -> 1 per channel) on the fp32 activations: this warp's 32 neurons, reduced over its lanes
 #pragma unroll
@@ -347,7 +360,7 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
 
 // One launch serves up to two row segments with different jet orders (training: on-surface rows carry the Hessian jet).
 // Queries use segment a only (x == null: grid points).
-template <int NA, int NB, int CL, bool TRAIN>
+template <int NA, int NB, int CL, bool TRAIN, int SC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev sa, SegDev sb, int64_t tiles_a, int64_t tiles_b, int gridN,
                    int64_t grid_first, QueryOut out, TcxTrain tr) {
@@ -382,10 +395,10 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
   if (warp >= 8) {
     setmaxnreg_dec<TC_REGS_AUX>();
     if (warp == 8) {
-      if (lane == 0) tcx_producer<CL>(packed, ring, full, empty, rounds, L - 1, CL > 1 ? cluster_ctarank() : 0u);
+      if (lane == 0) tcx_producer<CL>(packed, ring, full, empty, rounds, L - 1, CL > 1 ? cluster_ctarank() : 0u, tr.dbg);
     } else if (warp == 9) {
       tcx_mma_role<CL>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, ntiles, TRAIN ? tr.Aimg : nullptr,
-                       tr.ld >> 6, tr.col0 >> 6, TRAIN ? l2_policy_evict_first() : 0ull);
+                       tr.ld >> 6, tr.col0 >> 6, TRAIN ? l2_policy_evict_first() : 0ull, tr.dbg);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -401,9 +414,9 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
       const bool valid = tile < ntiles;
       const int64_t colt = tr.col0 + tile * 128;
       if (!valid || tile < tiles_a) {
-        tcx_tile<NA, TRAIN>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt);
+        tcx_tile<NA, TRAIN, SC>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, tr.dbg);
       } else {
-        if constexpr (NB > 0) tcx_tile<NB, TRAIN>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt);
+        if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, tr.dbg);
       }
     }
   }
@@ -414,19 +427,19 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
 }
 
 static int tcx_cluster_size() {
-  static int v = -1;            // DUDF_TCX_CLUSTER=1|2|4 overrides the cluster size (default 2: halves the L2 reads of the weight stream)
+  static int v = -1;            // DUDF_TCX_CLUSTER=1|2 overrides the cluster size (default 2: halves the L2 reads of the weight stream)
   if (v < 0) {
     const char* e = getenv("DUDF_TCX_CLUSTER");
     const int c = e ? atoi(e) : 2;
-    v = (c == 1 || c == 2 || c == 4) ? c : 2;
+    v = (c == 1 || c == 2) ? c : 2;
   }
   return v;
 }
 
-template <int NA, int NB, int CL, bool TRAIN>
+template <int NA, int NB, int CL, bool TRAIN, int SC>
 static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
                       const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
-  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN>;
+  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN, SC>;
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
   const int64_t ntiles = ta + tb;
   int grid = (int)std::min<int64_t>(ntiles, sms);
@@ -450,14 +463,35 @@ static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, c
   return 0;
 }
 
+// sine / cosine of the epilogue: 1 (default) = FMA-only polynomials, ~1e-7 (fp32-grade jets); 0 = MUFU after an explicit
+// reduction, 4e-7 (DUDF_TCX_SINCOS=mufu; faster for value-only queries, jets at ~1e-5)
+static int tcx_sincos_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DUDF_TCX_SINCOS");
+    v = (e && strcmp(e, "mufu") == 0) ? 0 : 1;
+  }
+  return v;
+}
+static int tcx_dbg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DUDF_TCX_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <int NA, int NB, bool TRAIN>
 static int tcx_launch_cl(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
-                         const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
+                         const QueryOut& out, const TcxTrain& tr0, int sms, cudaStream_t st) {
   int cl = tcx_cluster_size();
   while (cl > 1 && ta + tb < 2 * cl) cl >>= 1;
-  if (cl == 4) return tcx_launch<NA, NB, 4, TRAIN>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
-  if (cl == 2) return tcx_launch<NA, NB, 2, TRAIN>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
-  return tcx_launch<NA, NB, 1, TRAIN>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  TcxTrain tr = tr0;
+  tr.dbg = tcx_dbg();
+  if (tcx_sincos_mode() == 0) {
+    if (cl >= 2) return tcx_launch<NA, NB, 2, TRAIN, 0>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+    return tcx_launch<NA, NB, 1, TRAIN, 0>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  }
+  if (cl >= 2) return tcx_launch<NA, NB, 2, TRAIN, 1>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  return tcx_launch<NA, NB, 1, TRAIN, 1>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
 }
 
 int tcx_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN, int64_t grid_first, const QueryOut& out,
@@ -495,7 +529,7 @@ int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* s
   const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
   const int64_t ta = 2 * a.npairs, tb = 2 * b.npairs;       // whole pairs: the reverse sweep reads the stash of a padding sub-tile too
   DUDF_REQUIRE(col0 + (ta + tb) * 128 <= ld, "tensor-core stash too small");
-  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0};
+  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0, 0};
   QueryOut out;
   memset(&out, 0, sizeof(out));
   if (nb == 0) {

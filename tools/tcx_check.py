@@ -67,6 +67,19 @@ if "rates" in what:
         vecs = torch.empty(N ** 3, 3, device="cuda")
         ms = timed(lambda: eng.query_grid(N, 0, N ** 3, prec, flags=3, alpha=100.0, out=(df, vecs)), 3)
         print(f"rate {prec} grid {N}^3 (f, grad): {ms:8.3f} ms {N ** 3 / ms / 1e3:8.1f} M q/s {N ** 3 * F[1] / ms / 1e9:7.1f} TFLOP/s", flush=True)
+if "grid" in what:          # one line per process: used by the probe loop over DUDF_TCX_* environment settings
+    params, m = load("trained")
+    eng = m._engine_synced()
+    N = 256
+    df = torch.empty(N ** 3, device="cuda")
+    vecs = torch.empty(N ** 3, 3, device="cuda")
+    ms = timed(lambda: eng.query_grid(N, 0, N ** 3, "tcx3", flags=3, alpha=100.0, out=(df, vecs)), 3)
+    xq = torch.rand(1 << 20, 3, device="cuda") * 2 - 1
+    ms0 = timed(lambda: eng.query(xq, 0, "tcx3"), 10)
+    ms2 = timed(lambda: eng.query(xq, 2, "tcx3"), 5)
+    env = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("DUDF_TCX"))
+    print(f"probe [{env}] grid256 (f,grad) {ms:8.2f} ms {N ** 3 / ms / 1e3:7.1f} M q/s | value 1M {ms0:6.3f} ms {(1 << 20) / ms0 / 1e3:7.1f} M q/s | "
+          f"hess 1M {ms2:6.2f} ms {(1 << 20) / ms2 / 1e3:6.1f} M q/s", flush=True)
 if "train" in what:
     shape = synthetic.make_shape(0)
     sp, sn = shape.sample_surface(200000, np.random.default_rng(0))
