@@ -79,6 +79,7 @@ SIGNATURES = {
     "dudf_jet_backward": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                           ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_void_p],
     "dudf_jet_wgrad": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, ctypes.POINTER(c_void_p), c_int, c_void_p],
+    "dudf_jet_wgrad_layers": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p],
     "dudf_loss": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, ctypes.POINTER(c_float), c_float,
                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "dudf_loss_s2_stats": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p],

@@ -486,6 +486,18 @@ int dudf_jet_backward(dudf_ctx* c, const float* x, int64_t P, int order, const f
   return dudf_jet_backward_multi(c, &s, 1, seed_absmax, Z, Zb, ld, gW, gb, precision, stream);
 }
 
+int dudf_jet_wgrad_layers(dudf_ctx* c, const void* Zb, const void* A, int64_t ld, const float* seed_absmax, float* const* gW, int layer_lo,
+                          int layer_hi, int precision, void* stream) {
+  DUDF_REQUIRE(c && Zb && A && gW, "dudf_jet_wgrad_layers: null argument");
+  DUDF_REQUIRE(precision == DUDF_PRECISION_TC16 || precision == DUDF_PRECISION_TCX3, "dudf_jet_wgrad_layers: tensor-core precisions only");
+  DUDF_REQUIRE(layer_lo >= 1 && layer_hi <= c->n_lin - 1 && layer_lo <= layer_hi, "dudf_jet_wgrad_layers: layer range [%d, %d) outside [1, %d)",
+               layer_lo, layer_hi, c->n_lin - 1);
+  GradView gv;
+  int rc = fill_grad_view(c, gW, nullptr, gv, "dudf_jet_wgrad_layers");
+  if (rc) return rc;
+  return tc_train_wgrad(c->view(), gv, Zb, A, ld, seed_absmax, c->sms, (cudaStream_t)stream, layer_lo, layer_hi);
+}
+
 int dudf_jet_wgrad(dudf_ctx* c, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax, float* const* gW,
                    int precision, void* stream) {
   DUDF_REQUIRE(c && Zb && A && gW, "dudf_jet_wgrad: null argument");

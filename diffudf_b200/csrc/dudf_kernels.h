@@ -94,7 +94,7 @@ int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* s
 int tc_train_backward(const void* packed, const NetView& net, const GradView& grad, const TcSegment* segs, int nseg,
                       const float* seed_absmax, const float* Ust, void* Zimg, int64_t ld, int64_t col0, int sms, cudaStream_t st);
 int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,
-                   int sms, cudaStream_t st);
+                   int sms, cudaStream_t st, int layer_lo = 0, int layer_hi = 0);
 // ---- device-side batch sampler for oriented point clouds (dudf_sampler.cu; src/dataset.py:72-131) ----
 struct SampleArgs {
   const float* surf_pts;    // [n_surf][3]

@@ -393,14 +393,14 @@ constexpr int TW_SMEM = TW_STAGES * 2 * TC_IMG_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(192, 1)
 tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const unsigned char* __restrict__ Aimg, int64_t ncb, int splits,
-                float ww, const float* __restrict__ seed_absmax) {
+                float ww, const float* __restrict__ seed_absmax, int layer0) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + TW_STAGES * 2 * TC_IMG_BYTES);
   uint64_t *full = bars, *empty = bars + TW_STAGES, *done = bars + 2 * TW_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TW_STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int l = 1 + blockIdx.x / splits;
+  const int l = layer0 + blockIdx.x / splits;
   const int split = blockIdx.x % splits;
   const int64_t per = (ncb + splits - 1) / splits;
   const int64_t cb0 = split * per, cb1 = min(ncb, cb0 + per);
@@ -550,18 +550,24 @@ int tc_train_backward(const void* packed, const NetView& net, const GradView& gr
   DUDF_REQUIRE(false, "tensor-core training: unsupported segment channel counts (%d, %d)", na, nb);
 }
 
+// layers [layer_lo, layer_hi) of the hidden 256 x 256 matrices (1 .. L-1); the whole grid is spent on that range, so a caller can
+// launch the layers in groups and hand each finished group to the gradient all-reduce while the next one runs
 int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, const void* Aimg, int64_t ld, const float* seed_absmax,
-                   int sms, cudaStream_t st) {
+                   int sms, cudaStream_t st, int layer_lo, int layer_hi) {
   const int L = net.n_lin - 1;
   if (L < 2 || ld <= 0) return 0;
+  if (layer_lo <= 0) layer_lo = 1;
+  if (layer_hi <= 0 || layer_hi > L) layer_hi = L;
+  if (layer_hi <= layer_lo) return 0;
   DUDF_REQUIRE(ld % 64 == 0, "tensor-core stash: ld must be a multiple of 64");
   DUDF_REQUIRE(seed_absmax != nullptr, "tensor-core weight gradient needs the seed magnitude (loss scale)");
   const int64_t ncb = ld / 64;
-  int splits = std::max(1, sms / (L - 1));
+  const int nl = layer_hi - layer_lo;
+  int splits = std::max(1, sms / nl);
   splits = (int)std::min<int64_t>(splits, ncb);
   DUDF_CUDA_OK(cudaFuncSetAttribute(tt_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
-  tt_wgrad_kernel<<<(L - 1) * splits, 192, TW_SMEM, st>>>(grad, (const unsigned char*)Zimg, (const unsigned char*)Aimg, ncb, splits, net.ww,
-                                                         seed_absmax);
+  tt_wgrad_kernel<<<nl * splits, 192, TW_SMEM, st>>>(grad, (const unsigned char*)Zimg, (const unsigned char*)Aimg, ncb, splits, net.ww,
+                                                    seed_absmax, layer_lo);
   DUDF_LAUNCH_OK();
   return 0;
 }

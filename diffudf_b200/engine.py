@@ -228,6 +228,13 @@ class Engine:
             _lib.check(self.L.dudf_jet_wgrad(self.h, Zb.data_ptr(), A.data_ptr(), ld, ncols, _lib.ptr(seed_absmax), _ptr_array(gW),
                                              PRECISIONS[precision], _lib.current_stream()), "dudf_jet_wgrad")
 
+    def jet_wgrad_layers(self, Zb, A, ld, gW, layer_lo, layer_hi, precision="tc16", seed_absmax=None):
+        """weight gradients of the hidden layers [layer_lo, layer_hi) only (tensor-core precisions)"""
+        with torch.cuda.device(Zb.device):
+            _lib.check(self.L.dudf_jet_wgrad_layers(self.h, Zb.data_ptr(), A.data_ptr(), ld, _lib.ptr(seed_absmax), _ptr_array(gW),
+                                                    int(layer_lo), int(layer_hi), PRECISIONS[precision], _lib.current_stream()),
+                       "dudf_jet_wgrad_layers")
+
     def fused_scratch_bytes(self):
         return int(self.L.dudf_fused_scratch_bytes(self.h))
 

@@ -158,6 +158,10 @@ int dudf_jet_backward(dudf_ctx* ctx, const float* x, int64_t P, int order, const
                       int precision, void* stream);
 int dudf_jet_wgrad(dudf_ctx* ctx, const void* Zb, const void* A, int64_t ld, int64_t ncols, const float* seed_absmax,
                    float* const* gW_host, int precision, void* stream);
+/* The same contraction for the hidden layers [layer_lo, layer_hi) only (1 <= layer_lo <= layer_hi <= n_hidden), tensor-core
+ * precisions: lets a data-parallel caller launch the layers in groups and all-reduce each finished group while the next runs. */
+int dudf_jet_wgrad_layers(dudf_ctx* ctx, const void* Zb, const void* A, int64_t ld, const float* seed_absmax, float* const* gW,
+                          int layer_lo, int layer_hi, int precision, void* stream);
 /* Several row segments of one batch in one call (one launch on the tensor-core path, which balances its persistent
  * grid over all segments): loss_s1 evaluates the Hessian jet (order 2) on the on-surface rows and the gradient jet on
  * the others.  Tensor-core path: at most 2 segments, contiguous stash columns, the order-2 segment first. */

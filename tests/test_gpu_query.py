@@ -1,7 +1,9 @@
 """Parity of the field queries (f, grad f, Hessian, third derivatives) against the fp64 oracle and the
 reference's own fp32 outputs (golden fixtures).  Tolerances (max|err| / max|ref|, BASELINE.md's measure):
-fp32 CUDA-core path 2e-5 (north_star: 1e-5-class fp32 path; the reference's fp32 run itself sits at 2.6e-6
-from fp64), tcgen05 fp16-operand path 1e-3 in relative L2 and 4e-3 in the max measure."""
+fp32 CUDA-core path 1e-5 (north_star's fp32 tolerance; measured 2e-7..5e-6, the reference's own fp32 run sits at 2.6e-6
+from fp64).  The single-pass fp16-operand tcgen05 path (tc16) is the NON-conforming fast mode: 1e-3 in relative L2 on
+trained weights, 2.5e-3 at the SIREN init, 4e-3 in the max measure — documented, not the bar; the conforming tensor-core
+mode is tcx3 (tests/test_gpu_tcx3.py)."""
 import numpy as np
 import pytest
 import torch
@@ -37,14 +39,14 @@ def test_fp32_query_matches_oracle(tag, order, golden, oracle, weights, cuda_mod
         Tref = np.stack([Tr[:, a, b, c] for a, b, c in idx], 1)
         e["T"] = rel_max(T, Tref)
     print(f"fp32 {tag} order {order}: {e}")
-    assert all(v < 2e-5 for v in e.values()), e
+    assert all(v < 1e-5 for v in e.values()), e
 
 
 @pytest.mark.parametrize("tag", ["init", "trained"])
 def test_fp32_query_matches_reference_fixture(tag, golden, cuda_models):
     J = golden(f"jets_{tag}.npz")
     f, g, H, _ = _query(cuda_models[tag], J["x"], 2, "fp32")
-    assert rel_max(f, J["f32"]) < 2e-5 and rel_max(g, J["g32"]) < 2e-5 and rel_max(H, J["H32"]) < 2e-5
+    assert rel_max(f, J["f32"]) < 1e-5 and rel_max(g, J["g32"]) < 1e-5 and rel_max(H, J["H32"]) < 1e-5
 
 
 @pytest.mark.parametrize("tag", ["init", "trained"])
@@ -74,7 +76,7 @@ def test_ragged_sizes(P, precision, oracle, weights, cuda_models):
     x = rng.uniform(-1, 1, (P, 3)).astype(np.float32)
     ref = oracle.siren_jet(weights["trained"], x, 1)
     f, g, _, _ = _query(cuda_models["trained"], x, 1, precision)
-    tol = 2e-5 if precision == "fp32" else 4e-3
+    tol = 1e-5 if precision == "fp32" else 4e-3
     assert np.max(np.abs(f - ref["f"])) <= tol * max(np.max(np.abs(ref["f"])), 1e-3)
     assert np.max(np.abs(g - ref["g"])) <= tol * np.max(np.abs(ref["g"]))
 
@@ -95,7 +97,7 @@ def test_shallow_network_and_state_dict_roundtrip(oracle):
     params = oracle.params_from_state_dict(sd)
     x = np.random.default_rng(0).uniform(-1, 1, (300, 3)).astype(np.float32)
     ref = oracle.siren_jet(params, x, 2)
-    for prec, tol in (("fp32", 2e-5), ("tc16", 4e-3)):
+    for prec, tol in (("fp32", 1e-5), ("tcx3", 2e-5), ("tc16", 4e-3)):
         f, g, H, _ = _query(m, x, 2, prec)
         assert rel_max(f, ref["f"]) < tol and rel_max(g, ref["g"]) < tol and rel_max(H, ref["H"]) < tol
     m2 = SIREN(3, 1, [256] * 4, w0=30, delay_init=True).cuda()
@@ -118,9 +120,9 @@ def test_dropin_forward_gradient_hessian(tag, golden, cuda_models):
     g = gradient(y, x)
     H = hessian(y, x)
     assert g.shape == (1, 512, 3) and H.shape == (1, 512, 3, 3)
-    assert rel_max(y.detach().cpu().numpy()[0, :, 0], J["f32"]) < 2e-5
-    assert rel_max(g.detach().cpu().numpy()[0], J["g32"]) < 2e-5
-    assert rel_max(H.detach().cpu().numpy()[0], J["H32"]) < 2e-5
+    assert rel_max(y.detach().cpu().numpy()[0, :, 0], J["f32"]) < 1e-5
+    assert rel_max(g.detach().cpu().numpy()[0], J["g32"]) < 1e-5
+    assert rel_max(H.detach().cpu().numpy()[0], J["H32"]) < 1e-5
 
 
 def test_unsupported_inputs_raise(cuda_models):
