@@ -15,6 +15,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
 SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_tcx.cu", "dudf_mesh.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
+HOST_SOURCES = ["meshudf_mc.cpp"]            # plain C++17 (no CUDA): g++, strict IEEE arithmetic (no contraction)
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"]
 HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh", "dudf_mc_table.h",
            os.path.join(ROOT, "include", "dudf_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -28,6 +30,12 @@ c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int6
 class Segment(ctypes.Structure):
     """struct dudf_segment of include/dudf_b200.h"""
     _fields_ = [("x", c_void_p), ("rows", c_int64), ("order", c_int), ("packed", c_void_p), ("seeds", c_void_p), ("col0", c_int64)]
+
+
+class MeshResult(ctypes.Structure):
+    """struct dudf_meshudf_result of include/dudf_b200.h"""
+    _fields_ = [("vertices", c_void_p), ("normals", c_void_p), ("values", c_void_p), ("faces", c_void_p), ("n_vertices", c_int64),
+                ("n_faces", c_int64)]
 
 
 class TrainSegment(ctypes.Structure):
@@ -85,6 +93,11 @@ SIGNATURES = {
     "dudf_loss_s2_stats": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "dudf_loss_s2_finish": [c_void_p, c_float, c_float, c_void_p, c_void_p],
     "dudf_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64, c_void_p],
+    "dudf_adam_step_guarded": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64, c_void_p,
+                               c_void_p, c_void_p],
+    "dudf_scale_guard": [c_void_p, c_void_p, c_float, c_void_p, c_void_p],
+    "dudf_meshudf_mc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p],
+    "dudf_meshudf_free": [c_void_p],
     "dudf_selftest_umma": [c_int, ctypes.POINTER(c_float)],
 }
 
@@ -93,7 +106,7 @@ def _needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HOST_SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -112,13 +125,17 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s in HOST_SOURCES:
+        obj = os.path.join(objdir, s.replace(".cpp", ".o"))
+        cmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for s, obj, p in procs:
         out, _ = p.communicate()
         with open(os.path.join(objdir, s + ".log"), "w") as fh:
             fh.write(out)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {s}:\n{out}")
+            raise RuntimeError(f"compiler failed for {s}:\n{out}")
         if verbose:
             print(out)
         objs.append(obj)

@@ -631,6 +631,18 @@ int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream);
 }
 
+int dudf_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                           int64_t t, const float* unsafe_flag, int64_t* skipped, void* stream) {
+  DUDF_REQUIRE(p && g && m && v && unsafe_flag, "dudf_adam_step_guarded: null argument");
+  DUDF_REQUIRE(t >= 1, "dudf_adam_step_guarded: step count must be >= 1");
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream, unsafe_flag, (long long*)skipped);
+}
+
+int dudf_scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, void* stream) {
+  DUDF_REQUIRE(amax_prev && amax_next && flag, "dudf_scale_guard: null argument");
+  return scale_guard(amax_prev, amax_next, limit, flag, (cudaStream_t)stream);
+}
+
 int dudf_selftest_umma(int variant, float* max_err_host) {
   DUDF_REQUIRE(max_err_host != nullptr, "dudf_selftest_umma: null output");
   return tc_selftest(variant, max_err_host, 0);

@@ -140,8 +140,9 @@ int cap_emit(const float* df, const unsigned char* code, int N, const long long*
 int loss_seeds(const LossArgs& a, cudaStream_t st);
 int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream_t st);
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);
-int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-              int64_t t, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
+              cudaStream_t st, const float* unsafe = nullptr, long long* skipped = nullptr);
+int scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, cudaStream_t st);
 int transpose256(const float* W, float* Wt, cudaStream_t st);
 int eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,
                 cudaStream_t st);

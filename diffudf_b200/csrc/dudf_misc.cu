@@ -121,9 +121,18 @@ int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream
 // ---------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam defaults used by train.py:334-337)
 // ---------------------------------------------------------------------------------------------
+// unsafe / skipped (optional): the fused tensor-core step scales its fp16 adjoints with the PREVIOUS step's seed magnitude; when
+// this step's seeds outgrew that scale (scale_guard_kernel below, summed over the ranks by the gradient all-reduce) the gradient
+// may hold saturated adjoints, so the update is skipped on every rank — what torch.cuda.amp.GradScaler does on overflow — and
+// counted.  The next step's scale comes from this step's magnitude, so at most one step is lost per jump.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float step_size, float bc2_sqrt,
-                                                   float b1, float b2, float eps) {
+                                                   float b1, float b2, float eps, const float* __restrict__ unsafe,
+                                                   long long* __restrict__ skipped) {
+  if (unsafe && *unsafe != 0.f) {
+    if (skipped && blockIdx.x == 0 && threadIdx.x == 0) *skipped += 1;
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
@@ -136,12 +145,26 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
-              cudaStream_t st) {
+              cudaStream_t st, const float* unsafe, long long* skipped) {
   if (n <= 0) return 0;
   const double bc1 = 1.0 - pow((double)b1, (double)t);
   const double bc2 = 1.0 - pow((double)b2, (double)t);
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)sqrt(bc2), b1, b2, eps);
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)sqrt(bc2), b1, b2, eps, unsafe, skipped);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
+// flag += 1 when the seeds of this step, under the loss scale derived from the previous step's magnitude, exceed `limit`
+// (nominal range of S * max|seed| is (1024, 2048]; fp16 saturates at 65504)
+__global__ void scale_guard_kernel(const float* __restrict__ amax_prev, const float* __restrict__ amax_next, float limit,
+                                   float* __restrict__ flag) {
+  const float mp = *amax_prev, mn = *amax_next;
+  const float S = (mp > 0.f && isfinite(mp)) ? exp2f(floorf(log2f(2048.f / mp))) : 1.f;      // loss_scale_from()
+  if (!(S * mn <= limit)) *flag += 1.f;                                                        // NaN / inf trip it too
+}
+int scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, cudaStream_t st) {
+  scale_guard_kernel<<<1, 1, 0, st>>>(amax_prev, amax_next, limit, flag);
   DUDF_LAUNCH_OK();
   return 0;
 }

@@ -300,6 +300,30 @@ __device__ __forceinline__ void tc_act_point(float* u, float s, float c) {
   u[0] = s;
 }
 
+// the same for accumulators that still carry a power-of-two scale 1 / inv on their derivative channels (split-precision path:
+// weights are packed times 64): a_i = (c inv) z_i, b_ij = (c inv) z_ij - (KAPPA s inv^2) z_i z_j.  inv is a power of two, so every
+// product equals the one tc_act_point forms from the unscaled values bit for bit; the value channel u[0] is not read.
+template <int NCH>
+__device__ __forceinline__ void tc_act_point_scaled(float* u, float s, float c, float inv) {
+  const float ci = c * inv;
+  if constexpr (NCH >= 10) {
+    const float ks = (TC_KAPPA * inv * inv) * s;
+    const float kx = ks * u[1], ky = ks * u[2], kz = ks * u[3];
+    u[4] = fmaf(ci, u[4], -kx * u[1]);
+    u[5] = fmaf(ci, u[5], -kx * u[2]);
+    u[6] = fmaf(ci, u[6], -kx * u[3]);
+    u[7] = fmaf(ci, u[7], -ky * u[2]);
+    u[8] = fmaf(ci, u[8], -ky * u[3]);
+    u[9] = fmaf(ci, u[9], -kz * u[3]);
+  }
+  if constexpr (NCH >= 4) {
+    u[1] = ci * u[1];
+    u[2] = ci * u[2];
+    u[3] = ci * u[3];
+  }
+  u[0] = s;
+}
+
 // stored pre-activations of the first layer for GC/NCH consecutive points (pts: xyz triples)
 template <int NCH, int GC>
 __device__ __forceinline__ void tc_first_layer_group(float* u, const float* pts, float w0, float r0x, float r0y, float r0z, float b0) {

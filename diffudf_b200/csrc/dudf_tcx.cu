@@ -74,8 +74,13 @@ template <int NCH>
 struct TcxCfg {
   using B = TcCfg<NCH>;
   static constexpr int PT = B::PT, NV = B::NV, GC = B::GC, NGRP = B::NGRP;
-  static constexpr int G0 = (NCH == 10) ? 2 : NGRP / 2;      // column groups of warps 0-3; warps 4-7 take the rest
 };
+// EW epilogue warps (8 or 16): warp w serves TMEM lane quarter w & 3 and the column groups of set w >> 2.  With 16 warps every
+// warp owns ONE column group per neuron half (jet-10 tiles have 3 groups: the fourth set idles), 4 warps per scheduler hide the
+// TMEM-load / conversion / store latencies of each other, and a neuron half is turned around in ~half the time — the half
+// epilogue sits on the critical path of the in-place schedule (tools/tcx_trace.py).
+template <int EW> __device__ __forceinline__ void tcx_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); }
+template <int EW> struct TcxRegs { static constexpr int EPI = (EW == 8) ? TC_REGS_EPI : 104, AUX = TC_REGS_AUX; };   // 20 warps launch at 96: (640 * 96 - 128 * 56) / 512 = 106
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -114,8 +119,10 @@ __device__ __forceinline__ void tcx_producer(const unsigned char* packed, unsign
 template <int CL>
 __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* ring, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
                                              uint64_t* acc_ready, uint32_t tmem_base, int64_t rounds, int n_phase, int64_t ntiles,
-                                             unsigned char* img, int64_t ncb, int64_t cb0, uint64_t img_policy, int dbg) {
+                                             unsigned char* img, int64_t ncb, int64_t cb0, uint64_t img_policy, int dbg,
+                                             unsigned long long* trace) {
   const bool skip = (dbg & 2) != 0;
+  uint32_t tn = 0;
   constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, /*A K-major*/ 0, /*B MN-major*/ 1);
   constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
   const uint64_t a_desc0 = make_desc_sw128(smem_u32(ring), 16, 1024);
@@ -135,6 +142,7 @@ __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* 
         mbar_wait(&act_ready[kh], (act_phase >> kh) & 1u, 0x1200 + kh);
         act_phase ^= 1u << kh;
         tc_fence_after();
+        tc_trace(trace, tn, 1, kh);
         if (copy) {
           if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -156,8 +164,12 @@ __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* 
             mbar_wait(&full[stage], phase, 0x1300 + stage);                    // hi chunk: against the hi and the lo tile
             const uint64_t a_hi = desc_advance(a_desc0, stage * TC_CHUNK_BYTES);
             if (!skip) {
-              mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), idesc, (kh | kb) != 0);
-              mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bl_desc0, koff), idesc, 1);
+              if (dbg & 16) {       // diagnostics: no collector reuse (A re-read from shared memory by every MMA)
+                mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), idesc, (kh | kb) != 0);
+                mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bl_desc0, koff), idesc, 1);
+              } else {
+                mma_f16_ss_k64_pair_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), desc_advance(bl_desc0, koff), idesc, (kh | kb) != 0);
+              }
             }
             release(stage);
             if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
@@ -166,6 +178,7 @@ __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* 
             release(stage);
             if (++stage == TCX_STAGES) { stage = 0; phase ^= 1; }
           }
+          tc_trace(trace, tn, 2, kh * 2 + h);
           if (kh == 1) {
             if (copy) {
               if ((threadIdx.x & 31) == 0) {
@@ -237,6 +250,8 @@ struct TcxEpi {
   uint32_t acc_phase;     // bit h = parity of acc_ready[h]
   uint32_t jg;            // layer phases completed so far (accumulator parity)
   int q, cw, lane, tid;
+  unsigned long long* trace;   // diagnostics (tools/tcx_trace.py): event log of CTA 0 / warp 0, or null
+  uint32_t tn;
 };
 
 struct TcxTrain {         // training forward: stash + operand images (null for queries)
@@ -244,10 +259,12 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   unsigned char* Aimg;
   int64_t ld, col0;
   int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
-};                        //   8 no tile stores
+                          //   8 no tile stores, 16 no collector reuse of the weight operand, 32 no accumulator loads
+  unsigned long long* trace;
+};
 
 // all layers of one 128-column tile.  x == null: grid points (first + p).  TRAIN: stash the pre-activations, write raw channels.
-template <int NCH, bool TRAIN, int SC>
+template <int NCH, bool TRAIN, int SC, int EW>
 __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const float* __restrict__ x, int64_t P, int gridN, int64_t grid_first,
                                          float vs, int64_t tile, bool valid, const QueryOut& out, float* outp, float* Ust, int64_t ld, int64_t colt,
                                          int dbg) {
@@ -255,8 +272,9 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
   constexpr int GC = C::GC;
   const int L = net.n_lin - 1;
   const float w0 = net.w0, ww = net.ww;
-  tc_epi_bar();
-  for (int i = e.tid; i < C::PT; i += 256) {
+  tc_trace(e.trace, e.tn, 14, NCH);
+  tcx_epi_bar<EW>();
+  for (int i = e.tid; i < C::PT; i += EW * 32) {
     const int64_t p = tile * C::PT + i;
     float pt[3] = {0.f, 0.f, 0.f};
     if (valid && p < P) {
@@ -265,12 +283,13 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
     }
     e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
   }
-  if (C::NV < 128) {       // idle columns of both tiles are zero for this tile's math (a launch may mix jet orders)
+  if (C::NV < 128 && e.tid < 256) {       // idle columns of both tiles are zero for this tile's math (a launch may mix jet orders)
     *reinterpret_cast<uint4*>(tc_tile_row(e.act, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(tc_tile_row(e.act + TCX_OFF_LO, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
   }
-  tc_epi_bar();
-  const int g_begin = e.cw ? C::G0 : 0, g_end = e.cw ? C::NGRP : C::G0;
+  tcx_epi_bar<EW>();
+  constexpr int NG_PER = (C::NGRP + EW / 4 - 1) / (EW / 4);
+  const int g_begin = min(e.cw * NG_PER, C::NGRP), g_end = min(g_begin + NG_PER, C::NGRP);
   for (int l = 0; l < L; ++l) {
     for (int h = 0; h < 2; ++h) {
       const int n = h * 128 + e.q * 32 + e.lane;               // this thread's neuron in this half = its row of the B operand
@@ -280,25 +299,36 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       if (l == 0) { r0x = net.W[0][n * 3]; r0y = net.W[0][n * 3 + 1]; r0z = net.W[0][n * 3 + 2]; b0 = net.b[0][n]; }
       else bias = ww * net.b[l][n];
       const float wl = (l == L - 1) ? e.wl_s[n] : 0.f;
+      tc_trace(e.trace, e.tn, 40 + h, l);
       if (l > 0) {
         mbar_wait(&e.acc_ready[h], (e.acc_phase >> h) & 1u, 0x1400 + h);
         e.acc_phase ^= 1u << h;
         tc_fence_after();
       }
+      tc_trace(e.trace, e.tn, 10 + h, l);
       const uint32_t taddr = e.tmem_q + ((e.jg + (uint32_t)l - 1u) & 1u) * 256 + h * 128;
-#pragma unroll 1
-      for (int g = g_begin; g < g_end; ++g) {
+      auto group = [&](int g) {
         float u[GC];
         if (l == 0) {
           tc_first_layer_group<NCH, GC>(u, e.xs + g * (GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
         } else {
-          TmemRegs<GC> tr;
-          tc_ld_issue<GC>(taddr + g * GC, tr);
-          tc_ld_take<GC>(tr, u);
+          if (dbg & 32) {            // diagnostics: no accumulator loads
 #pragma unroll
-          for (int j = 0; j < GC; ++j) u[j] *= TCX_WSCALE_INV;
+            for (int j = 0; j < GC; ++j) u[j] = (float)(j + e.lane);
+          } else {
+            TmemRegs<GC> tr;
+            tc_ld_issue<GC>(taddr + g * GC, tr);
+            tc_ld_take<GC>(tr, u);
+          }
+          if constexpr (TRAIN) {       // the stash holds the unscaled pre-activations of every channel
 #pragma unroll
-          for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
+            for (int j = 0; j < GC; ++j) u[j] *= TCX_WSCALE_INV;
+#pragma unroll
+            for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
+          } else {                     // queries: only the sine argument is unscaled, the derivative channels keep the 64 (below)
+#pragma unroll
+            for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] = fmaf(u[pp * NCH], TCX_WSCALE_INV, bias);
+          }
         }
         if constexpr (TRAIN) {
           if (valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + colt) * 256 + n * 4 + (size_t)g * GC * 256);
@@ -309,7 +339,8 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
             float sn, cs;
             if constexpr (SC == 1) sincos_poly(u[pp * NCH], sn, cs);
             else sincos_fast(u[pp * NCH], sn, cs);
-            tc_act_point<NCH>(u + pp * NCH, sn, cs);
+            if constexpr (TRAIN) tc_act_point<NCH>(u + pp * NCH, sn, cs);
+            else tc_act_point_scaled<NCH>(u + pp * NCH, sn, cs, l == 0 ? 1.f : TCX_WSCALE_INV);
           }
         }
         if (l < L - 1) {
@@ -326,17 +357,22 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
             if (e.lane < 8) dst[32 + e.lane] = u[32];
           }
         }
-      }
+      };
+#pragma unroll 1
+      for (int g = g_begin; g < g_end; ++g) group(g);
+      tc_trace(e.trace, e.tn, 12 + h, l);
       if (l < L - 1) {
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
         if (e.lane == 0) mbar_arrive(&e.act_ready[h]);
       }
+      tc_trace(e.trace, e.tn, 30 + h, l);
     }
   }
+  tc_trace(e.trace, e.tn, 20, 0);
   e.jg += (uint32_t)(L - 1);
-  tc_epi_bar();
+  tcx_epi_bar<EW>();
   if (e.tid < C::NV) {
     float v = 0.f;
 #pragma unroll
@@ -344,7 +380,7 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
     const int ch = e.tid % NCH;
     e.os[e.tid] = (ch == 0) ? v + net.b[L][0] : (ch >= 4 ? v * TC_KAPPA_INV : v);
   }
-  tc_epi_bar();
+  tcx_epi_bar<EW>();
   if (e.tid < C::PT) {
     const int64_t p = tile * C::PT + e.tid;
     if (valid && p < P) {
@@ -356,12 +392,13 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       }
     }
   }
+  tc_trace(e.trace, e.tn, 15, 0);
 }
 
 // One launch serves up to two row segments with different jet orders (training: on-surface rows carry the Hessian jet).
 // Queries use segment a only (x == null: grid points).
-template <int NA, int NB, int CL, bool TRAIN, int SC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NA, int NB, int CL, bool TRAIN, int SC, int EW>
+__global__ void __launch_bounds__((EW + 4) * 32, 1)
 tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev sa, SegDev sb, int64_t tiles_a, int64_t tiles_b, int gridN,
                    int64_t grid_first, QueryOut out, TcxTrain tr) {
   extern __shared__ unsigned char smem_raw[];
@@ -381,10 +418,10 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
                                   : (((int64_t)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   if (tid == 0) {
     for (int i = 0; i < TCX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], 8); mbar_init(&acc_ready[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&act_ready[s], EW); mbar_init(&acc_ready[s], 1); }
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == EW + 1) tmem_alloc<512>(tmem_slot);
   if (tid < 256) wl_s[tid] = net.W[L][tid];
   tc_fence_before();
   __syncthreads();
@@ -392,38 +429,41 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
-    setmaxnreg_dec<TC_REGS_AUX>();
-    if (warp == 8) {
+  if (warp >= EW) {
+    setmaxnreg_dec<TcxRegs<EW>::AUX>();
+    if (warp == EW) {
       if (lane == 0) tcx_producer<CL>(packed, ring, full, empty, rounds, L - 1, CL > 1 ? cluster_ctarank() : 0u, tr.dbg);
-    } else if (warp == 9) {
+    } else if (warp == EW + 1) {
       tcx_mma_role<CL>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, ntiles, TRAIN ? tr.Aimg : nullptr,
-                       tr.ld >> 6, tr.col0 >> 6, TRAIN ? l2_policy_evict_first() : 0ull, tr.dbg);
+                       tr.ld >> 6, tr.col0 >> 6, TRAIN ? l2_policy_evict_first() : 0ull, tr.dbg,
+                       (tr.trace && blockIdx.x == 0) ? tr.trace : nullptr);
     }
   } else {
-    setmaxnreg_inc<TC_REGS_EPI>();
+    setmaxnreg_inc<TcxRegs<EW>::EPI>();
     TcxEpi e;
     e.act = act; e.xs = (float*)(smem + TCX_OFF_XS); e.os = (float*)(smem + TCX_OFF_OS); e.wl_s = wl_s;
     e.act_ready = act_ready; e.acc_ready = acc_ready;
     e.q = warp & 3; e.cw = warp >> 2; e.lane = lane; e.tid = tid;
     e.tmem_q = tmem_base + ((uint32_t)(e.q * 32) << 16);
     e.acc_phase = 0; e.jg = 0;
+    e.trace = (tr.trace && blockIdx.x == 0 && warp == 0) ? tr.trace + TC_TRACE_REGION : nullptr;
+    e.tn = 0;
     const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
     for (int64_t rd = 0; rd < rounds; ++rd) {
       const int64_t tile = blockIdx.x + rd * gridDim.x;
       const bool valid = tile < ntiles;
       const int64_t colt = tr.col0 + tile * 128;
       if (!valid || tile < tiles_a) {
-        tcx_tile<NA, TRAIN, SC>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, tr.dbg);
+        tcx_tile<NA, TRAIN, SC, EW>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, tr.dbg);
       } else {
-        if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, tr.dbg);
+        if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC, EW>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, tr.dbg);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();                 // nobody exits while a peer may still multicast into its ring
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == EW + 1) tmem_dealloc<512>(tmem_base);
 }
 
 static int tcx_cluster_size() {
@@ -436,10 +476,10 @@ static int tcx_cluster_size() {
   return v;
 }
 
-template <int NA, int NB, int CL, bool TRAIN, int SC>
+template <int NA, int NB, int CL, bool TRAIN, int SC, int EW>
 static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
                       const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
-  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN, SC>;
+  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN, SC, EW>;
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
   const int64_t ntiles = ta + tb;
   int grid = (int)std::min<int64_t>(ntiles, sms);
@@ -448,7 +488,7 @@ static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, c
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3((EW + 4) * 32);
   cfg.dynamicSmemBytes = TCX_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -479,6 +519,27 @@ static int tcx_dbg() {
   return v;
 }
 
+// epilogue warps per CTA: 8.  The 16-warp variant (4 warps per scheduler, one column group per warp and neuron half) is kept behind
+// -DDUDF_TCX_EW16 + DUDF_TCX_EW=16: parity green, but the half epilogue is instruction-issue bound (~390 instructions per 32-column
+// group, the same total on 8 or 16 warps: 2 200 clk either way, tools/tcx_trace.py), so it buys 3 % on grid queries and costs 2 % on
+// the training forward (profiles/r2_tcx_ab.txt)
+static int tcx_epi_warps() {
+#ifdef DUDF_TCX_EW16
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DUDF_TCX_EW"); v = (e && atoi(e) == 16) ? 16 : 8; }
+  return v;
+#else
+  return 8;
+#endif
+}
+
+template <int NA, int NB, bool TRAIN, int SC, int EW>
+static int tcx_launch_ew(int cl, const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN,
+                         int64_t first, const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
+  if (cl >= 2) return tcx_launch<NA, NB, 2, TRAIN, SC, EW>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  return tcx_launch<NA, NB, 1, TRAIN, SC, EW>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+}
+
 template <int NA, int NB, bool TRAIN>
 static int tcx_launch_cl(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
                          const QueryOut& out, const TcxTrain& tr0, int sms, cudaStream_t st) {
@@ -486,12 +547,15 @@ static int tcx_launch_cl(const void* packed, const NetView& net, const SegDev& a
   while (cl > 1 && ta + tb < 2 * cl) cl >>= 1;
   TcxTrain tr = tr0;
   tr.dbg = tcx_dbg();
-  if (tcx_sincos_mode() == 0) {
-    if (cl >= 2) return tcx_launch<NA, NB, 2, TRAIN, 0>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
-    return tcx_launch<NA, NB, 1, TRAIN, 0>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  tr.trace = tc_get_trace();
+#ifdef DUDF_TCX_EW16
+  if (tcx_epi_warps() == 16) {
+    if (tcx_sincos_mode() == 0) return tcx_launch_ew<NA, NB, TRAIN, 0, 16>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+    return tcx_launch_ew<NA, NB, TRAIN, 1, 16>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
   }
-  if (cl >= 2) return tcx_launch<NA, NB, 2, TRAIN, 1>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
-  return tcx_launch<NA, NB, 1, TRAIN, 1>(packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+#endif
+  if (tcx_sincos_mode() == 0) return tcx_launch_ew<NA, NB, TRAIN, 0, 8>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
+  return tcx_launch_ew<NA, NB, TRAIN, 1, 8>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
 }
 
 int tcx_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN, int64_t grid_first, const QueryOut& out,
@@ -529,7 +593,7 @@ int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* s
   const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
   const int64_t ta = 2 * a.npairs, tb = 2 * b.npairs;       // whole pairs: the reverse sweep reads the stash of a padding sub-tile too
   DUDF_REQUIRE(col0 + (ta + tb) * 128 <= ld, "tensor-core stash too small");
-  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0, 0};
+  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0, 0, nullptr};
   QueryOut out;
   memset(&out, 0, sizeof(out));
   if (nb == 0) {

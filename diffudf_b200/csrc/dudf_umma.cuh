@@ -206,6 +206,31 @@ __device__ __forceinline__ void mma_f16_ss_k64_warp(uint32_t d_tmem, uint64_t a_
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(first)
       : "memory");
 }
+// Split-precision pair: the same A slice (a weight chunk's K = 16 step) against TWO B tiles (hi and lo activations), step by
+// step over a 64-wide k chunk.  The first instruction of each step latches A in the collector buffer (collector::a::fill), the
+// second reuses it (collector::a::lastuse): A crosses shared memory once per step instead of twice — at M = N = 128 the two
+// operands of an MMA already take the whole 128 B/clk of the shared-memory port, so every byte not re-read is tensor time.
+__device__ __forceinline__ void mma_f16_ss_k64_pair_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t bh_desc, uint64_t bl_desc, uint32_t idesc,
+                                                         uint32_t first) {
+  asm volatile(
+      "{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3, c1, c2, c3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 a3, %1, 6;\n\t"
+      "add.s64 b1, %2, 128;\n\tadd.s64 b2, %2, 256;\n\tadd.s64 b3, %2, 384;\n\t"
+      "add.s64 c1, %3, 128;\n\tadd.s64 c2, %3, 256;\n\tadd.s64 c3, %3, 384;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %4, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %3, %4, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], a1, b1, %4, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], a1, c1, %4, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], a2, b2, %4, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], a2, c2, %4, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], a3, b3, %4, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], a3, c3, %4, t;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(bh_desc), "l"(bl_desc), "r"(idesc), "r"(first)
+      : "memory");
+}
 // descriptor with the start address advanced by `bytes` (no carry out of the 14-bit address field for our tiles)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // all previously issued tcgen05.mma of this thread complete -> one arrival on the mbarrier

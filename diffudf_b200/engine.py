@@ -272,9 +272,23 @@ class Engine:
                        "dudf_loss_s2_finish")
 
 
-def adam_step(p, g, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
-    """In-place Adam on flat fp32 CUDA tensors (train.py:334-337 semantics)."""
+def adam_step(p, g, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, unsafe_flag=None, skipped=None):
+    """In-place Adam on flat fp32 CUDA tensors (train.py:334-337 semantics).  unsafe_flag (1-element fp32 device tensor): the
+    update is skipped, and `skipped` (1-element int64 device tensor) incremented, when it is non-zero (dudf_adam_step_guarded)."""
     L = _lib.lib()
     with torch.cuda.device(p.device):
-        _lib.check(L.dudf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
-                                    float(beta2), float(eps), int(t), _lib.current_stream()), "dudf_adam_step")
+        if unsafe_flag is None:
+            _lib.check(L.dudf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
+                                        float(beta2), float(eps), int(t), _lib.current_stream()), "dudf_adam_step")
+        else:
+            _lib.check(L.dudf_adam_step_guarded(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
+                                                float(beta2), float(eps), int(t), unsafe_flag.data_ptr(), _lib.ptr(skipped),
+                                                _lib.current_stream()), "dudf_adam_step_guarded")
+
+
+def scale_guard(amax_prev, amax_next, flag, limit=16384.0):
+    """flag += 1 when this step's seeds outgrew the loss scale derived from the previous step (dudf_scale_guard)."""
+    L = _lib.lib()
+    with torch.cuda.device(flag.device):
+        _lib.check(L.dudf_scale_guard(amax_prev.data_ptr(), amax_next.data_ptr(), float(limit), flag.data_ptr(), _lib.current_stream()),
+                   "dudf_scale_guard")

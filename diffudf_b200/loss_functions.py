@@ -28,6 +28,7 @@ class TrainCore:
         self.precision = precision          # None -> model.train_precision (default 'fp32')
         self.amax = None                    # (2,) fp32: max|stored seed| of the last two tensor-core steps (loss scale source)
         self.amax_key, self.amax_slot = None, 0
+        self.last_fused = None              # (amax_prev, amax_next) views of the last single-launch fused step, else None
         self.fused_flags = int(os.environ.get("DUDF_FUSED_FLAGS", "2"))   # evict-first operand images; discarding consumed scratch lines (bit 0) costs 1.5 %
 
     def _prec(self):
@@ -115,6 +116,7 @@ class TrainCore:
         key = (mode, tuple(float(v) for v in w), float(alpha), int(P_global), int(n_on), int(P))
         if self.amax is None:
             self.amax = torch.zeros(2, device=x.device, dtype=torch.float32)
+        self.last_fused = None
         if prec != "tc16" or mode == "s2" or self.amax_key != key:     # (tcx3 has no single-launch kernel yet)
             terms = self.forward(mode, x, normals, d, n_on, w, alpha, P_global, None)
             slot = 1 - self.amax_slot
@@ -135,12 +137,16 @@ class TrainCore:
                                          d=d[s["row0"]:s["row0"] + s["rows"]], order=s["order"]) for s in segs],
                              P_global, w, alpha, terms, self.amax[prev:prev + 1], self.amax[nxt:nxt + 1], scratch, A, Zb, ld, gW, gB,
                              self.fused_flags)
+        self.last_fused = (self.amax[prev:prev + 1], self.amax[nxt:nxt + 1])
         self.amax_slot = nxt
         self.pending = None
         return terms
 
-    def backward(self, upstream, gW, gB, absmax=None):
-        """Accumulates d(sum_k upstream[k] term_k)/d(params) into gW / gB (lists of tensors)."""
+    def backward(self, upstream, gW, gB, absmax=None, wgrad_groups=None, after_group=None):
+        """Accumulates d(sum_k upstream[k] term_k)/d(params) into gW / gB (lists of tensors).
+        wgrad_groups [(layer_lo, layer_hi, flat_lo, flat_hi)] (tensor-core precisions): the weight-gradient GEMMs are launched
+        group by group and after_group(flat_lo, flat_hi) is called behind each — the data-parallel trainer hands the finished
+        slice of the flat gradient to its all-reduce while the next group computes."""
         p = self.pending
         if p is None:
             raise RuntimeError("TrainCore.backward without a pending forward")
@@ -163,7 +169,12 @@ class TrainCore:
                                      seeds=seeds[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]) for s in p["segs"]],
                                p["Z"], p["Zb"], p["ld"], gW, gB, prec, seed_absmax=absmax)
         ncols = max(s["col0"] + s["cols"] for s in p["segs"])
-        eng.jet_wgrad(p["Zb"], p["A"], p["ld"], ncols, gW, prec, seed_absmax=absmax)
+        if wgrad_groups and prec in TC_PRECISIONS:
+            for lo, hi, a, b in wgrad_groups:
+                eng.jet_wgrad_layers(p["Zb"], p["A"], p["ld"], gW, lo, hi, prec, seed_absmax=absmax)
+                after_group(a, b)
+        else:
+            eng.jet_wgrad(p["Zb"], p["A"], p["ld"], ncols, gW, prec, seed_absmax=absmax)
 
 
 def _core(model):

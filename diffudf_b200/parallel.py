@@ -39,6 +39,24 @@ def shard_batch(x, normals, d, n_on, n_far, rank, world):
     return cat(xs), cat(ns), cat(ds), n_on_r
 
 
+def grad_groups(sizes, n_groups):
+    """Layer groups for the overlapped gradient all-reduce.  sizes: [(W.numel(), b.numel())] per linear layer 0..L in the order of
+    the flat gradient [W0 b0 W1 b1 ... WL bL]; the 256 x 256 weight-gradient GEMMs are layers 1..L-1.  Returns
+    [(layer_lo, layer_hi, flat_lo, flat_hi)]: after the GEMMs of layers [layer_lo, layer_hi) the slice [flat_lo, flat_hi) is final
+    (the first group carries layer 0, the last one the output layer: those gradients come out of the reverse sweep)."""
+    L = len(sizes) - 1
+    n_groups = max(1, min(n_groups, L - 1))
+    offs = [0]
+    for a, b in sizes:
+        offs.append(offs[-1] + a + b)
+    bounds = [1 + (L - 1) * g // n_groups for g in range(n_groups + 1)]
+    out = []
+    for g in range(n_groups):
+        lo, hi = bounds[g], bounds[g + 1]
+        out.append((lo, hi, 0 if g == 0 else offs[lo], offs[-1] if g == n_groups - 1 else offs[hi]))
+    return out
+
+
 class DataParallel:
     """Attach to a model (`model._dp = DataParallel(...)`) to make the fused losses data-parallel."""
 
@@ -60,6 +78,15 @@ class DataParallel:
     def reduce_grads(self, flat_grad):
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
 
+    def reduce_grads_behind(self, flat_slice, side):
+        """all-reduce of a finished slice of the flat gradient on the stream `side`, ordered behind the work enqueued so far on
+        the current stream; the current stream keeps going (the next group's weight-gradient GEMM runs under the collective)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(flat_slice.device))
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.group)
+
     def reduce_terms(self, terms):
         dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=self.group)
 
@@ -73,16 +100,57 @@ class DataParallel:
         return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
 
 
-def extract_fields_sharded(model, N, gt_mode, alpha, dp):
-    """Grid query sharded by contiguous ranges of the flat index (slabs of the slowest axis when N
-    divides evenly), gathered on every rank.  Returns df (N,N,N), vecs (N,N,N,3)."""
+def round_robin_blocks(total, world, rounds):
+    """Block decomposition for a gathered query: the flat index range is cut into world * rounds blocks of `s` rows; block b is
+    computed by rank b % world in round b // world, so the blocks of one round are CONTIGUOUS in the output and one
+    all_gather_into_tensor per round lands them in place (no padding pass, no list of buffers, no concatenation).
+    Returns the block size s (the last blocks may be short or empty)."""
+    return -(-total // (world * rounds))
+
+
+def gather_round_robin(fill, total, dp, tails, dtypes, device, rounds=4):
+    """Sharded evaluation + gather with the collective of round k overlapped with the compute of round k + 1.
+
+    fill(first, count, views): writes rows [first, first + count) of the result into `views` (one (s,) + tail view of each output,
+    already positioned at this rank's block).  Outputs are allocated once at world * rounds * s rows and returned as [:total]
+    views.  The gathers run on a side stream (CUDA) behind an event, in place: every rank's input is its own block of the
+    output tensor."""
+    world, rank = dp.world, dp.rank
+    s = round_robin_blocks(total, world, rounds)
+    outs = [torch.empty((world * rounds * s,) + tuple(t), dtype=dt, device=device) for t, dt in zip(tails, dtypes)]
+    cuda = torch.device(device).type == "cuda"
+    side = torch.cuda.Stream(device) if cuda else None
+    for k in range(rounds):
+        first = (k * world + rank) * s
+        count = max(0, min(s, total - first))
+        views = [o[first:first + s] for o in outs]
+        if count > 0:
+            fill(first, count, views)
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for o, v in zip(outs, views):
+                    dist.all_gather_into_tensor(o[k * world * s:(k + 1) * world * s], v, group=dp.group)
+        else:
+            for o, v in zip(outs, views):
+                dist.all_gather_into_tensor(o[k * world * s:(k + 1) * world * s], v.clone(), group=dp.group)
+    if cuda:
+        torch.cuda.current_stream(device).wait_stream(side)
+    return [o[:total] for o in outs]
+
+
+def extract_fields_sharded(model, N, gt_mode, alpha, dp, rounds=4):
+    """Grid query sharded over the ranks in round-robin blocks of the flat index and gathered on every rank straight into the
+    (N^3,) / (N^3, 3) outputs; the gather of one round runs under the next round's compute.  Returns df (N,N,N), vecs (N,N,N,3)."""
     from .render_mc import extract_fields
-    total = N ** 3
-    lo, hi = shard_range(total, dp.rank, dp.world)
-    df, vecs = extract_fields(model, None, N, gt_mode, None, alpha, first=lo, count=hi - lo)
-    counts = [shard_range(total, r, dp.world)[1] - shard_range(total, r, dp.world)[0] for r in range(dp.world)]
-    df = dp.gather_rows(df, counts)
-    vecs = dp.gather_rows(vecs, counts)
+    dev = model._weights_biases()[0][0].device
+
+    def fill(first, count, views):
+        extract_fields(model, None, N, gt_mode, None, alpha, first=first, count=count, out=(views[0][:count], views[1][:count]))
+
+    df, vecs = gather_round_robin(fill, N ** 3, dp, [(), (3,)], [torch.float32, torch.float32], dev, rounds)
     return df.reshape(N, N, N), vecs.reshape(N, N, N, 3)
 
 

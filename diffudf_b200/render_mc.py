@@ -10,11 +10,12 @@ from .engine import Q_ABS_INV_TANH, Q_NEG_NORMALIZE
 from .inverses import inverse_torch
 
 
-def extract_fields(decoder, latent_vec, N, gt_mode, device, alpha, first=0, count=None):
+def extract_fields(decoder, latent_vec, N, gt_mode, device, alpha, first=0, count=None, out=None):
     """Returns df (N,N,N) fp32 = inverse(gt_mode, |f|) and vecs (N,N,N,3) fp32 = -normalize(grad f) on `device`.
     Where grad f is exactly zero the sign-aligned top Hessian eigenvector is used (render_mc.py:77-93).
     `first`/`count` restrict the evaluation to a range of the flat index (slab sharding); the
-    returned tensors are then flat: df (count,), vecs (count,3)."""
+    returned tensors are then flat: df (count,), vecs (count,3).  `out` = (df, vecs) preallocated flat tensors of `count` rows
+    to write into (the sharded driver passes slices of the gathered output)."""
     if latent_vec is not None and torch.is_tensor(latent_vec) and latent_vec.numel() != 0:
         raise ValueError("extract_fields: latent conditioning is not supported")
     eng = decoder._engine_synced()
@@ -22,9 +23,12 @@ def extract_fields(decoder, latent_vec, N, gt_mode, device, alpha, first=0, coun
     full = count is None
     count = total - first if count is None else count
     flags = Q_NEG_NORMALIZE | (Q_ABS_INV_TANH if gt_mode == "tanh" else 0)
-    df, vecs, _ = eng.query_grid(N, first, count, decoder.precision, flags, alpha, want_vecs=True)
+    df, vecs, _ = eng.query_grid(N, first, count, decoder.precision, flags, alpha, want_vecs=True, out=out)
     if gt_mode != "tanh":
-        df = inverse_torch(gt_mode, df.abs(), alpha)
+        if out is not None:
+            df.copy_(inverse_torch(gt_mode, df.abs(), alpha))
+        else:
+            df = inverse_torch(gt_mode, df.abs(), alpha)
     # zero-gradient fallback (rare): Hessian eigenvector, aligned with the (zero) gradient like the reference
     small = torch.linalg.norm(vecs, dim=-1) < 0.04
     if bool(small.any()):
@@ -64,6 +68,19 @@ class TriangleSoup:
             else:
                 fh.writelines(f"v {p[0]!r} {p[1]!r} {p[2]!r}\n" for p in v.tolist())
                 fh.writelines(f"f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n" for t in f.tolist())
+
+
+def extract_mesh_MESHUDF(df_values, normals, device=None, smooth_borders=False, **kwargs):
+    """Drop-in for the numerical part of extract_mesh_MESHUDF (src/render_mc.py:103-134): clamp, MeshUDF marching cubes with
+    spacing 2 / (N - 1), avg_thresh 1.05, max_thresh 1.75, shift by -1 — through the C++ mesher (marching_cubes.udf_mc_lewiner,
+    identical arrays to the reference's Cython module).  Returns (TriangleSoup, None) where the reference returns
+    (pred_mesh, trimesh.Trimesh): its trimesh clean-up loops and the border smoothing (:136-199) are third-party mesh hygiene and
+    are not rebuilt (smooth_borders=True raises)."""
+    if smooth_borders:
+        raise NotImplementedError("border smoothing / trimesh clean-up are downstream mesh hygiene (SURVEY.md 2 #9), not part of this path")
+    from .marching_cubes import meshudf_from_fields
+    verts, faces = meshudf_from_fields(df_values, normals)
+    return TriangleSoup(verts, faces), None
 
 
 def cap_triangles(ndf, grad, resolution, threshold=0.008, device=None):

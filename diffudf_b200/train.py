@@ -12,7 +12,7 @@ import time
 import numpy as np
 import torch
 
-from .engine import adam_step
+from .engine import adam_step, scale_guard
 from .loss_functions import S1_KEYS, S2_KEYS, SIREN_KEYS, TrainCore
 
 
@@ -42,7 +42,11 @@ class FusedTrainer:
             tensors += [w, b]
         n = sum(t.numel() for t in tensors)
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        # one slot behind the flat gradient carries the "loss scale outgrown" flag of the fused step: zeroed with the gradient,
+        # summed over the ranks by the gradient all-reduce, read by the guarded Adam kernel
+        self.grad_all = torch.zeros(n + 1, device=dev, dtype=torch.float32)
+        self.grad = self.grad_all[:n]
+        self.skipped = torch.zeros(1, device=dev, dtype=torch.int64)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
@@ -56,26 +60,51 @@ class FusedTrainer:
             off += k
         self.core = TrainCore(model, precision)
         self.t = 0
+        # data parallel: the gradient all-reduce of a finished layer group runs on a side stream under the next group's
+        # weight-gradient GEMM (tensor-core precisions; DUDF_DP_GROUPS=1 restores the single blocking all-reduce)
+        self.groups, self.side = None, None
+        if dp is not None:
+            import os
+            from .parallel import grad_groups
+            ng = int(os.environ.get("DUDF_DP_GROUPS", "2"))
+            if ng > 1:
+                self.groups = grad_groups([(w.numel(), b.numel()) for w, b in zip(ws, bs)], ng)
+                self.side = torch.cuda.Stream(dev)
 
     def step(self, mode, x, normals, d, n_on, weights, alpha, lr):
         """One optimisation step on a device-resident batch (x (P,3), normals (P,3), d (P,), fp32).
         Returns the (4,) float64 device tensor of this rank's loss-term shares (no sync)."""
         dp = self.dp
         P_global = dp.global_rows(x.shape[0]) if dp is not None else None
-        self.grad.zero_()
+        self.grad_all.zero_()
+        guarded = False
         if mode != "s2" and self.core._prec() == "tc16" and self.fused:
             terms = self.core.fused_step(mode, x, normals, d, n_on, weights, alpha, P_global, self.gW, self.gB)
+            if self.core.last_fused is not None:           # the single-launch kernel ran with the previous step's loss scale
+                scale_guard(*self.core.last_fused, self.grad_all[-1:])
+                guarded = True
         else:
             terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None)
-            self.core.backward(None, self.gW, self.gB)
+            if self.groups is not None and self.core._prec() in ("tc16", "tcx3"):
+                self.core.backward(None, self.gW, self.gB, wgrad_groups=self.groups,
+                                   after_group=lambda a, b: dp.reduce_grads_behind(self.grad[a:b], self.side))
+                torch.cuda.current_stream(self.grad.device).wait_stream(self.side)
+                dp = None                                  # reduced
+            else:
+                self.core.backward(None, self.gW, self.gB)
         if dp is not None:
-            dp.reduce_grads(self.grad)
+            dp.reduce_grads(self.grad_all if guarded else self.grad)
         self.t += 1
-        adam_step(self.flat, self.grad, self.m, self.v, lr, self.t, self.betas[0], self.betas[1], self.eps)
+        adam_step(self.flat, self.grad, self.m, self.v, lr, self.t, self.betas[0], self.betas[1], self.eps,
+                  unsafe_flag=self.grad_all[-1:] if guarded else None, skipped=self.skipped if guarded else None)
         # parameters changed in place behind torch's back: make the engine re-pack on next use
         if self.model._engine is not None:
             self.model._engine._sig = None
         return terms
+
+    def skipped_steps(self):
+        """Number of fused steps whose update was skipped because the seeds outgrew the (one step stale) loss scale (one sync)."""
+        return int(self.skipped.item())
 
 
 class BatchFeeder:

@@ -251,6 +251,34 @@ int dudf_mesh_sample_surface(const float* triangles, const float* cdf, int64_t n
  * t is the 1-based step count.  Flat fp32 arrays of n elements. */
 int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int64_t t, void* stream);
+/* Safety net of the fused tensor-core step (dudf_train_step_fused scales its fp16 adjoints with the PREVIOUS step's seed
+ * magnitude): dudf_scale_guard adds 1 to *flag when S(amax_prev) * amax_next exceeds `limit` (nominal range (1024, 2048], fp16
+ * saturates at 65504) or is not finite; the flag lives in the slot behind the flat gradient so that the data-parallel
+ * all-reduce sums it over the ranks.  dudf_adam_step_guarded is dudf_adam_step that leaves p, m, v untouched and increments
+ * *skipped (device int64, may be NULL) when *unsafe_flag != 0 — the GradScaler rule of the reference ecosystem's mixed-precision
+ * training (the reference itself trains in fp32, train.py:204-222, and has no such window). */
+int dudf_scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, void* stream);
+int dudf_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                           float eps, int64_t t, const float* unsafe_flag, int64_t* skipped, void* stream);
+
+/* MeshUDF marching cubes — HOST code, plain C++17, no device involved.  Replaces
+ * _marching_cubes_lewiner_cy.marching_cubes_udf(im, grads, luts, st, classic, avg_thresh, max_thresh, mask)
+ * (src/marching_cubes/_marching_cubes_lewiner_cy.pyx:1116-1774) as called by udf_mc_lewiner (_marching_cubes_lewiner.py:80-141)
+ * from extract_mesh_MESHUDF (src/render_mc.py:127-133): im [nz][ny][nx] fp32 distances, grads [nz][ny][nx][3] fp32, mask
+ * [nz][ny][nx] bytes or NULL; luts_blob = Lewiner's look-up tables as written by tools/export_lewiner_luts.py
+ * (diffudf_b200/data/lewiner_luts.bin).  The result arrays are malloc'ed by the library (vertices in (x, y, z) grid units,
+ * normalised normals, values, faces in emission order — what Cell.get_vertices / get_normals / get_values / get_faces return) and
+ * released with dudf_meshudf_free.  Same serial visit order as the reference: identical arrays on identical fields. */
+typedef struct dudf_meshudf_result {
+  float* vertices;
+  float* normals;
+  float* values;
+  int32_t* faces;
+  int64_t n_vertices, n_faces;
+} dudf_meshudf_result;
+int dudf_meshudf_mc(const float* im, const float* grads, int nz, int ny, int nx, int step, float avg_thresh, float max_thresh,
+                    const unsigned char* mask, const void* luts_blob, int64_t luts_bytes, dudf_meshudf_result* out);
+void dudf_meshudf_free(dudf_meshudf_result* r);
 
 /* bring-up / regression tests of the tcgen05 building blocks (tests/test_gpu_umma.py) */
 int dudf_selftest_umma(int variant, float* max_err_host);

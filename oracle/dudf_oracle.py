@@ -467,19 +467,25 @@ def _normalize_rows(v, eps=1e-12):
     return v / n
 
 
-def extract_fields(params, N, gt_mode, alpha, w0=30.0, dtype=np.float32):
-    """src/render_mc.py:20-101: returns df (N,N,N) fp32 and vecs (N,N,N,3) fp32."""
+def extract_fields(params, N, gt_mode, alpha, w0=30.0, dtype=np.float32, chunk=None):
+    """src/render_mc.py:20-101: returns df (N,N,N) fp32 and vecs (N,N,N,3) fp32.  chunk: evaluate that many grid points at a
+    time (the reference itself evaluates in chunks of max_batch points, src/evaluate.py:21-35; points are independent)."""
     xs = grid_coords(N)
-    f, g, H = evaluate(params, xs, True, True, w0, dtype)
-    df = inverse(gt_mode, np.abs(f), alpha)[:, 0]
-    grads = -1.0 * _normalize_rows(g)
-    lam, V = eig_top(H)
-    n = V[..., 2]
-    sgn = np.where(np.sum(grads * n, -1, keepdims=True) < 0, -1.0, 1.0)
-    n = n * sgn
-    gn = np.linalg.norm(grads, axis=-1, keepdims=True)
-    vecs = np.where(gn < 0.04, n, grads)
-    return df.astype(np.float32).reshape(N, N, N), vecs.astype(np.float32).reshape(N, N, N, 3)
+    total = xs.shape[0]
+    chunk = total if chunk is None else int(chunk)
+    df = np.empty(total, np.float32)
+    vecs = np.empty((total, 3), np.float32)
+    for a in range(0, total, chunk):
+        f, g, H = evaluate(params, xs[a:a + chunk], True, True, w0, dtype)
+        df[a:a + chunk] = inverse(gt_mode, np.abs(f), alpha)[:, 0]
+        grads = -1.0 * _normalize_rows(g)
+        lam, V = eig_top(H)
+        n = V[..., 2]
+        sgn = np.where(np.sum(grads * n, -1, keepdims=True) < 0, -1.0, 1.0)
+        n = n * sgn
+        gn = np.linalg.norm(grads, axis=-1, keepdims=True)
+        vecs[a:a + chunk] = np.where(gn < 0.04, n, grads)
+    return df.reshape(N, N, N), vecs.reshape(N, N, N, 3)
 
 
 def propagate_rays(params, rays, t0, mask, gt_mode, alpha, surface_threshold, max_iterations,

@@ -85,3 +85,26 @@ def test_batch_feeder_preserves_order_and_content():
         seen.append((float(x[3, 1]), float(n[0, 2]), float(d[6])))
     assert seen == [(float(i), float(-i), float(10 * i)) for i in range(9)]
     assert list(feeder.feed([])) == []
+
+
+def test_fused_step_skips_the_update_when_the_loss_scale_is_outgrown(weights):
+    """the fused tc16 step scales its fp16 adjoints with the PREVIOUS step's seed magnitude.  When the seeds
+    outgrow that scale (here: the recorded magnitude is shrunk 100x, i.e. the scale is 64-128x too large and adjoints would
+    saturate), the guard flag trips, Adam leaves parameters and moments untouched, the skip is counted, and the next step —
+    whose scale comes from the skipped step's own magnitude — updates normally again."""
+    from diffudf_b200.train import FusedTrainer
+    m, batches, n_on = _make(weights, n_batches=1, rows=3000)
+    x, n, d = (torch.from_numpy(a).cuda() for a in (batches[0][0][0], batches[0][1][0], batches[0][2][0, :, 0]))
+    w = [1e4, 1e4, 1e4, 1e3]
+    tr = FusedTrainer(m, precision="tc16")
+    tr.step("s1", x, n, d, n_on, w, 100.0, 1e-6)          # three-kernel route: measures the scale
+    tr.step("s1", x, n, d, n_on, w, 100.0, 1e-6)          # fused launch, scale one step stale but adequate
+    assert tr.core.last_fused is not None and tr.skipped_steps() == 0
+    tr.core.amax[tr.core.amax_slot] *= 1e-2               # pretend the previous step's seeds were 100x smaller
+    before, m_before = tr.flat.clone(), tr.m.clone()
+    tr.step("s1", x, n, d, n_on, w, 100.0, 1e-6)
+    assert tr.skipped_steps() == 1
+    assert torch.equal(tr.flat, before) and torch.equal(tr.m, m_before)
+    tr.step("s1", x, n, d, n_on, w, 100.0, 1e-6)
+    assert tr.skipped_steps() == 1 and not torch.equal(tr.flat, before)
+    assert bool(torch.isfinite(tr.flat).all())
