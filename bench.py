@@ -500,6 +500,10 @@ def run_ours(args, rank, local_rank, world):
             prof[tag] = prof.get(tag, 0.0) + s.elapsed_time(t) / nrep
     # ---- field queries (secondary metric: UDF+grad queries/s on a dense grid) ----
     if world > 1:
+        aux["gradient_exchange"] = ("peer memory: reduction fused into the Adam kernel (dudf_adam_step_peers) behind a symmetric-memory barrier"
+                                    if trainer.peer is not None else
+                                    f"NCCL all-reduce in {len(trainer.groups) if trainer.groups else 1} layer group(s) under the weight-gradient GEMMs")
+    if world > 1 and not args.light:
         # BASELINE's second metric at N GPUs: the 512^3 grid sharded by contiguous slabs of the flat index (no data-path
         # collective), then gathered (all_gather_into_tensor straight into the output); max over ranks, like the headline
         from diffudf_b200.parallel import extract_fields_sharded, shard_range
@@ -522,7 +526,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(tq, op=dist.ReduceOp.MAX)
         aux["grid512_tcx3_sharded_compute_queries_per_s"] = Ng ** 3 / (float(tq[0]) * 1e-3)
         aux["grid512_tcx3_sharded_compute_plus_gather_queries_per_s"] = Ng ** 3 / (float(tq[1]) * 1e-3)
-    if rank == 0:
+    if rank == 0 and not args.light:
         eng = model._engine_synced()
         for prec, N in (("tcx3", 256), ("tc16", 256), ("fp32", 128)):
             cnt = N ** 3
@@ -633,6 +637,8 @@ def main():
     ap.add_argument("--precision", default="tcx3", choices=["tcx3", "tc16", "fp32"],
                     help="arithmetic of the training step: split-precision tcgen05 (default, conforming), single-pass fp16 tcgen05, "
                          "or fp32 CUDA cores")
+    ap.add_argument("--light", action="store_true", help="headline, e2e, sustained loop and roofline only (skips the secondary `aux` "
+                                                         "measurements: full-size queries, other losses, eager reference, sampler)")
     args = ap.parse_args()
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"

@@ -638,6 +638,13 @@ int dudf_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream, unsafe_flag, (long long*)skipped);
 }
 
+int dudf_adam_step_peers(float* p, const float* const* peer_grads, int world, float* m, float* v, int64_t n, float lr, float beta1,
+                         float beta2, float eps, int64_t t, int guarded, int64_t* skipped, float* g_sum_out, void* stream) {
+  DUDF_REQUIRE(p && peer_grads && m && v, "dudf_adam_step_peers: null argument");
+  DUDF_REQUIRE(t >= 1, "dudf_adam_step_peers: step count must be >= 1");
+  return adam_step_peers(p, peer_grads, world, m, v, n, lr, beta1, beta2, eps, t, guarded, (long long*)skipped, g_sum_out, (cudaStream_t)stream);
+}
+
 int dudf_scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, void* stream) {
   DUDF_REQUIRE(amax_prev && amax_next && flag, "dudf_scale_guard: null argument");
   return scale_guard(amax_prev, amax_next, limit, flag, (cudaStream_t)stream);

@@ -142,6 +142,8 @@ int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
               cudaStream_t st, const float* unsafe = nullptr, long long* skipped = nullptr);
+int adam_step_peers(float* p, const float* const* peer_grads, int world, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                    int64_t t, int guarded, long long* skipped, float* g_sum_out, cudaStream_t st);
 int scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, cudaStream_t st);
 int transpose256(const float* W, float* Wt, cudaStream_t st);
 int eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,

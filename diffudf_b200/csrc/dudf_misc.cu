@@ -155,6 +155,66 @@ int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
   return 0;
 }
 
+// Data-parallel Adam with the gradient all-reduce FUSED IN: every rank owns a gradient buffer in peer-mapped (symmetric) memory;
+// after a cross-rank barrier each rank's kernel reads element i of ALL ranks' buffers over NVLink (fixed rank order 0..W-1, so
+// every rank forms the bit-identical sum and the replicated parameters stay in lock-step), and applies the update — one pass
+// over peer memory instead of an NCCL all-reduce (2 latency-bound ring / tree phases for 1.85 MB) followed by an Adam launch.
+// The element behind the gradient (index n) is the "loss scale outgrown" flag of the fused step, summed the same way.
+struct PeerGrads { const float* g[16]; int world; };
+__global__ void __launch_bounds__(256) adam_peers_kernel(float* __restrict__ p, PeerGrads pg, float* __restrict__ m, float* __restrict__ v,
+                                                         int64_t n, float step_size, float bc2_sqrt, float b1, float b2, float eps,
+                                                         int guarded, long long* __restrict__ skipped, float* __restrict__ g_sum_out) {
+  if (guarded) {
+    float flag = 0.f;
+    for (int r = 0; r < pg.world; ++r) flag += pg.g[r][n];
+    if (flag != 0.f) {
+      if (skipped && blockIdx.x == 0 && threadIdx.x == 0) *skipped += 1;
+      return;
+    }
+  }
+  const int64_t n4 = n >> 2;
+  for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4 + 1; i4 += (int64_t)gridDim.x * blockDim.x) {
+    float gi[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t i0 = i4 * 4;
+    const int cnt = (i4 < n4) ? 4 : (int)(n - i0);
+    if (cnt <= 0) break;
+    if (cnt == 4) {
+      for (int r = 0; r < pg.world; ++r) {
+        const float4 t = __ldcv(reinterpret_cast<const float4*>(pg.g[r] + i0));       // peer memory: never a stale cached line
+        gi[0] += t.x; gi[1] += t.y; gi[2] += t.z; gi[3] += t.w;
+      }
+    } else {
+      for (int r = 0; r < pg.world; ++r)
+        for (int k = 0; k < cnt; ++k) gi[k] += __ldcv(pg.g[r] + i0 + k);
+    }
+    for (int k = 0; k < cnt; ++k) {
+      const int64_t i = i0 + k;
+      const float mi = b1 * m[i] + (1.f - b1) * gi[k];
+      const float vi = b2 * v[i] + (1.f - b2) * gi[k] * gi[k];
+      m[i] = mi;
+      v[i] = vi;
+      p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      if (g_sum_out) g_sum_out[i] = gi[k];
+    }
+  }
+}
+
+int adam_step_peers(float* p, const float* const* peer_grads, int world, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                    int64_t t, int guarded, long long* skipped, float* g_sum_out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  DUDF_REQUIRE(world >= 1 && world <= 16, "dudf_adam_step_peers: 1 .. 16 ranks (got %d)", world);
+  PeerGrads pg;
+  pg.world = world;
+  for (int r = 0; r < 16; ++r) pg.g[r] = r < world ? peer_grads[r] : nullptr;
+  for (int r = 0; r < world; ++r) DUDF_REQUIRE(pg.g[r] != nullptr && ((uintptr_t)pg.g[r] & 15) == 0, "dudf_adam_step_peers: peer buffer %d null or not 16-byte aligned", r);
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  const int blocks = (int)std::min<int64_t>((n / 4 + 256) / 256, 148 * 4);
+  adam_peers_kernel<<<blocks, 256, 0, st>>>(p, pg, m, v, n, (float)((double)lr / bc1), (float)sqrt(bc2), b1, b2, eps, guarded, skipped, g_sum_out);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
 // flag += 1 when the seeds of this step, under the loss scale derived from the previous step's magnitude, exceed `limit`
 // (nominal range of S * max|seed| is (1024, 2048]; fp16 saturates at 65504)
 __global__ void scale_guard_kernel(const float* __restrict__ amax_prev, const float* __restrict__ amax_next, float limit,

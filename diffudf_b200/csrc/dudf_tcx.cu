@@ -503,13 +503,16 @@ static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, c
   return 0;
 }
 
-// sine / cosine of the epilogue: 1 (default) = FMA-only polynomials, ~1e-7 (fp32-grade jets); 0 = MUFU after an explicit
-// reduction, 4e-7 (DUDF_TCX_SINCOS=mufu; faster for value-only queries, jets at ~1e-5)
+// sine / cosine of the epilogue: 0 (default) = MUFU.SIN / MUFU.COS after an explicit 2 pi Cody-Waite reduction (absolute error 4e-7;
+// jets f 1-3e-6, grad / Hessian 0.9-1.3e-5 of max, MeshUDF topology at 128^3 identical to the oracle's — tests/test_gpu_tcx3.py,
+// tests/test_mc_topology.py pass in both modes); 1 = FMA-only minimax polynomials (DUDF_TCX_SINCOS=poly, 1e-7, ~190 instructions
+// per 8-point group more: 8 % slower on grid queries, 25 % on value-only queries, profiles/r2_tcx_ab_sincos_burst.txt) for the
+// same measured jet error — what remains is the truncating fp32 accumulation of the tensor pipe, not the sine
 static int tcx_sincos_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DUDF_TCX_SINCOS");
-    v = (e && strcmp(e, "mufu") == 0) ? 0 : 1;
+    v = (e && strcmp(e, "poly") == 0) ? 1 : 0;
   }
   return v;
 }

@@ -127,7 +127,7 @@ class PointCloud(torch.utils.data.IterableDataset):
     """Iterable of device-generated batches; same attributes as the reference dataset (`batchesPerEpoch`,
     `samplesOnSurface`, `samplesFarSurface`) so the training loops take it unchanged."""
 
-    def __init__(self, points, normals, batchSize, samplingPercentiles, batchesPerEpoch, device, seed=0, triangles=None):
+    def __init__(self, points, normals, batchSize, samplingPercentiles, batchesPerEpoch, device, seed=0, triangles=None, prefetch=True):
         """triangles=None is the reference's onlyPCloud=True mode (distances to the cloud); with a triangle list
         ((n_tri,3,3) or (vertices, faces)) the off-surface distances are measured to the mesh (onlyPCloud=False)."""
         super().__init__()
@@ -144,14 +144,45 @@ class PointCloud(torch.utils.data.IterableDataset):
         self.batchesPerEpoch = batchesPerEpoch
         self.seed = seed
         self.batches_drawn = 0
+        self.prefetch = prefetch
+        self._side = None
+
+    def _draw(self):
+        if self.onlyPCloud:
+            out = sampleTrainingDataPC(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
+                                       seed=self.seed, batch_index=self.batches_drawn)
+        else:
+            out = sampleTrainingData(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
+                                     self.triangles, seed=self.seed, batch_index=self.batches_drawn)
+        self.batches_drawn += 1
+        return out
 
     def __iter__(self):
-        for _ in range(self.batchesPerEpoch):
-            if self.onlyPCloud:
-                out = sampleTrainingDataPC(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
-                                           seed=self.seed, batch_index=self.batches_drawn)
-            else:
-                out = sampleTrainingData(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
-                                         self.triangles, seed=self.seed, batch_index=self.batches_drawn)
-            self.batches_drawn += 1
-            yield out
+        """Batch i + 1 is drawn on a side stream while the consumer works on batch i (the reference draws synchronously inside the
+        loop, src/dataset.py:176-185): the sampler's kernels fill the SMs the persistent training kernels leave idle at their
+        tails.  `prefetch=False` draws in the consumer's stream."""
+        if not self.prefetch:
+            for _ in range(self.batchesPerEpoch):
+                yield self._draw()
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        side = self._side
+        side.wait_stream(main)                 # the cloud / triangle uploads of the constructor
+
+        def draw_ahead():
+            with torch.cuda.stream(side):
+                out = self._draw()
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return out, ev
+        nxt = draw_ahead() if self.batchesPerEpoch > 0 else None
+        for i in range(self.batchesPerEpoch):
+            cur, ev = nxt
+            nxt = draw_ahead() if i + 1 < self.batchesPerEpoch else None
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(ev)
+            for t in cur:                       # allocated on the side stream, consumed on this one
+                t.record_stream(main)
+            yield cur

@@ -286,6 +286,16 @@ def adam_step(p, g, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, unsafe_flag=N
                                                 _lib.current_stream()), "dudf_adam_step_guarded")
 
 
+def adam_step_peers(p, peer_ptrs, world, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, guarded=False, skipped=None, g_sum_out=None):
+    """Adam with the gradient all-reduce fused in (dudf_adam_step_peers): peer_ptrs = ctypes array of `world` device pointers to
+    the ranks' (n + 1)-float gradient buffers in peer-mapped memory; the caller has ordered a cross-rank barrier before."""
+    L = _lib.lib()
+    with torch.cuda.device(p.device):
+        _lib.check(L.dudf_adam_step_peers(p.data_ptr(), peer_ptrs, int(world), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
+                                          float(beta2), float(eps), int(t), 1 if guarded else 0, _lib.ptr(skipped), _lib.ptr(g_sum_out),
+                                          _lib.current_stream()), "dudf_adam_step_peers")
+
+
 def scale_guard(amax_prev, amax_next, flag, limit=16384.0):
     """flag += 1 when this step's seeds outgrew the loss scale derived from the previous step (dudf_scale_guard)."""
     L = _lib.lib()

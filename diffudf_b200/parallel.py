@@ -141,6 +141,35 @@ def gather_round_robin(fill, total, dp, tails, dtypes, device, rounds=4):
     return [o[:total] for o in outs]
 
 
+class PeerGradients:
+    """Two flat gradient buffers of n + 1 floats per rank in symmetric (peer-mapped) memory — the operand of the fused
+    all-reduce + Adam kernel (dudf_adam_step_peers).  torch.distributed._symmetric_memory provides the allocation, the exchange
+    of the mappings over NVLink and the cross-rank barrier (plumbing); the reduction itself is our kernel reading the peers.
+    Buffers alternate per step: a rank may start accumulating step t + 1 while a slower peer still reads step t."""
+
+    def __init__(self, dp, n, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.n = int(n)
+        self.stride = (self.n + 1 + 3) // 4 * 4
+        group = dp.group if dp.group is not None else dist.group.WORLD
+        self.buf = symm.empty(2 * self.stride, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world = dp.world
+        base = [int(self.hdl.buffer_ptrs[r]) for r in range(self.world)]
+        self.ptrs = [(ctypes.c_void_p * self.world)(*[b + k * self.stride * 4 for b in base]) for k in (0, 1)]
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)
+
+    def local(self, k):
+        return self.buf[k * self.stride:k * self.stride + self.n + 1]
+
+    def barrier(self):
+        """stream-ordered: returns (on the device) when every rank's work enqueued before its own barrier has finished"""
+        self.hdl.barrier(channel=0)
+
+
 def extract_fields_sharded(model, N, gt_mode, alpha, dp, rounds=4):
     """Grid query sharded over the ranks in round-robin blocks of the flat index and gathered on every rank straight into the
     (N^3,) / (N^3, 3) outputs; the gather of one round runs under the next round's compute.  Returns df (N,N,N), vecs (N,N,N,3)."""

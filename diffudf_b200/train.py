@@ -7,12 +7,13 @@ stream.  The reference's per-step `.item()` calls become one read-back per epoch
 File IO (TensorBoard, checkpoints every epoch, plots, meshing) is host glue and is left to the caller.
 """
 import copy
+import os
 import time
 
 import numpy as np
 import torch
 
-from .engine import adam_step, scale_guard
+from .engine import adam_step, adam_step_peers, scale_guard
 from .loss_functions import S1_KEYS, S2_KEYS, SIREN_KEYS, TrainCore
 
 
@@ -42,22 +43,40 @@ class FusedTrainer:
             tensors += [w, b]
         n = sum(t.numel() for t in tensors)
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
-        # one slot behind the flat gradient carries the "loss scale outgrown" flag of the fused step: zeroed with the gradient,
-        # summed over the ranks by the gradient all-reduce, read by the guarded Adam kernel
-        self.grad_all = torch.zeros(n + 1, device=dev, dtype=torch.float32)
-        self.grad = self.grad_all[:n]
-        self.skipped = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.n = n
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.skipped = torch.zeros(1, device=dev, dtype=torch.int64)
         off = 0
-        self.gW, self.gB = [], []
+        self.slices = []
         for i, t in enumerate(tensors):
             k = t.numel()
             self.flat[off:off + k].copy_(t.detach().reshape(-1))
             t.data = self.flat[off:off + k].view_as(t)
-            gv = self.grad[off:off + k].view_as(t)
-            (self.gW if i % 2 == 0 else self.gB).append(gv)
+            self.slices.append((off, k, tuple(t.shape)))
             off += k
+        # Gradient buffers.  One slot behind the flat gradient carries the "loss scale outgrown" flag of the fused step: zeroed
+        # with the gradient, summed over the ranks with it, read by the guarded Adam kernel.
+        # Data parallel, peer mode (default when torch's symmetric memory can map the ranks' buffers; DUDF_DP_PEER=0 disables):
+        # two buffer sets in peer-mapped memory, alternated per step, reduced INSIDE the Adam kernel (dudf_adam_step_peers).
+        self.peer = None
+        if dp is not None and dp.world > 1 and os.environ.get("DUDF_DP_PEER", "1") != "0":
+            try:
+                from .parallel import PeerGradients
+                self.peer = PeerGradients(dp, n, dev)
+            except Exception as exc:            # no peer access / symmetric memory unavailable: NCCL all-reduce path
+                import warnings
+                warnings.warn(f"diffudf_b200: peer-memory gradient exchange unavailable ({exc!r}); using the NCCL all-reduce")
+                self.peer = None
+        self.sets = []
+        for k in range(2 if self.peer is not None else 1):
+            ga = self.peer.local(k) if self.peer is not None else torch.zeros(n + 1, device=dev, dtype=torch.float32)
+            gW, gB = [], []
+            for i, (o, cnt, shape) in enumerate(self.slices):
+                (gW if i % 2 == 0 else gB).append(ga[o:o + cnt].view(shape))
+            self.sets.append((ga, gW, gB))
+        self.grad_sum = None                     # peer mode: set to a (n,) tensor to receive the summed gradient of every step
+        self._use_set(0)
         self.core = TrainCore(model, precision)
         self.t = 0
         # data parallel: the gradient all-reduce of a finished layer group runs on a side stream under the next group's
@@ -71,11 +90,17 @@ class FusedTrainer:
                 self.groups = grad_groups([(w.numel(), b.numel()) for w, b in zip(ws, bs)], ng)
                 self.side = torch.cuda.Stream(dev)
 
+    def _use_set(self, k):
+        self.grad_all, self.gW, self.gB = self.sets[k]
+        self.grad = self.grad_all[:self.n]
+
     def step(self, mode, x, normals, d, n_on, weights, alpha, lr):
         """One optimisation step on a device-resident batch (x (P,3), normals (P,3), d (P,), fp32).
         Returns the (4,) float64 device tensor of this rank's loss-term shares (no sync)."""
         dp = self.dp
         P_global = dp.global_rows(x.shape[0]) if dp is not None else None
+        if self.peer is not None:
+            self._use_set(self.t % 2)
         self.grad_all.zero_()
         guarded = False
         if mode != "s2" and self.core._prec() == "tc16" and self.fused:
@@ -85,18 +110,25 @@ class FusedTrainer:
                 guarded = True
         else:
             terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None)
-            if self.groups is not None and self.core._prec() in ("tc16", "tcx3"):
+            if self.peer is not None:
+                self.core.backward(None, self.gW, self.gB)
+            elif self.groups is not None and self.core._prec() in ("tc16", "tcx3"):
                 self.core.backward(None, self.gW, self.gB, wgrad_groups=self.groups,
                                    after_group=lambda a, b: dp.reduce_grads_behind(self.grad[a:b], self.side))
                 torch.cuda.current_stream(self.grad.device).wait_stream(self.side)
                 dp = None                                  # reduced
             else:
                 self.core.backward(None, self.gW, self.gB)
-        if dp is not None:
-            dp.reduce_grads(self.grad_all if guarded else self.grad)
         self.t += 1
-        adam_step(self.flat, self.grad, self.m, self.v, lr, self.t, self.betas[0], self.betas[1], self.eps,
-                  unsafe_flag=self.grad_all[-1:] if guarded else None, skipped=self.skipped if guarded else None)
+        if self.peer is not None:
+            self.peer.barrier()                    # every rank's gradient is complete
+            adam_step_peers(self.flat, self.peer.ptrs[(self.t - 1) % 2], self.peer.world, self.m, self.v, lr, self.t, self.betas[0],
+                            self.betas[1], self.eps, guarded=guarded, skipped=self.skipped, g_sum_out=self.grad_sum)
+        else:
+            if dp is not None:
+                dp.reduce_grads(self.grad_all if guarded else self.grad)
+            adam_step(self.flat, self.grad, self.m, self.v, lr, self.t, self.betas[0], self.betas[1], self.eps,
+                      unsafe_flag=self.grad_all[-1:] if guarded else None, skipped=self.skipped if guarded else None)
         # parameters changed in place behind torch's back: make the engine re-pack on next use
         if self.model._engine is not None:
             self.model._engine._sig = None

@@ -261,6 +261,15 @@ int dudf_scale_guard(const float* amax_prev, const float* amax_next, float limit
 int dudf_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                            float eps, int64_t t, const float* unsafe_flag, int64_t* skipped, void* stream);
 
+/* Data-parallel optimiser step with the gradient all-reduce fused in (the reference has no distributed code — this is
+ * the one exchange step of the sharded training path): peer_grads = HOST array of `world` DEVICE pointers, rank r's flat gradient
+ * buffer of n + 1 floats (element n = the dudf_scale_guard flag) mapped into this process (CUDA IPC / symmetric memory over
+ * NVLink).  The caller orders the launch behind a cross-rank barrier (every rank's gradient complete) and alternates two buffer
+ * sets per step.  Each rank sums the peers in rank order (bit-identical on all ranks) and applies dudf_adam_step's update;
+ * guarded != 0: skip + count when the summed flag is non-zero; g_sum_out (optional, n floats): the summed gradient. */
+int dudf_adam_step_peers(float* p, const float* const* peer_grads, int world, float* m, float* v, int64_t n, float lr, float beta1,
+                         float beta2, float eps, int64_t t, int guarded, int64_t* skipped, float* g_sum_out, void* stream);
+
 /* MeshUDF marching cubes — HOST code, plain C++17, no device involved.  Replaces
  * _marching_cubes_lewiner_cy.marching_cubes_udf(im, grads, luts, st, classic, avg_thresh, max_thresh, mask)
  * (src/marching_cubes/_marching_cubes_lewiner_cy.pyx:1116-1774) as called by udf_mc_lewiner (_marching_cubes_lewiner.py:80-141)
