@@ -96,6 +96,7 @@ SIGNATURES = {
     "dudf_adam_step_guarded": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64, c_void_p,
                                c_void_p, c_void_p],
     "dudf_scale_guard": [c_void_p, c_void_p, c_float, c_void_p, c_void_p],
+    "dudf_mean_curvature": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     "dudf_adam_step_peers": [c_void_p, ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                              c_int64, c_int, c_void_p, c_void_p, c_void_p],
     "dudf_meshudf_mc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p],

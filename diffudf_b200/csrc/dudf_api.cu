@@ -210,6 +210,25 @@ int dudf_query_grid(dudf_ctx* c, int N, int64_t first, int64_t count, int flags,
   return run_forward(c, nch, nullptr, count, N, first, o, precision, (cudaStream_t)stream);
 }
 
+int dudf_mean_curvature(dudf_ctx* c, const float* x, int64_t P, float* normals, float* dirs, float* mean, void* stream) {
+  DUDF_REQUIRE(c && c->weights_set, "dudf_mean_curvature: weights not set");
+  DUDF_REQUIRE((x && normals && mean) || P == 0, "dudf_mean_curvature: null argument");
+  if (P <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // workspace: H [P][9], lam [P][3], dirs6 [P][6], dirs9 [P][9], jet [P][10]
+  float* ws = nullptr;
+  DUDF_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)P * 37 * sizeof(float), st));
+  float *H = ws, *lam = ws + P * 9, *d6 = ws + P * 12, *d9 = ws + P * 18, *jet = ws + P * 27;
+  QueryOut o{nullptr, nullptr, H, nullptr, nullptr, 0, 0.f};
+  int rc = tcx_forward(c->tcx_packed, c->view(), 10, x, P, 0, 0, o, c->sms, st);
+  if (!rc) rc = eig_normals(H, nullptr, 0, P, normals, dirs ? dirs : d6, lam, st);
+  if (!rc) rc = dirs9(normals, dirs ? dirs : d6, P, d9, st);
+  if (!rc) rc = tcx_forward_dir3(c->tcx_packed, c->view(), x, d9, P, jet, c->sms, st);
+  if (!rc) rc = mean_dir3(jet, lam, P, mean, st);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
 int dudf_eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,
                      void* stream) {
   DUDF_REQUIRE(H && n, "dudf_eig_normals: null argument");

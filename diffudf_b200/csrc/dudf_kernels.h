@@ -38,6 +38,8 @@ int tc_forward(const void* packed, const NetView& net, int nch, const float* x, 
 // ---- split-precision tcgen05 path (dudf_tcx.cu): hi + lo fp16 operands, fp32-grade results ----
 size_t tcx_packed_bytes(int n_lin);
 int tcx_pack(const NetView& net, void* packed, cudaStream_t st);
+int tcx_forward_dir3(const void* packed, const NetView& net, const float* x, const float* dirs, int64_t P, float* out_packed, int sms,
+                     cudaStream_t st);
 int tcx_forward(const void* packed, const NetView& net, int nch, const float* x, int64_t P, int gridN,
                 int64_t grid_first, const QueryOut& out, int sms, cudaStream_t st);
 int tc_selftest(int variant, float* max_err, cudaStream_t st);
@@ -144,6 +146,8 @@ int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
               cudaStream_t st, const float* unsafe = nullptr, long long* skipped = nullptr);
 int adam_step_peers(float* p, const float* const* peer_grads, int world, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                     int64_t t, int guarded, long long* skipped, float* g_sum_out, cudaStream_t st);
+int dirs9(const float* n, const float* dirs6, int64_t P, float* d9, cudaStream_t st);
+int mean_dir3(const float* jet, const float* lam, int64_t P, float* mean, cudaStream_t st);
 int scale_guard(const float* amax_prev, const float* amax_next, float limit, float* flag, cudaStream_t st);
 int transpose256(const float* W, float* Wt, cudaStream_t st);
 int eig_normals(const float* H, const float* ref_dir, int ref_mode, int64_t P, float* n, float* dirs, float* lam,

@@ -353,6 +353,37 @@ int curvature(const float* H, const float* T, int64_t P, float* n, float* mean, 
   return 0;
 }
 
+// ---- mean curvature from the directional third-order jet (dudf_mean_curvature) ----
+// dirs9[p] = (v_0, v_1, n): the three directions the directional jet of point p is taken along
+__global__ void __launch_bounds__(256) dirs9_kernel(const float* __restrict__ n, const float* __restrict__ dirs6, int64_t P, float* __restrict__ d9) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  for (int i = 0; i < 3; ++i) {
+    d9[p * 9 + i] = dirs6[p * 6 + i * 2];
+    d9[p * 9 + 3 + i] = dirs6[p * 6 + i * 2 + 1];
+    d9[p * 9 + 6 + i] = n[p * 3 + i];
+  }
+}
+// mean curvature = tr(dn/dx) / 2 = (T(v_0, v_0, n) / (lam_2 - lam_0) + T(v_1, v_1, n) / (lam_2 - lam_1)) / 2
+__global__ void __launch_bounds__(256) mean_dir3_kernel(const float* __restrict__ jet, const float* __restrict__ lam, int64_t P, float* __restrict__ mean) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double l0 = lam[p * 3], l1 = lam[p * 3 + 1], l2 = lam[p * 3 + 2];
+  mean[p] = (float)(0.5 * ((double)jet[p * 10 + 8] / (l2 - l0) + (double)jet[p * 10 + 9] / (l2 - l1)));
+}
+int dirs9(const float* n, const float* dirs6, int64_t P, float* d9, cudaStream_t st) {
+  if (P <= 0) return 0;
+  dirs9_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(n, dirs6, P, d9);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+int mean_dir3(const float* jet, const float* lam, int64_t P, float* mean, cudaStream_t st) {
+  if (P <= 0) return 0;
+  mean_dir3_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(jet, lam, P, mean);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
 // extract_fields fallback (src/render_mc.py:77-93): where the normalised gradient has norm < 0.04
 // (only possible when grad f == 0 exactly) use the sign-aligned top eigenvector of the Hessian.
 __global__ void __launch_bounds__(256) field_vectors_kernel(const float* __restrict__ g, const float* __restrict__ Hm, int64_t P,

@@ -261,13 +261,55 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
                           //   8 no tile stores, 16 no collector reuse of the weight operand, 32 no accumulator loads
   unsigned long long* trace;
+  const float* dirs;      // DIR3 queries: [P][9] = three unit directions (a, b, c) per point
 };
 
+// ---- directional third-order jet (mean curvature on tensor cores, src/render_st.py:42-62; SURVEY.md §8 a-M) -------------------
+// Ten channels per point for three per-point directions a, b, c (a, b = the two tangent eigen-directions, c = the eigen-normal):
+//   0: f   1-3: D_a, D_b, D_c   4-7: D_aa, D_ac, D_bb, D_bc (x KAPPA)   8-9: D_aac, D_bbc (x KAPPA3)
+// — everything the chain rule of sin needs to carry D^3 f[a, a, c] and D^3 f[b, b, c] through the layers, and exactly what
+// tr(dn/dx) = sum_j T(v_j, v_j, n) / (lambda_2 - lambda_j) consumes: the same 128-column tile as the Hessian jet instead of the
+// 20-channel full third-order jet on the CUDA cores.
+constexpr float TCX_KAPPA3 = 1.f / 256.f, TCX_KAPPA3_INV = 256.f;
+template <int GC>
+__device__ __forceinline__ void tcx_first_layer_dir(float* u, const float* pts, float w0, float r0x, float r0y, float r0z, float b0) {
+#pragma unroll
+  for (int pp = 0; pp < GC / 10; ++pp) {
+    const float* q = pts + pp * 12;
+    float* up = u + pp * 10;
+    up[0] = w0 * fmaf(r0z, q[2], fmaf(r0y, q[1], fmaf(r0x, q[0], b0)));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) up[1 + d] = w0 * fmaf(r0z, q[5 + 3 * d], fmaf(r0y, q[4 + 3 * d], r0x * q[3 + 3 * d]));
+#pragma unroll
+    for (int ch = 4; ch < 10; ++ch) up[ch] = 0.f;
+  }
+}
+// stored pre-activations (derivative channels still times 1 / inv) -> stored activations, in place; u[0] is not read
+__device__ __forceinline__ void tcx_act_point_dir(float* u, float s, float c, float inv) {
+  const float ci = c * inv;
+  const float za = inv * u[1], zb = inv * u[2], zc = inv * u[3];
+  const float vaa = inv * u[4], vac = inv * u[5], vbb = inv * u[6], vbc = inv * u[7];
+  constexpr float K32 = TCX_KAPPA3 / TC_KAPPA;
+  const float s32 = K32 * s, c3 = TCX_KAPPA3 * c, ks = TC_KAPPA * s;
+  u[8] = fmaf(ci, u[8], -fmaf(s32, fmaf(vaa, zc, 2.f * vac * za), c3 * za * za * zc));
+  u[9] = fmaf(ci, u[9], -fmaf(s32, fmaf(vbb, zc, 2.f * vbc * zb), c3 * zb * zb * zc));
+  u[4] = fmaf(c, vaa, -ks * za * za);
+  u[5] = fmaf(c, vac, -ks * za * zc);
+  u[6] = fmaf(c, vbb, -ks * zb * zb);
+  u[7] = fmaf(c, vbc, -ks * zb * zc);
+  u[1] = c * za;
+  u[2] = c * zb;
+  u[3] = c * zc;
+  u[0] = s;
+}
+
 // all layers of one 128-column tile.  x == null: grid points (first + p).  TRAIN: stash the pre-activations, write raw channels.
-template <int NCH, bool TRAIN, int SC, int EW>
+template <int NCH, bool TRAIN, int SC, int EW, bool DIR = false>
 __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const float* __restrict__ x, int64_t P, int gridN, int64_t grid_first,
                                          float vs, int64_t tile, bool valid, const QueryOut& out, float* outp, float* Ust, int64_t ld, int64_t colt,
-                                         int dbg) {
+                                         int dbg, const float* __restrict__ dirs = nullptr) {
+  static_assert(!DIR || (NCH == 10 && !TRAIN), "directional third-order jet: 10 channels, queries only");
+  constexpr int XS = DIR ? 12 : 3;             // floats per point in xs: the point (+ its three directions)
   using C = TcxCfg<NCH>;
   constexpr int GC = C::GC;
   const int L = net.n_lin - 1;
@@ -281,7 +323,11 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       if (x) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
       else grid_point(grid_first + p, gridN, vs, pt);
     }
-    e.xs[i * 3] = pt[0]; e.xs[i * 3 + 1] = pt[1]; e.xs[i * 3 + 2] = pt[2];
+    e.xs[i * XS] = pt[0]; e.xs[i * XS + 1] = pt[1]; e.xs[i * XS + 2] = pt[2];
+    if constexpr (DIR) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) e.xs[i * XS + 3 + k] = (valid && p < P) ? dirs[p * 9 + k] : 0.f;
+    }
   }
   if (C::NV < 128 && e.tid < 256) {       // idle columns of both tiles are zero for this tile's math (a launch may mix jet orders)
     *reinterpret_cast<uint4*>(tc_tile_row(e.act, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
@@ -310,7 +356,8 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       auto group = [&](int g) {
         float u[GC];
         if (l == 0) {
-          tc_first_layer_group<NCH, GC>(u, e.xs + g * (GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
+          if constexpr (DIR) tcx_first_layer_dir<GC>(u, e.xs + g * (GC / NCH) * XS, w0, r0x, r0y, r0z, b0);
+          else tc_first_layer_group<NCH, GC>(u, e.xs + g * (GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
         } else {
           if (dbg & 32) {            // diagnostics: no accumulator loads
 #pragma unroll
@@ -340,6 +387,7 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
             if constexpr (SC == 1) sincos_poly(u[pp * NCH], sn, cs);
             else sincos_fast(u[pp * NCH], sn, cs);
             if constexpr (TRAIN) tc_act_point<NCH>(u + pp * NCH, sn, cs);
+            else if constexpr (DIR) tcx_act_point_dir(u + pp * NCH, sn, cs, l == 0 ? 1.f : TCX_WSCALE_INV);
             else tc_act_point_scaled<NCH>(u + pp * NCH, sn, cs, l == 0 ? 1.f : TCX_WSCALE_INV);
           }
         }
@@ -378,7 +426,8 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
 #pragma unroll
     for (int k = 0; k < 8; ++k) v += e.os[k * 128 + e.tid];
     const int ch = e.tid % NCH;
-    e.os[e.tid] = (ch == 0) ? v + net.b[L][0] : (ch >= 4 ? v * TC_KAPPA_INV : v);
+    if constexpr (DIR) e.os[e.tid] = (ch == 0) ? v + net.b[L][0] : (ch >= 8 ? v * TCX_KAPPA3_INV : (ch >= 4 ? v * TC_KAPPA_INV : v));
+    else e.os[e.tid] = (ch == 0) ? v + net.b[L][0] : (ch >= 4 ? v * TC_KAPPA_INV : v);
   }
   tcx_epi_bar<EW>();
   if (e.tid < C::PT) {
@@ -397,7 +446,7 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
 
 // One launch serves up to two row segments with different jet orders (training: on-surface rows carry the Hessian jet).
 // Queries use segment a only (x == null: grid points).
-template <int NA, int NB, int CL, bool TRAIN, int SC, int EW>
+template <int NA, int NB, int CL, bool TRAIN, int SC, int EW, bool DIR = false>
 __global__ void __launch_bounds__((EW + 4) * 32, 1)
 tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev sa, SegDev sb, int64_t tiles_a, int64_t tiles_b, int gridN,
                    int64_t grid_first, QueryOut out, TcxTrain tr) {
@@ -454,7 +503,7 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
       const bool valid = tile < ntiles;
       const int64_t colt = tr.col0 + tile * 128;
       if (!valid || tile < tiles_a) {
-        tcx_tile<NA, TRAIN, SC, EW>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, tr.dbg);
+        tcx_tile<NA, TRAIN, SC, EW, DIR>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, tr.dbg, tr.dirs);
       } else {
         if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC, EW>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, tr.dbg);
       }
@@ -476,10 +525,10 @@ static int tcx_cluster_size() {
   return v;
 }
 
-template <int NA, int NB, int CL, bool TRAIN, int SC, int EW>
+template <int NA, int NB, int CL, bool TRAIN, int SC, int EW, bool DIR = false>
 static int tcx_launch(const void* packed, const NetView& net, const SegDev& a, const SegDev& b, int64_t ta, int64_t tb, int gridN, int64_t first,
                       const QueryOut& out, const TcxTrain& tr, int sms, cudaStream_t st) {
-  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN, SC, EW>;
+  auto k = tcx_forward_kernel<NA, NB, CL, TRAIN, SC, EW, DIR>;
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
   const int64_t ntiles = ta + tb;
   int grid = (int)std::min<int64_t>(ntiles, sms);
@@ -578,6 +627,32 @@ int tcx_forward(const void* packed, const NetView& net, int nch, const float* x,
   DUDF_REQUIRE(false, "split tensor-core path: unsupported channel count %d", nch);
 }
 
+// directional third-order jet of P points: packed [P][10] raw channels (see tcx_first_layer_dir)
+int tcx_forward_dir3(const void* packed, const NetView& net, const float* x, const float* dirs, int64_t P, float* out_packed, int sms,
+                     cudaStream_t st) {
+  SegDev a, b;
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  a.x = x;
+  a.P = P;
+  TcxTrain tr;
+  memset(&tr, 0, sizeof(tr));
+  tr.dbg = tcx_dbg();
+  tr.dirs = dirs;
+  QueryOut out;
+  memset(&out, 0, sizeof(out));
+  out.packed = out_packed;
+  const int64_t tiles = (P + TcxCfg<10>::PT - 1) / TcxCfg<10>::PT;
+  int cl = tcx_cluster_size();
+  while (cl > 1 && tiles < 2 * cl) cl >>= 1;
+  if (tcx_sincos_mode() == 0) {
+    if (cl >= 2) return tcx_launch<10, 0, 2, false, 0, 8, true>(packed, net, a, b, tiles, 0, 0, 0, out, tr, sms, st);
+    return tcx_launch<10, 0, 1, false, 0, 8, true>(packed, net, a, b, tiles, 0, 0, 0, out, tr, sms, st);
+  }
+  if (cl >= 2) return tcx_launch<10, 0, 2, false, 1, 8, true>(packed, net, a, b, tiles, 0, 0, 0, out, tr, sms, st);
+  return tcx_launch<10, 0, 1, false, 1, 8, true>(packed, net, a, b, tiles, 0, 0, 0, out, tr, sms, st);
+}
+
 // training forward: same stash / operand-image layout and column allocation (256 columns per sub-tile pair) as tc_train_forward
 int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* segs, int nseg, float* Ust, void* Aimg, int64_t ld, int64_t col0,
                       int sms, cudaStream_t st) {
@@ -596,7 +671,7 @@ int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* s
   const int na = segs[0].nch, nb = nseg == 2 ? segs[1].nch : 0;
   const int64_t ta = 2 * a.npairs, tb = 2 * b.npairs;       // whole pairs: the reverse sweep reads the stash of a padding sub-tile too
   DUDF_REQUIRE(col0 + (ta + tb) * 128 <= ld, "tensor-core stash too small");
-  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0, 0, nullptr};
+  TcxTrain tr{Ust, (unsigned char*)Aimg, ld, col0, 0, nullptr, nullptr};
   QueryOut out;
   memset(&out, 0, sizeof(out));
   if (nb == 0) {

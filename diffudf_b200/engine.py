@@ -171,6 +171,18 @@ class Engine:
                                              J.data_ptr(), _lib.current_stream()), "dudf_curvature")
         return n, mean, gauss, J
 
+    def mean_curvature(self, x):
+        """Eigen-normals, principal directions and mean curvature at x (P,3) on tensor cores (dudf_mean_curvature): Hessian jet,
+        eigen-solve and the 10-channel directional third-order jet.  Returns (normals (P,3), dirs (P,3,2), mean (P,))."""
+        P = x.shape[0]
+        n = torch.empty(P, 3, device=x.device, dtype=torch.float32)
+        dirs = torch.empty(P, 3, 2, device=x.device, dtype=torch.float32)
+        mean = torch.empty(P, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(self.L.dudf_mean_curvature(self.h, x.data_ptr(), P, n.data_ptr(), dirs.data_ptr(), mean.data_ptr(),
+                                                  _lib.current_stream()), "dudf_mean_curvature")
+        return n, dirs, mean
+
     def field_vectors(self, g, H):
         vecs = torch.empty_like(g)
         with torch.cuda.device(g.device):

@@ -112,7 +112,10 @@ def hit_attributes(model, points, ray_dirs=None, curvature="mean"):
     eng = model._engine_synced()
     x = points.to(torch.float32).contiguous()
     out = {}
-    if curvature in ("mean", "gaussian"):
+    if curvature == "mean" and model.precision == "tcx3":
+        # tensor-core route: Hessian jet + eigen-solve + 10-channel directional third-order jet (engine.mean_curvature)
+        n, dirs, out["mean"] = eng.mean_curvature(x)
+    elif curvature in ("mean", "gaussian"):
         _, _, H, T = eng.query(x, 3, "fp32")
         n, mean, gauss, _ = eng.curvature(H, T)
         out["mean"], out["gauss"] = mean, gauss

@@ -79,13 +79,13 @@ class FusedTrainer:
         self._use_set(0)
         self.core = TrainCore(model, precision)
         self.t = 0
-        # data parallel: the gradient all-reduce of a finished layer group runs on a side stream under the next group's
-        # weight-gradient GEMM (tensor-core precisions; DUDF_DP_GROUPS=1 restores the single blocking all-reduce)
+        # NCCL route (no peer memory): one all-reduce of the flat gradient.  DUDF_DP_GROUPS=g > 1 launches the weight-gradient GEMMs
+        # in g layer groups and all-reduces each finished group on a side stream under the next group's GEMM — measured SLOWER at
+        # N = 2 (1.250 vs 1.226 ms / step: the collective is latency-bound, two of them cost more than one hides), so it is opt-in
         self.groups, self.side = None, None
         if dp is not None:
-            import os
             from .parallel import grad_groups
-            ng = int(os.environ.get("DUDF_DP_GROUPS", "2"))
+            ng = int(os.environ.get("DUDF_DP_GROUPS", "1"))
             if ng > 1:
                 self.groups = grad_groups([(w.numel(), b.numel()) for w, b in zip(ws, bs)], ng)
                 self.side = torch.cuda.Stream(dev)

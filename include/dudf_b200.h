@@ -261,6 +261,13 @@ int dudf_scale_guard(const float* amax_prev, const float* amax_next, float limit
 int dudf_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                            float eps, int64_t t, const float* unsafe_flag, int64_t* skipped, void* stream);
 
+/* Eigen-normals, principal directions and MEAN curvature of P points on tensor cores (split-precision mode): replaces
+ * compute_normals_and_cd + compute_curvature(..., 'mean') of src/render_st.py:42-62 (autograd Hessian, torch.linalg.eigh, autograd
+ * Jacobian of the eigen-normal).  Hessian jet -> 3x3 eigen-solve -> a 10-channel DIRECTIONAL third-order jet along (v_0, v_1, n) per
+ * point (SURVEY 8 a-M) -> tr(dn/dx) / 2 = (T(v_0,v_0,n) / (lam_2 - lam_0) + T(v_1,v_1,n) / (lam_2 - lam_1)) / 2.
+ * normals [P][3], dirs [P][3][2] (may be NULL), mean [P]: fp32 device arrays, eigenvector signs canonical as dudf_eig_normals. */
+int dudf_mean_curvature(dudf_ctx* ctx, const float* x, int64_t P, float* normals, float* dirs, float* mean, void* stream);
+
 /* Data-parallel optimiser step with the gradient all-reduce fused in (the reference has no distributed code — this is
  * the one exchange step of the sharded training path): peer_grads = HOST array of `world` DEVICE pointers, rank r's flat gradient
  * buffer of n + 1 floats (element n = the dudf_scale_guard flag) mapped into this process (CUDA IPC / symmetric memory over

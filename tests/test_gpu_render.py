@@ -78,6 +78,20 @@ def test_sphere_tracing_and_curvature(golden, oracle, weights, cuda_models):
     assert rel_max(gauss, R["gauss64"]) < 5e-3
     attrs = render_st.hit_attributes(m, pts, torch.from_numpy(R["rays"][R["hits"]]).cuda(), "mean")
     assert rel_max(np.abs(attrs["mean"].cpu().numpy()), np.abs(R["mean64"])) < 2e-3
+    # tensor-core route: Hessian jet + eigen-solve + 10-channel DIRECTIONAL third-order jet on the split-precision
+    # tcgen05 kernel (dudf_mean_curvature) against the same float64 truth of the unmodified reference, same tolerance
+    prec = m.precision
+    try:
+        m.precision = "tcx3"
+        a3 = render_st.hit_attributes(m, pts, torch.from_numpy(R["rays"][R["hits"]]).cuda(), "mean")
+    finally:
+        m.precision = prec
+    e_tc = rel_max(np.abs(a3["mean"].cpu().numpy()), np.abs(R["mean64"]))
+    n3 = a3["normals"].cpu().numpy()
+    print(f"mean curvature on tensor cores: {e_tc:.2e} of the range; normals |dot| min {np.min(np.abs(np.sum(n3 * R['n64'], axis=1))):.6f}")
+    assert e_tc < 2e-3
+    assert np.min(np.abs(np.sum(n3 * R["n64"], axis=1))) > 1 - 1e-4
+    assert np.allclose(np.abs(a3["mean"].cpu().numpy()), np.abs(attrs["mean"].cpu().numpy()), rtol=0, atol=2e-3 * np.abs(R["mean64"]).max())
 
 
 def test_point_projection(golden, oracle, weights, cuda_models):
