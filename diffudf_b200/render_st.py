@@ -195,17 +195,37 @@ def create_projectional_image(model, rays, t0, mask_rays, network_config, render
     and the shading all run on the device; the percentile clip of the curvature colour map (a global statistic over the hits) and
     the colour-map lookup are the reference's numpy expressions on the (H,) curvature vector."""
     dev = torch.device(device)
-    hits = propagate_rays(model, rays, t0, mask_rays, network_config, rendering_config, device)
-    grad_descent(model, t0, hits, network_config, rendering_config, device)
-    pts = torch.from_numpy(np.ascontiguousarray(t0[hits], dtype=np.float64)).to(dev)
+    eng = model._engine_synced()
+    # one upload of the ray set; marching, refinement, attributes and shading work on device-resident state, the reference's in-place
+    # contract on t0 / mask_rays is honoured with one download each
+    rays_d = torch.from_numpy(np.ascontiguousarray(rays, dtype=np.float64)).to(dev)
+    t0_d = torch.from_numpy(np.ascontiguousarray(t0, dtype=np.float64)).to(dev)
+    idx = torch.nonzero(torch.from_numpy(np.asarray(mask_rays, dtype=bool)).to(dev)).reshape(-1)
+    hits_d, idx, _ = _march(model, rays_d, t0_d, idx, network_config["gt_mode"], network_config["alpha"],
+                            rendering_config["surface_threshold"], rendering_config["max_iterations"])
+    if int(hits_d.sum()) == 0:
+        raise ValueError(f"Ray tracing did not converge in {rendering_config['max_iterations']} iterations to any point at "
+                         f"distance {rendering_config['surface_threshold']} or lower from surface.")
+    pts = t0_d[hits_d]
+    for _ in range(rendering_config["gd_steps"]):          # grad_descent (:163-172) on the hit points
+        f, g, _, _ = eng.query(pts.to(torch.float32).contiguous(), 1, model.precision)
+        gn = g / torch.linalg.norm(g, dim=1, keepdim=True)
+        steps = inverse_torch(network_config["gt_mode"], f.abs(), network_config["alpha"])
+        pts = pts - (gn * steps[:, None]).to(torch.float64)
+    if rendering_config["gd_steps"] > 0:
+        t0_d[hits_d] = pts
+    t0[...] = t0_d.cpu().numpy()
+    still = torch.zeros(t0_d.shape[0], dtype=torch.bool, device=dev)
+    still[idx] = True
+    mask_rays[...] = still.cpu().numpy()
     shape = (rendering_config["height"], rendering_config["width"], 3)
     if network_config["gt_mode"] == "siren":
-        eng = model._engine_synced()
         _, g, _, _ = eng.query(pts.to(torch.float32).contiguous(), 1, model.precision)
         normals = (g / torch.linalg.norm(g, dim=1, keepdim=True)).to(torch.float64)
-        return phong_shading(rendering_config["light_position"], rendering_config["shininess"], hits, t0, normals).reshape(shape)
+        return _shade(0, rendering_config["light_position"], None, hits_d, t0_d, normals, shininess=rendering_config["shininess"]
+                      ).cpu().numpy().reshape(shape)
     kind = rendering_config["plot_curvatures"] if rendering_config["plot_curvatures"] in ("mean", "gaussian") else None
-    att = hit_attributes(model, pts, torch.from_numpy(np.ascontiguousarray(rays[hits])).to(dev), curvature=kind)
+    att = hit_attributes(model, pts, rays_d[hits_d], curvature=kind)
     normals = att["normals"].to(torch.float64)
     colours = None
     if kind is not None:
@@ -215,10 +235,11 @@ def create_projectional_image(model, rays, t0, mask_rays, network_config, render
         curv /= np.max(curv)
         colours = _rdylbu(curv.squeeze(1))
     if rendering_config["reflection_method"] == "blinn-phong":
-        return phong_shading(rendering_config["light_position"], rendering_config["shininess"], hits, t0, normals, color_map=colours).reshape(shape)
+        return _shade(0, rendering_config["light_position"], None, hits_d, t0_d, normals, shininess=rendering_config["shininess"],
+                      color_map=colours).cpu().numpy().reshape(shape)
     if rendering_config["reflection_method"] == "ward":
         dirs = att["dirs"].to(torch.float64)
-        return ward_reflectance(rendering_config["light_position"], rendering_config["camera_position"], hits, t0, normals,
-                                alpha1=rendering_config["alpha1"], alpha2=rendering_config["alpha2"], pc1=dirs[..., 0].contiguous(),
-                                pc2=dirs[..., 1].contiguous(), color_map=colours).reshape(shape)
+        return _shade(1, rendering_config["light_position"], rendering_config["camera_position"], hits_d, t0_d, normals,
+                      alpha1=rendering_config["alpha1"], alpha2=rendering_config["alpha2"], pc1=dirs[..., 0].contiguous(),
+                      pc2=dirs[..., 1].contiguous(), color_map=colours).cpu().numpy().reshape(shape)
     raise KeyError(rendering_config["reflection_method"])

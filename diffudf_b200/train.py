@@ -197,8 +197,16 @@ class BatchFeeder:
 
 
 def _epoch_loop(dataset, model, device, config, stage_fn):
+    """config['dp'] (parallel.DataParallel): every rank iterates the SAME dataset (same seed) and trains on its share of each row
+    group of every batch (parallel.shard_batch), so the job as a whole sees the reference's batches; the loss means are taken
+    over the global row count.  Ignored keys of the reference's config (`optimizer.type`, `log_path`, checkpoint / plot settings:
+    file IO and TensorBoard are left to the caller) raise nothing; an optimizer other than Adam raises."""
     epochs = config["epochs"]
-    trainer = FusedTrainer(model.to(device), dp=config.get("dp"), precision=config.get("precision"))
+    opt = config.get("optimizer")
+    if isinstance(opt, dict) and str(opt.get("type", "adam")).lower() != "adam":
+        raise NotImplementedError(f"optimizer {opt.get('type')!r}: the fused loop implements torch.optim.Adam (train.py:334-337)")
+    dp = config.get("dp")
+    trainer = FusedTrainer(model.to(device), dp=dp, precision=config.get("precision"))
     feeder = BatchFeeder(device)
     losses, best_loss, best_weights = {}, np.inf, None
     torch.cuda.synchronize(device)
@@ -206,15 +214,34 @@ def _epoch_loop(dataset, model, device, config, stage_fn):
     for epoch in range(epochs):
         mode, keys, weights, lr = stage_fn(epoch)
         running = torch.zeros(4, device=device, dtype=torch.float64)
+        misplaced = torch.zeros(1, device=device, dtype=torch.int64)      # rows that contradict the [on | off] layout (read per epoch)
         for x, n, d in feeder.feed((tuple(torch.as_tensor(t, dtype=torch.float32) for t in b) for b in iter(dataset))):
             n_on = getattr(dataset, "samplesOnSurface", None)
-            if n_on is None and mode == "s1" and weights[2] != 0:
+            need_on = mode == "s1" and weights[2] != 0
+            if n_on is None and need_on:
                 from .loss_functions import on_surface_prefix
                 n_on = on_surface_prefix(d)
                 if n_on is None:
                     raise RuntimeError("batches must be ordered [on-surface | off-surface] for the fused step")
-            running += trainer.step(mode, x, n, d, n_on or 0, weights, config.get("alpha", 0.0), lr)
+            elif need_on:
+                # the reference masks the alignment term on d == 0 (loss_functions.py:45-53); the fused step takes the first n_on
+                # rows: count disagreements on the device, raise at the epoch's read-back
+                misplaced += (d[:n_on] != 0).sum() + (d[n_on:] == 0).sum()
+            n_on = n_on or 0
+            if dp is not None and dp.world > 1:
+                from .parallel import shard_batch
+                P = x.shape[0]
+                n_far = (P - n_on) // 2                 # [on | far | near] with far = half of the off-surface rows (src/dataset.py:92-94)
+                dp.rows_global = P
+                x, n, d, n_on = shard_batch(x, n, d, n_on, n_far, dp.rank, dp.world)
+                x, n, d = x.contiguous(), n.contiguous(), d.contiguous()
+            running += trainer.step(mode, x, n, d, n_on, weights, config.get("alpha", 0.0), lr)
+        if dp is not None and dp.world > 1:
+            dp.reduce_terms(running)
         vals = running.cpu().numpy()                        # one read-back per epoch
+        if int(misplaced.item()) != 0:
+            raise RuntimeError(f"{int(misplaced.item())} rows of this epoch's batches contradict the [on-surface (d == 0) | off-surface] layout "
+                               "the fused loss_s1 step relies on (dataset.samplesOnSurface leading rows)")
         epoch_loss = 0.0
         for i, k in enumerate(keys):
             losses.setdefault(k, [0.0] * epochs)[epoch] = float(vals[i])

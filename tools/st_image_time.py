@@ -13,7 +13,7 @@ W = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 m = SIREN(3, 1, [256] * 8, w0=30, delay_init=True)
 m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(W[f"{'W' if k == 'weight' else 'b'}{i}"]) for i in range(9) for k in ("weight", "bias")})
 m = m.cuda()
-m.precision = "tc16"
+m.precision = sys.argv[1] if len(sys.argv) > 1 else "tcx3"
 R = 1024
 cam = np.array([0.8939, 0.7, 2.86]) * 0.45
 u, v = np.meshgrid(np.linspace(-0.6, 0.6, R), np.linspace(-0.6, 0.6, R))
