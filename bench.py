@@ -512,6 +512,7 @@ def run_ours(args, rank, local_rank, world):
         Ng = 512
         lo, hi = shard_range(Ng ** 3, rank, world)
         extract_fields(model, None, 64, "tanh", dev, ALPHA)
+        extract_fields_sharded(model, 64, "tanh", ALPHA, dp)        # untimed: NCCL's first all-gather sets up its channels (~0.2 s once)
         barrier()
         q0, q1, q2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         q0.record()

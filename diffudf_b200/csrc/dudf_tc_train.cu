@@ -253,6 +253,7 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
   const int L = net.n_lin - 1;
   const float invS = 1.0f / S;
   float* sd = e.os;                                               // stored seeds of both sub-tiles [2][256]
+  tc_trace(e.trace, e.tn, 14, NCH);
   tc_epi_bar();
   for (int i = e.tid; i < 2 * C::PT; i += 256) {
     const int64_t p = pair * 2 * C::PT + i;
@@ -286,29 +287,33 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
       constexpr int NRAW = Stash<NCH, C::GC>::CHUNKS;
       uint4 nxt[NRAW];
       tt_stash_load<NCH, C::GC>(nxt, ust);                       // in flight while we wait for the accumulator
+      tc_trace(e.trace, e.tn, 40 + s, l);
       if (!top) {
         mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
         e.acc_phase ^= 1u << s;
         tc_fence_after();
       }
+      tc_trace(e.trace, e.tn, 30 + s, l);
       float bsum = 0.f, wlsum = 0.f, w0s[3] = {0.f, 0.f, 0.f};
       TmemRegs<C::GC> tr;
-      if (!top) tc_ld_issue<C::GC>(e.tmem_lane + s * 256, tr);
 #pragma unroll 1
       for (int g = 0; g < C::NGRP; ++g) {
         uint4 ug[NRAW];
 #pragma unroll
         for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
         if (g + 1 < C::NGRP) tt_stash_load<NCH, C::GC>(nxt, ust + (size_t)(g + 1) * C::GC * 256);
-        const uint32_t tnext = (g + 1 < C::NGRP) ? e.tmem_lane + s * 256 + (g + 1) * C::GC : 0u;
+        // the group's own accumulators are loaded inside the group and used in place (NOW): the TMEM load hides behind the stash
+        // conversion, and ptxas no longer copies the 32 / 40 staging registers of a prefetched group out and back
+        const uint32_t tcur = e.tmem_lane + s * 256 + g * C::GC;
         const float* sdg = sd + s * 256 + g * C::GC;
         const float* pts = e.xs + (s * C::PT + g * (C::GC / NCH)) * 3;
         const int c0 = g * (C::GC / 8);
-        if (top && first) tt_bwd_group<NCH, C::GC, true, true>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else if (top)     tt_bwd_group<NCH, C::GC, true, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else if (first)   tt_bwd_group<NCH, C::GC, false, true>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else              tt_bwd_group<NCH, C::GC, false, false>(ug, tr, tnext, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        if (top && first) tt_bwd_group<NCH, C::GC, true, true, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (top)     tt_bwd_group<NCH, C::GC, true, false, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (first)   tt_bwd_group<NCH, C::GC, false, true, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else              tt_bwd_group<NCH, C::GC, false, false, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
       }
+      tc_trace(e.trace, e.tn, 32 + s, l);
       atomicAdd(&grad.b[l][e.n], bsum * wl_cur * invS);
       if (top) atomicAdd(&grad.W[L][e.n], wlsum * invS);
       if (first) {
@@ -328,7 +333,7 @@ template <int NA, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradView grad, SegDev sa, SegDev sb,
                    const float* __restrict__ seed_absmax, const float* __restrict__ Ust, unsigned char* __restrict__ Zimg, int64_t ld,
-                   int64_t col0) {
+                   int64_t col0, unsigned long long* trace) {
   using C = TcCfg<NA>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -357,12 +362,14 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
     if (warp == 8) {
       if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BWD);
     } else if (warp == 9) {
-      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD);
+      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD, 0, 0ull,
+                     (trace && blockIdx.x == 0) ? trace : nullptr);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
     const int q = warp & 3, h = warp >> 2;
     EpiCtx e;
+    e.trace = (trace && blockIdx.x == 0 && warp == 0) ? trace + TC_TRACE_REGION : nullptr;
     e.act = act; e.xs = (float*)(smem + C::OFF_XS); e.os = (float*)(smem + C::OFF_OS); e.wl_s = nullptr;
     e.act_ready = act_ready; e.acc_ready = acc_ready;
     e.n = h * 128 + q * 32 + lane; e.tid = tid; e.lane = lane; e.r7 = e.n & 7;
@@ -505,7 +512,8 @@ static int tt_launch_bwd(const void* packed, const NetView& net, const GradView&
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
   const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
   if (grid < 1) return 0;
-  k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, seed_absmax, Ust, (unsigned char*)Zimg, ld, col0);
+  k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, seed_absmax, Ust, (unsigned char*)Zimg, ld, col0,
+                                               tc_get_trace());
   DUDF_LAUNCH_OK();
   return 0;
 }
