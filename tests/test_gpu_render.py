@@ -106,3 +106,25 @@ def test_point_projection(golden, oracle, weights, cuda_models):
     if pts.shape[0] == Pc["points"].shape[0]:
         assert np.max(np.abs(pts - Pc["points"])) < 1e-3
         assert np.median(np.abs(np.sum(nrm * Pc["normals"], axis=1))) > 0.999
+
+
+@pytest.mark.parametrize("P", [1, 11, 12, 13, 500, 4097])
+def test_mean_curvature_on_tensor_cores_matches_the_third_order_route(P, cuda_models):
+    """dudf_mean_curvature (Hessian jet -> eigen-solve -> 10-channel directional third-order jet on the split-precision tcgen05
+    kernel) against the fp32 CUDA-core route (full 20-channel third-order jet + dudf_curvature, itself held to the reference's
+    float64 curvature in test_sphere_tracing_and_curvature) at random points near the trained surface; tile boundaries of the
+    12-point jet-10 tiles included."""
+    m = cuda_models["trained"]
+    eng = m._engine_synced()
+    rng = np.random.default_rng(P)
+    x = torch.from_numpy(rng.uniform(-0.5, 0.5, (P, 3)).astype(np.float32)).cuda()
+    n3, dirs3, mean3 = eng.mean_curvature(x)
+    _, _, H, T = eng.query(x, 3, "fp32")
+    n, mean, _, _ = eng.curvature(H, T)
+    _, dirs, lam = eng.eig_normals(H, want_dirs=True, want_lam=True)
+    gap = (lam[:, 2:3] - lam[:, :2]).abs().min(dim=1).values          # the curvature carries 1 / (lambda_2 - lambda_j)
+    ok = gap > 1e-2 * lam.abs().max()
+    assert float(((n3 * n).sum(-1).abs()[ok]).min()) > 1 - 1e-4 if bool(ok.any()) else True
+    scale = float(mean.abs()[ok].max()) if bool(ok.any()) else 1.0
+    err = float(((mean3.abs() - mean.abs()).abs()[ok]).max()) / max(scale, 1e-6) if bool(ok.any()) else 0.0
+    assert err < 2e-3, (P, err, scale)

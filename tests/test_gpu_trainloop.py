@@ -108,3 +108,32 @@ def test_fused_step_skips_the_update_when_the_loss_scale_is_outgrown(weights):
     tr.step("s1", x, n, d, n_on, w, 100.0, 1e-6)
     assert tr.skipped_steps() == 1 and not torch.equal(tr.flat, before)
     assert bool(torch.isfinite(tr.flat).all())
+
+
+def test_adam_step_peers_with_one_rank_equals_adam_step():
+    """dudf_adam_step_peers (gradient sum over peer-mapped buffers fused into Adam) with a single 'peer' — this process's own buffer —
+    is dudf_adam_step bit for bit, including the tail that is not a multiple of 4 and the guard flag behind the gradient."""
+    import ctypes
+    from diffudf_b200.engine import adam_step, adam_step_peers
+    torch.manual_seed(0)
+    n = 4099
+    g_all = torch.randn(n + 1, device="cuda")
+    g_all[-1] = 0.0
+    p1, m1, v1 = torch.randn(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p2, m2, v2 = p1.clone(), m1.clone(), v1.clone()
+    ptrs = (ctypes.c_void_p * 1)(g_all.data_ptr())
+    gsum = torch.zeros(n, device="cuda")
+    skipped = torch.zeros(1, device="cuda", dtype=torch.int64)
+    for t in (1, 2, 3):
+        adam_step(p1, g_all[:n], m1, v1, 1e-3, t)
+        adam_step_peers(p2, ptrs, 1, m2, v2, 1e-3, t, guarded=True, skipped=skipped, g_sum_out=gsum)
+    assert torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2) and torch.equal(gsum, g_all[:n]) and int(skipped) == 0
+    # two "ranks" that are the same buffer: the sum is 2 g, in rank order
+    ptrs2 = (ctypes.c_void_p * 2)(g_all.data_ptr(), g_all.data_ptr())
+    adam_step_peers(p2, ptrs2, 2, m2, v2, 1e-3, 4, g_sum_out=gsum)
+    assert torch.equal(gsum, g_all[:n] + g_all[:n])
+    # a raised guard flag skips the update on "every rank" and is counted
+    g_all[-1] = 1.0
+    before = p2.clone()
+    adam_step_peers(p2, ptrs, 1, m2, v2, 1e-3, 5, guarded=True, skipped=skipped)
+    assert torch.equal(p2, before) and int(skipped) == 1
