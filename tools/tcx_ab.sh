@@ -3,9 +3,8 @@
 out=${1:-gpurun_out/tcx_ab.txt}
 : > $out
 run() { env "$@" timeout 200 python tools/tcx_check.py grid train >> $out 2>&1; }
-run DUDF_TCX_SINCOS=poly
-run DUDF_TCX_SINCOS=poly DUDF_TCX_DBG=64
-run DUDF_TCX_SINCOS=mufu
-run DUDF_TCX_SINCOS=mufu DUDF_TCX_DBG=64
-run DUDF_TCX_SINCOS=poly DUDF_TCX_DBG=16
+run DUDF_TCX_DBG=0
+run DUDF_TCX_DBG=64
+run DUDF_TCX_DBG=0 DUDF_TCX_SINCOS=poly
+run DUDF_TCX_DBG=64 DUDF_TCX_SINCOS=poly
 grep "probe\|train tcx3" $out
