@@ -107,6 +107,17 @@ int dudf_create(int n_hidden, float w0, float ww, dudf_ctx** out) {
   }
   DUDF_CUDA_OK(cudaMalloc(&c->tc_packed, tc_packed_bytes(c->n_lin)));
   DUDF_CUDA_OK(cudaMalloc(&c->tcx_packed, tcx_packed_bytes(c->n_lin)));
+  // stream-ordered scratch (cudaMallocAsync in the samplers, the mesh distance, dudf_mean_curvature, the ray / projection drivers):
+  // keep freed blocks in the device's default pool instead of returning them to the driver at every synchronisation (the default
+  // release threshold is 0: a 25 MB workspace re-mapped per call cost 10 ... 850 ms on a multi-GPU box)
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   *out = c;
   return 0;
 }

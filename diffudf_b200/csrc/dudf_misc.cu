@@ -125,6 +125,18 @@ int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream
 // this step's seeds outgrew that scale (scale_guard_kernel below, summed over the ranks by the gradient all-reduce) the gradient
 // may hold saturated adjoints, so the update is skipped on every rank — what torch.cuda.amp.GradScaler does on overflow — and
 // counted.  The next step's scale comes from this step's magnitude, so at most one step is lost per jump.
+// one element of torch.optim.Adam.step (no weight decay, no amsgrad), every operation pinned (no contraction left to the compiler) so
+// that the plain and the peer-reducing kernel give bit-identical parameters for the same summed gradient
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float step_size, float bc2_sqrt, float b1, float b2,
+                                            float eps) {
+  const float mi = __fmaf_rn(b1, m, __fmul_rn(1.f - b1, g));                       // exp_avg.lerp_(grad, 1-beta1)
+  const float vi = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.f - b2, g), g));         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  m = mi;
+  v = vi;
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+  p = __fmaf_rn(-step_size, __fdiv_rn(mi, denom), p);
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float step_size, float bc2_sqrt,
                                                    float b1, float b2, float eps, const float* __restrict__ unsafe,
@@ -134,13 +146,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     return;
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    adam_update(p[i], m[i], v[i], g[i], step_size, bc2_sqrt, b1, b2, eps);
   }
 }
 
@@ -189,11 +195,7 @@ __global__ void __launch_bounds__(256) adam_peers_kernel(float* __restrict__ p, 
     }
     for (int k = 0; k < cnt; ++k) {
       const int64_t i = i0 + k;
-      const float mi = b1 * m[i] + (1.f - b1) * gi[k];
-      const float vi = b2 * v[i] + (1.f - b2) * gi[k] * gi[k];
-      m[i] = mi;
-      v[i] = vi;
-      p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      adam_update(p[i], m[i], v[i], gi[k], step_size, bc2_sqrt, b1, b2, eps);
       if (g_sum_out) g_sum_out[i] = gi[k];
     }
   }

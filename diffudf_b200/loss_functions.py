@@ -75,8 +75,11 @@ class TrainCore:
             Zb = self._buf("Zb", (L, 256, ld))
         return Z, A, Zb
 
-    def forward(self, mode, x, normals, d, n_on, w, alpha, P_global=None, stats_reduce=None):
-        """Returns a (4,) float64 device tensor with this rank's share of the loss terms."""
+    def forward(self, mode, x, normals, d, n_on, w, alpha, P_global=None, stats_reduce=None, eager_seeds=False, absmax=None):
+        """Returns a (4,) float64 device tensor with this rank's share of the loss terms.
+        eager_seeds (loss_s1 / loss_siren, trainer path with unit upstream gradients): the loss kernel that forms the terms also
+        writes the adjoint seeds and their magnitude (the loss scale of the tensor-core reverse sweep) — one pass over the rows and
+        one 3 x 3 eigen-solve per on-surface row instead of two; backward(None, ...) then starts with the reverse sweep."""
         m = self.model
         prec = self._prec()
         eng = m._engine_synced(NEED[prec])
@@ -89,6 +92,11 @@ class TrainCore:
         stats = torch.zeros(3, device=x.device, dtype=torch.float64) if mode == "s2" else None
         eng.jet_forward_multi([dict(x=x[s["row0"]:s["row0"] + s["rows"]], order=s["order"], col0=s["col0"],
                                     packed=packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]) for s in segs], Z, A, ld, prec)
+        seeds = None
+        if eager_seeds and mode != "s2":
+            seeds = self._buf("seeds", (nout,))
+            if absmax is None and prec in TC_PRECISIONS:
+                absmax = torch.zeros(1, device=x.device, dtype=torch.float32)
         for s in segs:
             pk = packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]
             ds = d[s["row0"]:s["row0"] + s["rows"]]
@@ -96,13 +104,16 @@ class TrainCore:
                 eng.loss_s2_stats(pk, ds, s["rows"], stats)
             else:
                 ns = normals[s["row0"]:s["row0"] + s["rows"]]
-                eng.loss(mode, pk, NCH[s["order"]], ns, ds, s["rows"], P_global, w, alpha, terms=terms)
+                sd = seeds[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]] if seeds is not None else None
+                eng.loss(mode, pk, NCH[s["order"]], ns, ds, s["rows"], P_global, w, alpha, terms=terms, seeds=sd,
+                         seed_absmax=absmax if seeds is not None else None)
         if mode == "s2":
             if stats_reduce is not None:
                 stats_reduce(stats)
             eng.loss_s2_finish(stats, w[0], w[1], terms)
         self.pending = dict(mode=mode, x=x, normals=normals, d=d, w=list(w), alpha=alpha, P_global=P_global, segs=segs,
-                            ld=ld, Z=Z, A=A, Zb=Zb, packed=packed, stats=stats, sig=eng._sig, prec=prec)
+                            ld=ld, Z=Z, A=A, Zb=Zb, packed=packed, stats=stats, sig=eng._sig, prec=prec,
+                            seeds_ready=seeds is not None, absmax=absmax)
         return terms
 
     def fused_step(self, mode, x, normals, d, n_on, w, alpha, P_global, gW, gB):
@@ -118,9 +129,10 @@ class TrainCore:
             self.amax = torch.zeros(2, device=x.device, dtype=torch.float32)
         self.last_fused = None
         if prec != "tc16" or mode == "s2" or self.amax_key != key:     # (tcx3 has no single-launch kernel yet)
-            terms = self.forward(mode, x, normals, d, n_on, w, alpha, P_global, None)
             slot = 1 - self.amax_slot
             self.amax[slot:slot + 1].zero_()
+            terms = self.forward(mode, x, normals, d, n_on, w, alpha, P_global, None, eager_seeds=True,
+                                 absmax=self.amax[slot:slot + 1] if prec in TC_PRECISIONS else None)
             self.backward(None, gW, gB, absmax=self.amax[slot:slot + 1] if prec in TC_PRECISIONS else None)
             if prec == "tc16" and mode != "s2":
                 self.amax_key, self.amax_slot = key, slot
@@ -156,9 +168,12 @@ class TrainCore:
         if eng._sig != p["sig"]:
             raise RuntimeError("SIREN parameters changed between the loss forward and backward")
         seeds = self._buf("seeds", tuple(p["packed"].shape))
-        if absmax is None and prec in TC_PRECISIONS:
+        eager = bool(p.get("seeds_ready")) and upstream is None
+        if eager:
+            absmax = p["absmax"]            # seeds and their magnitude were written by the forward's loss pass
+        elif absmax is None and prec in TC_PRECISIONS:
             absmax = torch.zeros(1, device=p["x"].device, dtype=torch.float32)
-        for s in p["segs"]:                 # all seeds (and their magnitude) before the first reverse sweep
+        for s in ([] if eager else p["segs"]):                 # all seeds (and their magnitude) before the first reverse sweep
             r0, r1 = s["row0"], s["row0"] + s["rows"]
             nch = NCH[s["order"]]
             pk = p["packed"][s["off"]:s["off"] + s["rows"] * nch]

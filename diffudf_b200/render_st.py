@@ -189,11 +189,43 @@ def _rdylbu(x):
         return lut[idx]
 
 
+def _percentile(sorted_vals, q):
+    """np.percentile(a, q) (method 'linear') on an ascending float64 CUDA vector, with numpy's own interpolation formula
+    (a + (b - a) t below t = 0.5, b - (b - a)(1 - t) from there on), so the clip bounds equal the reference's to the last bit."""
+    n = sorted_vals.numel()
+    pos = (n - 1) * (float(q) / 100.0)
+    i = int(np.floor(pos))
+    t = pos - i
+    a = sorted_vals[i]
+    b = sorted_vals[min(i + 1, n - 1)]
+    return a + (b - a) * t if t < 0.5 else b - (b - a) * (1.0 - t)
+
+
+def _curvature_colours(curv, q_lo, q_hi):
+    """The colour-map block of create_projectional_image (src/render_st.py:109-114) on the device: 5-95 percentile clip (one sort of
+    the (H,) float64 curvature vector), shift / scale to [0, 1], RdYlBu lookup.  Returns (H, 3) float64 on the device.  matplotlib's
+    own map is used when it is installed (one small host round trip); otherwise the ColorBrewer anchors interpolated on the device."""
+    srt = torch.sort(curv).values
+    lo, hi = _percentile(srt, q_lo), _percentile(srt, q_hi)
+    c = torch.clamp(curv, min=lo, max=hi)
+    c = c - c.min()
+    c = c / c.max()
+    try:
+        from matplotlib import cm
+        return torch.from_numpy(np.ascontiguousarray(cm.get_cmap("RdYlBu")(c.cpu().numpy())[:, :3])).to(curv.device)
+    except Exception:
+        lut_x = np.linspace(0.0, 1.0, 256)
+        lut = torch.from_numpy(np.stack([np.interp(lut_x, np.linspace(0.0, 1.0, 11), _RDYLBU[:, k]) for k in range(3)], 1)).to(curv.device)
+        idx = torch.clamp((c * 256).to(torch.int64), 0, 255)
+        idx[c == 1.0] = 255
+        return lut[idx]
+
+
 def create_projectional_image(model, rays, t0, mask_rays, network_config, rendering_config, device):
     """src/render_st.py:67-134 with the same arguments and in-place effects on t0 / mask_rays; returns the (height, width, 3)
     float64 image.  Marching, the gradient-descent refinement, the hit attributes (eigen-normals, principal directions, curvature)
-    and the shading all run on the device; the percentile clip of the curvature colour map (a global statistic over the hits) and
-    the colour-map lookup are the reference's numpy expressions on the (H,) curvature vector."""
+    and the shading all run on the device, the percentile clip of the curvature colour map (a global statistic over the hits:
+    one device sort) and the colour-map lookup included (_curvature_colours)."""
     dev = torch.device(device)
     eng = model._engine_synced()
     # one upload of the ray set; marching, refinement, attributes and shading work on device-resident state, the reference's in-place
@@ -229,11 +261,8 @@ def create_projectional_image(model, rays, t0, mask_rays, network_config, render
     normals = att["normals"].to(torch.float64)
     colours = None
     if kind is not None:
-        curv = (att["mean"] if kind == "mean" else att["gauss"]).to(torch.float64).cpu().numpy()[:, None]
-        curv = np.clip(curv, np.percentile(curv, rendering_config["curv_low_bound"]), np.percentile(curv, rendering_config["curv_high_bound"]))
-        curv -= np.min(curv)
-        curv /= np.max(curv)
-        colours = _rdylbu(curv.squeeze(1))
+        colours = _curvature_colours((att["mean"] if kind == "mean" else att["gauss"]).to(torch.float64),
+                                     rendering_config["curv_low_bound"], rendering_config["curv_high_bound"])
     if rendering_config["reflection_method"] == "blinn-phong":
         return _shade(0, rendering_config["light_position"], None, hits_d, t0_d, normals, shininess=rendering_config["shininess"],
                       color_map=colours).cpu().numpy().reshape(shape)

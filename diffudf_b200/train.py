@@ -109,7 +109,8 @@ class FusedTrainer:
                 scale_guard(*self.core.last_fused, self.grad_all[-1:])
                 guarded = True
         else:
-            terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None)
+            terms = self.core.forward(mode, x, normals, d, n_on, weights, alpha, P_global, dp.reduce_stats if dp is not None else None,
+                                      eager_seeds=True)
             if self.peer is not None:
                 self.core.backward(None, self.gW, self.gB)
             elif self.groups is not None and self.core._prec() in ("tc16", "tcx3"):
@@ -236,8 +237,8 @@ def _epoch_loop(dataset, model, device, config, stage_fn):
                 x, n, d, n_on = shard_batch(x, n, d, n_on, n_far, dp.rank, dp.world)
                 x, n, d = x.contiguous(), n.contiguous(), d.contiguous()
             running += trainer.step(mode, x, n, d, n_on, weights, config.get("alpha", 0.0), lr)
-        if dp is not None and dp.world > 1:
-            dp.reduce_terms(running)
+        if dp is not None and dp.world > 1 and mode != "s2":
+            dp.reduce_terms(running)            # shares of the means; loss_s2's terms come from the all-reduced statistics and are already global
         vals = running.cpu().numpy()                        # one read-back per epoch
         if int(misplaced.item()) != 0:
             raise RuntimeError(f"{int(misplaced.item())} rows of this epoch's batches contradict the [on-surface (d == 0) | off-surface] layout "

@@ -107,6 +107,33 @@ if rank == 0:
     same = all(torch.equal(torch.nan_to_num(a.to(b.dtype)), torch.nan_to_num(b)) for a, b in zip(pa, pb))
     print(f"sharded projection identical: {same}", flush=True)
     ok = ok and same
+# the public epoch loop with config["dp"]: every rank iterates the same dataset and trains on its share of each row group; the
+# per-epoch loss sums (all-reduced) equal the single-GPU loop's on the same batches
+from diffudf_b200.train import train_model_tanh  # noqa: E402
+
+
+class _DS:
+    def __init__(self, batches, n_on):
+        self.batches, self.batchesPerEpoch, self.samplesOnSurface = batches, len(batches), n_on
+
+    def __iter__(self):
+        for b in self.batches:
+            yield tuple(torch.from_numpy(a) for a in b)
+
+
+bs = [synthetic.make_batch(shape, sp, sn, 3000, (0.333, 0.666), np.random.default_rng(70 + i)) for i in range(2)]
+cfg = dict(epochs=3, s1_epochs=2, warmup_epochs=1, warmup_lr=1e-5, lr_s1=1e-6, lr_s2=1e-7, loss_s1_weights=[1e4, 1e4, 1e4, 1e3],
+           loss_s2_weights=[1e5, 1e5], alpha=100.0, precision="tcx3")
+torch.manual_seed(123)
+md = SIREN(3, 1, [256] * 8, w0=30).cuda()
+ld, _, _ = train_model_tanh(_DS(bs, 999), md, torch.device("cuda", local), dict(cfg, dp=DataParallel()))
+if rank == 0:
+    torch.manual_seed(123)
+    m1 = SIREN(3, 1, [256] * 8, w0=30).cuda()
+    l1, _, _ = train_model_tanh(_DS(bs, 999), m1, torch.device("cuda", local), cfg)
+    worst = max(abs(a - b) / max(abs(b), 1e-2) for k in l1 for a, b in zip(ld[k], l1[k]))
+    print(f"epoch loop with dp: worst relative difference of the per-epoch loss terms {worst:.2e}", flush=True)
+    ok = ok and worst < 5e-3
 dist.barrier()
 if rank == 0:
     print("DP_CHECK_OK" if ok else "DP_CHECK_FAILED", flush=True)
