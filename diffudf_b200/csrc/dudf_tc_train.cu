@@ -277,16 +277,21 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
     for (int s = 0; s < 2; ++s) *reinterpret_cast<uint4*>(tc_tile_row(e.act + s * TC_ACT_BYTES, e.n) + tc_chunk_off(15, e.r7)) = make_uint4(0, 0, 0, 0);
   }
   tc_epi_bar();
+  constexpr int NRAW = Stash<NCH, C::GC>::CHUNKS;
+  // stash of (layer l, sub-tile s): the first column group of the NEXT (layer, sub-tile) is requested while the last group of the current
+  // one is being worked on — an HBM read takes 1 500-2 000 clk under this kernel's load, and a request issued only at the boundary was
+  // fully exposed (0.372 -> 0.348 ms per launch).  Requesting TWO groups ahead costs more in register copies than it hides (0.362 ms).
+  auto stash_of = [&](int l, int s) { return Ust + ((size_t)l * ld + colp + s * 128) * 256 + e.n * 4; };
+  uint4 nxt[NRAW];
+  tt_stash_load<NCH, C::GC>(nxt, stash_of(L - 1, 0));
   for (int l = L - 1; l >= 0; --l) {
     const float wl_cur = (l == 0) ? net.w0 : net.ww;
     const bool top = (l == L - 1), first = (l == 0);
     for (int s = 0; s < 2; ++s) {
       unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
-      const int64_t colt = colp + s * 128;
-      const float* ust = Ust + ((size_t)l * ld + colt) * 256 + e.n * 4;
-      constexpr int NRAW = Stash<NCH, C::GC>::CHUNKS;
-      uint4 nxt[NRAW];
-      tt_stash_load<NCH, C::GC>(nxt, ust);                       // in flight while we wait for the accumulator
+      const float* ust = stash_of(l, s);
+      const bool more = (s == 0) || (l > 0);
+      const float* ust_next = more ? ((s == 0) ? stash_of(l, 1) : stash_of(l - 1, 0)) : ust;
       tc_trace(e.trace, e.tn, 40 + s, l);
       if (!top) {
         mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
@@ -302,6 +307,7 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
 #pragma unroll
         for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
         if (g + 1 < C::NGRP) tt_stash_load<NCH, C::GC>(nxt, ust + (size_t)(g + 1) * C::GC * 256);
+        else if (more) tt_stash_load<NCH, C::GC>(nxt, ust_next);
         // the group's own accumulators are loaded inside the group and used in place (NOW): the TMEM load hides behind the stash
         // conversion, and ptxas no longer copies the 32 / 40 staging registers of a prefetched group out and back
         const uint32_t tcur = e.tmem_lane + s * 256 + g * C::GC;
