@@ -157,15 +157,19 @@ def aux_device_sampler(dev, trainer):
     pts, nrm = shape.sample_surface(200000, np.random.default_rng(0))
     ds = PointCloud(pts.astype(np.float32), nrm.astype(np.float32), 30000, [0.333, 0.666], 20, dev, seed=5)
     out = {}
+    # the sampler alone: draws issued back to back in ONE stream (prefetch off), device time per batch
+    ds.prefetch = False
     for _ in ds:
         break
     s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
     s.record()
     nb = 0
     for _ in ds:
         nb += 1
     t.record()
     torch.cuda.synchronize()
+    ds.prefetch = True
     ms = s.elapsed_time(t) / nb
     rows = ds.samplesOnSurface + ds.samplesFarSurface
     out["sampler_pc_200k_ms_per_batch"] = ms
