@@ -174,7 +174,21 @@ def aux_device_sampler(dev, trainer):
     rows = ds.samplesOnSurface + ds.samplesFarSurface
     out["sampler_pc_200k_ms_per_batch"] = ms
     out["sampler_pc_200k_rows_per_s"] = rows / (ms * 1e-3)
-    out["sampler_pc_200k_pair_distances_per_s"] = (ds.samplesFarSurface // 2) * 200000 / (ms * 1e-3)
+    out["sampler_pc_200k_equivalent_pair_distances_per_s"] = (ds.samplesFarSurface // 2) * 200000 / (ms * 1e-3)
+    # the far rows' distances alone: the prebuilt index against the tiled scan of the whole cloud (DUDF_NN_SCAN=1)
+    from diffudf_b200.dataset import shortestDistance
+    far = next(iter(ds))[0][0, ds.samplesOnSurface:ds.samplesOnSurface + ds.samplesFarSurface // 2].contiguous()
+    for key, target, env in (("index", ds.index, None), ("scan", ds.surface_pc, "1")):
+        if env:
+            os.environ["DUDF_NN_SCAN"] = env
+        shortestDistance(far, target)
+        s.record()
+        for _ in range(10):
+            shortestDistance(far, target)
+        t.record()
+        torch.cuda.synchronize()
+        os.environ.pop("DUDF_NN_SCAN", None)
+        out[f"nearest_distance_{key}_9990x200k_ms"] = s.elapsed_time(t) / 10
     for x, n, d in ds:      # warm the step on this batch shape
         trainer.step("s1", x[0], n[0], d[0, :, 0], ds.samplesOnSurface, W_S1, ALPHA, LR)
         break

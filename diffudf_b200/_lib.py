@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdudf_b200.so")
-SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_tcx.cu", "dudf_mesh.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
+SOURCES = ["dudf_api.cu", "dudf_simt.cu", "dudf_tc.cu", "dudf_tc_train.cu", "dudf_tcx.cu", "dudf_mesh.cu", "dudf_misc.cu", "dudf_sampler.cu", "dudf_cloud_index.cu", "dudf_drivers.cu", "dudf_capmc.cu"]
 HOST_SOURCES = ["meshudf_mc.cpp"]            # plain C++17 (no CUDA): g++, strict IEEE arithmetic (no contraction)
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"]
 HEADERS = ["dudf_common.cuh", "dudf_kernels.h", "dudf_device.cuh", "dudf_umma.cuh", "dudf_tc_common.cuh", "dudf_loss.cuh", "dudf_mc_table.h",
@@ -56,6 +56,12 @@ SIGNATURES = {
     "dudf_sample_batch_pc": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, ctypes.POINTER(c_float),
                              ctypes.POINTER(c_float), ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p],
+    "dudf_cloud_index_bytes": [c_int64],
+    "dudf_cloud_index_build": [c_void_p, c_int64, c_void_p, c_void_p],
+    "dudf_nearest_distance_indexed": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
+    "dudf_sample_batch_pc_indexed": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float, ctypes.POINTER(c_float),
+                                     ctypes.POINTER(c_float), ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p],
     "dudf_mesh_distance": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
     "dudf_sample_batch_mesh": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, ctypes.POINTER(c_float),
                                ctypes.POINTER(c_float), ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -161,7 +167,7 @@ def lib():
             for name, args in SIGNATURES.items():
                 fn = getattr(L, name)
                 fn.argtypes = args
-                fn.restype = c_int64 if name in ("dudf_stash_columns", "dudf_launch_count", "dudf_fused_scratch_bytes") else c_int
+                fn.restype = c_int64 if name in ("dudf_stash_columns", "dudf_launch_count", "dudf_fused_scratch_bytes", "dudf_cloud_index_bytes") else c_int
             L.dudf_last_error.argtypes = []
             L.dudf_last_error.restype = ctypes.c_char_p
             _lib = L

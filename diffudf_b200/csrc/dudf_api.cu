@@ -619,6 +619,34 @@ int dudf_sample_batch_pc(const float* surf_pts, const float* surf_normals, int64
   return sample_batch_pc(a, device_sms(), (cudaStream_t)stream);
 }
 
+int64_t dudf_cloud_index_bytes(int64_t n_x) { return cloud_index_bytes(n_x); }
+
+int dudf_cloud_index_build(const float* cloud, int64_t n_x, void* index, void* stream) {
+  DUDF_REQUIRE(cloud && index, "dudf_cloud_index_build: null argument");
+  return cloud_index_build(cloud, n_x, index, (cudaStream_t)stream);
+}
+
+int dudf_nearest_distance_indexed(const float* queries, int64_t n_q, const void* index, int64_t n_x, float* dist, void* stream) {
+  DUDF_REQUIRE(queries && index && dist, "dudf_nearest_distance_indexed: null argument");
+  return cloud_index_query(queries, n_q, index, n_x, dist, (cudaStream_t)stream);
+}
+
+int dudf_sample_batch_pc_indexed(const float* surf_pts, const float* surf_normals, int64_t n_surf, const void* index, int64_t n_on,
+                                 int64_t n_far, int64_t n_near, float sigma, const float* lo_host, const float* hi_host, uint64_t seed,
+                                 uint64_t batch_index, const int64_t* on_idx, const float* far_pts, const int64_t* near_idx,
+                                 const float* near_off, float* coords, float* normals, float* dist, void* stream) {
+  DUDF_REQUIRE(surf_pts && surf_normals && index && coords && normals && dist, "dudf_sample_batch_pc_indexed: null argument");
+  DUDF_REQUIRE(n_surf > 0 && n_on >= 0 && n_far >= 0 && n_near >= 0, "dudf_sample_batch_pc_indexed: bad sizes");
+  DUDF_REQUIRE(n_near == 0 || n_on > 0, "dudf_sample_batch_pc_indexed: near rows are displaced ON rows; n_on must be positive");
+  SampleArgs a;
+  a.surf_pts = surf_pts; a.surf_nrm = surf_normals; a.n_surf = n_surf; a.n_on = n_on; a.n_far = n_far; a.n_near = n_near;
+  a.sigma = sigma; a.seed = seed; a.batch = batch_index;
+  for (int k = 0; k < 3; ++k) { a.lo[k] = lo_host ? lo_host[k] : -1.f; a.hi[k] = hi_host ? hi_host[k] : 1.f; }
+  a.on_idx = on_idx; a.far_pts = far_pts; a.near_idx = near_idx; a.near_off = near_off;
+  a.coords = coords; a.normals = normals; a.dist = dist;
+  return sample_batch_pc_indexed(a, index, (cudaStream_t)stream);
+}
+
 int dudf_mesh_distance(const float* queries, int64_t n_q, const float* triangles, int64_t n_tri, float* dist, void* stream) {
   DUDF_REQUIRE(queries && triangles && dist, "dudf_mesh_distance: null argument");
   return mesh_distance(queries, n_q, triangles, n_tri, dist, device_sms(), (cudaStream_t)stream);

@@ -120,6 +120,14 @@ int mesh_distance(const float* q, int64_t nq, const float* tri, int64_t nt, floa
 int mesh_sample_surface(const float* tri, const float* cdf, int64_t nt, int64_t n, uint64_t seed, const float* draws, float* pts, float* nrm,
                         cudaStream_t st);
 int nn_distance(const float* q, int64_t nq, const float* X, int64_t nx, float* dist, int sms, cudaStream_t st);
+// ---- spatial index of the cloud (dudf_cloud_index.cu): Morton-sorted points under a 32-ary box hierarchy, exact fp32 nearest distance ----
+constexpr int CLOUD_INDEX_MAX_LEVELS = 5;
+constexpr int64_t CLOUD_INDEX_MAX_POINTS = (int64_t)1 << 30;
+constexpr int64_t CLOUD_INDEX_MIN_POINTS = 2048;        // below this nn_distance scans the cloud by brute force
+int64_t cloud_index_bytes(int64_t n);                   // size of the caller-owned device buffer, -1 if n is out of range
+int cloud_index_build(const float* X, int64_t n, void* index, cudaStream_t st);
+int cloud_index_query(const float* q, int64_t nq, const void* index, int64_t n, float* dist, cudaStream_t st);
+int sample_batch_pc_indexed(const SampleArgs& a, const void* index, cudaStream_t st);
 // ---- device-resident query drivers (dudf_drivers.cu; src/render_st.py:136-172, src/render_pc.py:43-53) ----
 size_t drv_select_temp_bytes(int64_t R);
 int drv_select_initial(void* temp, size_t temp_bytes, const unsigned char* active, int64_t R, int* idx, int* d_count, cudaStream_t st);

@@ -7,6 +7,8 @@
 // queries from shared memory, nothing is materialised.
 // Random draws: counter-based Philox4x32-10 keyed by (seed, batch), so a row's draw does not depend on launch
 // geometry; every draw can instead be supplied by the caller (parity tests feed the reference's numpy / torch draws).
+#include <cstdlib>
+
 #include "dudf_common.cuh"
 #include "dudf_kernels.h"
 
@@ -245,6 +247,16 @@ __global__ void __launch_bounds__(256) nn_finish_kernel(const unsigned int* __re
 int nn_distance(const float* q, int64_t nq, const float* X, int64_t nx, float* dist, int sms, cudaStream_t st) {
   if (nq <= 0) return 0;
   DUDF_REQUIRE(nx > 0, "nearest-point distance: empty cloud");
+  const char* scan = getenv("DUDF_NN_SCAN");      // A/B switch of bench.py: force the tiled scan
+  if (nx >= CLOUD_INDEX_MIN_POINTS && nx <= CLOUD_INDEX_MAX_POINTS && nq * 16 >= nx && !(scan && scan[0] == '1')) {
+    // large cloud, no index supplied: sorting it once (~0.1 ms at 200 000 points) and walking the box hierarchy is cheaper than the scan
+    void* index = nullptr;
+    DUDF_CUDA_OK(cudaMallocAsync(&index, (size_t)cloud_index_bytes(nx), st));
+    int rc = cloud_index_build(X, nx, index, st);
+    if (rc == 0) rc = cloud_index_query(q, nq, index, nx, dist, st);
+    DUDF_CUDA_OK(cudaFreeAsync(index, st));
+    return rc;
+  }
   DUDF_REQUIRE(nq < (int64_t)0xffffffffu, "nearest-point distance: at most 2^32 - 2 queries per call");
   unsigned int* ws = nullptr;                  // stream-ordered scratch: key [nq], near list [nq], near count [1]
   DUDF_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)(2 * nq + 1) * sizeof(unsigned int), st));
@@ -285,6 +297,14 @@ int sample_batch_pc(const SampleArgs& a, int sms, cudaStream_t st) {
   int rc = sample_rows(a, st);
   if (rc) return rc;
   return nn_distance(a.coords + a.n_on * 3, a.n_far, a.surf_pts, a.n_surf, a.dist + a.n_on, sms, st);
+}
+
+int sample_batch_pc_indexed(const SampleArgs& a, const void* index, cudaStream_t st) {
+  const int64_t P = a.n_on + a.n_far + a.n_near;
+  if (P <= 0) return 0;
+  int rc = sample_rows(a, st);
+  if (rc) return rc;
+  return cloud_index_query(a.coords + a.n_on * 3, a.n_far, index, a.n_surf, a.dist + a.n_on, st);
 }
 
 }  // namespace dudf

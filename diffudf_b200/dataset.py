@@ -20,8 +20,39 @@ def _as_dev(t, device, dtype=torch.float32):
     return torch.as_tensor(t).to(device=device, dtype=dtype).contiguous()
 
 
+class CloudIndex:
+    """Spatial index of a cloud (dudf_cloud_index_build): Morton-sorted points under a 32-ary box hierarchy in one device buffer.
+    The reference measures every batch's far rows against the same cloud (src/dataset.py:116-118); `PointCloud` builds this once
+    and every batch walks it instead of scanning the cloud.  Distances are exact in fp32."""
+
+    def __init__(self, X):
+        if X.device.type != "cuda":
+            raise RuntimeError("diffudf_b200.dataset.CloudIndex needs a CUDA (sm_100) tensor; there is no CPU fallback")
+        self.cloud = X.detach().to(torch.float32).contiguous()
+        self.n = int(self.cloud.shape[0])
+        nbytes = int(_lib.lib().dudf_cloud_index_bytes(self.n))
+        if nbytes < 0:
+            raise ValueError("CloudIndex: 1 .. 2^30 points")
+        self.buffer = torch.empty(nbytes, device=self.cloud.device, dtype=torch.uint8)
+        with torch.cuda.device(self.cloud.device):
+            _lib.check(_lib.lib().dudf_cloud_index_build(self.cloud.data_ptr(), self.n, self.buffer.data_ptr(), _lib.current_stream()),
+                       "dudf_cloud_index_build")
+
+    def distance(self, P):
+        """(n, 3) CUDA queries -> (n,) fp32 distances to the nearest cloud point."""
+        P = P.detach().to(device=self.cloud.device, dtype=torch.float32).contiguous()
+        out = torch.empty(P.shape[0], device=P.device, dtype=torch.float32)
+        if P.shape[0]:
+            with torch.cuda.device(P.device):
+                _lib.check(_lib.lib().dudf_nearest_distance_indexed(P.data_ptr(), P.shape[0], self.buffer.data_ptr(), self.n, out.data_ptr(),
+                                                                    _lib.current_stream()), "dudf_nearest_distance_indexed")
+        return out
+
+
 def shortestDistance(P, X):
-    """Distance from each row of P to its nearest row of X (CUDA tensors (n, 3), (m, 3)) -> (n,) fp32."""
+    """Distance from each row of P to its nearest row of X (CUDA tensors (n, 3), (m, 3)) -> (n,) fp32.  X may be a `CloudIndex`."""
+    if isinstance(X, CloudIndex):
+        return X.distance(P)
     if P.device.type != "cuda":
         raise RuntimeError("diffudf_b200.dataset.shortestDistance needs CUDA (sm_100) tensors; there is no CPU fallback")
     P = P.detach().to(torch.float32).contiguous()
@@ -95,9 +126,10 @@ def sampleTrainingData(surface_pc, surface_normals, samplesOnSurface, samplesOff
 
 
 def sampleTrainingDataPC(surface_pc, surface_normals, samplesOnSurface, samplesOffSurface, domainBounds=([-1, -1, -1], [1, 1, 1]),
-                         seed=0, batch_index=0, draws=None, sigma=0.01):
+                         seed=0, batch_index=0, draws=None, sigma=0.01, index=None):
     """One batch (reference :80-131).  `draws` (optional): dict with any of on_idx (n_on,) int64, far (n_far, 3),
-    near_idx (n_near,) int64, near_off (n_near,) — replaces the corresponding Philox draws (parity tests)."""
+    near_idx (n_near,) int64, near_off (n_near,) — replaces the corresponding Philox draws (parity tests).
+    `index` (optional): a `CloudIndex` of surface_pc, built once by the caller, that serves the far rows' distances."""
     dev = surface_pc.device
     if dev.type != "cuda":
         raise RuntimeError("diffudf_b200.dataset.sampleTrainingDataPC needs the cloud on a CUDA (sm_100) device; there is no CPU fallback")
@@ -116,10 +148,19 @@ def sampleTrainingDataPC(surface_pc, surface_normals, samplesOnSurface, samplesO
     lo = (ctypes.c_float * 3)(*[float(v) for v in domainBounds[0]])
     hi = (ctypes.c_float * 3)(*[float(v) for v in domainBounds[1]])
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().dudf_sample_batch_pc(X.data_ptr(), N.data_ptr(), X.shape[0], n_on, n_far, n_near, float(sigma), lo, hi,
-                                                   int(seed) & (2 ** 64 - 1), int(batch_index), _lib.ptr(keep[0]), _lib.ptr(keep[1]),
-                                                   _lib.ptr(keep[2]), _lib.ptr(keep[3]), coords.data_ptr(), normals.data_ptr(),
-                                                   sdf.data_ptr(), _lib.current_stream()), "dudf_sample_batch_pc")
+        if index is not None:
+            if index.n != X.shape[0] or index.buffer.device != dev:
+                raise ValueError("sampleTrainingDataPC: the index was built for another cloud")
+            _lib.check(_lib.lib().dudf_sample_batch_pc_indexed(X.data_ptr(), N.data_ptr(), X.shape[0], index.buffer.data_ptr(), n_on, n_far, n_near,
+                                                               float(sigma), lo, hi, int(seed) & (2 ** 64 - 1), int(batch_index),
+                                                               _lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[2]), _lib.ptr(keep[3]),
+                                                               coords.data_ptr(), normals.data_ptr(), sdf.data_ptr(), _lib.current_stream()),
+                       "dudf_sample_batch_pc_indexed")
+        else:
+            _lib.check(_lib.lib().dudf_sample_batch_pc(X.data_ptr(), N.data_ptr(), X.shape[0], n_on, n_far, n_near, float(sigma), lo, hi,
+                                                       int(seed) & (2 ** 64 - 1), int(batch_index), _lib.ptr(keep[0]), _lib.ptr(keep[1]),
+                                                       _lib.ptr(keep[2]), _lib.ptr(keep[3]), coords.data_ptr(), normals.data_ptr(),
+                                                       sdf.data_ptr(), _lib.current_stream()), "dudf_sample_batch_pc")
     return coords, normals, sdf
 
 
@@ -146,11 +187,12 @@ class PointCloud(torch.utils.data.IterableDataset):
         self.batches_drawn = 0
         self.prefetch = prefetch
         self._side = None
+        self.index = CloudIndex(self.surface_pc) if self.onlyPCloud else None      # built once; every batch's far rows walk it
 
     def _draw(self):
         if self.onlyPCloud:
             out = sampleTrainingDataPC(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
-                                       seed=self.seed, batch_index=self.batches_drawn)
+                                       seed=self.seed, batch_index=self.batches_drawn, index=self.index)
         else:
             out = sampleTrainingData(self.surface_pc, self.surface_normals, self.samplesOnSurface, self.samplesFarSurface,
                                      self.triangles, seed=self.seed, batch_index=self.batches_drawn)

@@ -231,6 +231,19 @@ int dudf_sample_batch_pc(const float* surf_pts, const float* surf_normals, int64
                          const int64_t* on_idx, const float* far_pts, const int64_t* near_idx, const float* near_off, float* coords,
                          float* normals, float* dist, void* stream);
 int dudf_nearest_distance(const float* queries, int64_t n_q, const float* cloud, int64_t n_x, float* dist, void* stream);
+/* Spatial index of the cloud for the same distances (the reference calls shortestDistance on the SAME cloud for every batch,
+ * src/dataset.py:116-118, 176-185): the points sorted along a Morton curve under a 32-ary hierarchy of boxes, built once into a
+ * caller-owned, 16-byte aligned device buffer of dudf_cloud_index_bytes(n_x) bytes (-1: n_x outside 1 .. 2^30).  Queries walk it
+ * best-first, one warp each; distances are EXACT in fp32 (difference form, monotone lower bounds).  dudf_nearest_distance builds
+ * a temporary index by itself for clouds of 2 048 points and more; dudf_sample_batch_pc_indexed is dudf_sample_batch_pc with the
+ * far rows measured through a prebuilt index (what PointCloud does for every batch). */
+int64_t dudf_cloud_index_bytes(int64_t n_x);
+int dudf_cloud_index_build(const float* cloud, int64_t n_x, void* index, void* stream);
+int dudf_nearest_distance_indexed(const float* queries, int64_t n_q, const void* index, int64_t n_x, float* dist, void* stream);
+int dudf_sample_batch_pc_indexed(const float* surf_pts, const float* surf_normals, int64_t n_surf, const void* index, int64_t n_on,
+                                 int64_t n_far, int64_t n_near, float sigma, const float* lo_host, const float* hi_host, uint64_t seed,
+                                 uint64_t batch_index, const int64_t* on_idx, const float* far_pts, const int64_t* near_idx,
+                                 const float* near_off, float* coords, float* normals, float* dist, void* stream);
 /* ---- Mesh half of the batch sampler (src/dataset.py:14-70, PointCloud(onlyPCloud=False); src/preprocess_mesh.py:29-40) ----
  * dudf_mesh_distance replaces scene.compute_signed_distance (Open3D RaycastingScene, :35,50) by the UNSIGNED distance
  * dist[i] = min_t |q_i - triangle_t| (brute force; the losses are even in the distance and the ray-parity sign is undefined

@@ -44,6 +44,67 @@ def test_shortest_distance(nq, nx, golden, oracle):
     assert shortestDistance(torch.zeros(0, 3).cuda(), torch.from_numpy(X.astype(np.float32)).cuda()).shape == (0,)
 
 
+def _true_min_distance(P, X):
+    """fp64 minimum distance by blocks on the device (the definition, src/dataset.py:72-78 without the expansion)."""
+    P64, X64 = P.double(), X.double()
+    out = torch.empty(P.shape[0], device=P.device, dtype=torch.float64)
+    for i in range(0, P.shape[0], 2048):
+        out[i:i + 2048] = torch.cdist(P64[i:i + 2048], X64, compute_mode="donot_use_mm_for_euclid_dist").min(1).values
+    return out
+
+
+@pytest.mark.parametrize("nx", [1, 31, 33, 1024, 1025, 40000, 200000])
+def test_cloud_index_is_exact(nx):
+    """The box hierarchy prunes with monotone fp32 bounds: it must return the fp32 difference-form distance of the TRUE nearest
+    point (relative 1e-6 of the fp64 minimum), for queries inside, on and far outside the cloud, and at every padding edge."""
+    from diffudf_b200.dataset import CloudIndex, shortestDistance
+    g = torch.Generator(device="cuda").manual_seed(nx)
+    u = torch.randn(nx, 3, device="cuda", generator=g)
+    X = 0.6 * u / u.norm(dim=1, keepdim=True) + 0.002 * torch.randn(nx, 3, device="cuda", generator=g)     # a noisy sphere: a surface
+    if nx >= 1024:
+        X[: nx // 4] = torch.rand(nx // 4, 3, device="cuda", generator=g) * 0.5 - 1.0                          # plus a filled corner
+    P = torch.cat([torch.rand(3000, 3, device="cuda", generator=g) * 2 - 1,                                    # the sampler's far rows
+                   X[torch.randint(0, nx, (500,), device="cuda", generator=g)],                                # ON the cloud
+                   X[torch.randint(0, nx, (500,), device="cuda", generator=g)] + 1e-3 * torch.randn(500, 3, device="cuda", generator=g),
+                   torch.randn(300, 3, device="cuda", generator=g) * 5.0])                                     # far outside the boxes
+    idx = CloudIndex(X)
+    d = idx.distance(P)
+    ref = _true_min_distance(P, X)
+    assert float((d.double() - ref).abs().max()) <= 1e-6 * float(ref.max()) + 1e-7
+    assert float(((d.double() - ref).abs() / ref.clamp_min(1e-3)).max()) < 2e-6
+    assert float(d[3000:3500].max()) == 0.0
+    assert torch.equal(shortestDistance(P, idx), d)
+    if 2048 <= nx <= 16 * P.shape[0]:                       # the un-indexed entry point builds a temporary index of its own
+        assert torch.equal(shortestDistance(P, X), d)
+    assert idx.distance(torch.zeros(0, 3, device="cuda")).shape == (0,)
+
+
+def test_cloud_index_degenerate_clouds():
+    from diffudf_b200.dataset import CloudIndex
+    g = torch.Generator(device="cuda").manual_seed(0)
+    P = torch.rand(2000, 3, device="cuda", generator=g) * 2 - 1
+    same = torch.full((5000, 3), 0.25, device="cuda")                                       # one point 5 000 times
+    assert torch.allclose(CloudIndex(same).distance(P), (P - 0.25).norm(dim=1), rtol=1e-6, atol=0)
+    line = torch.zeros(7000, 3, device="cuda")
+    line[:, 0] = torch.linspace(-1, 1, 7000, device="cuda")                                 # boxes of zero volume
+    d = CloudIndex(line).distance(P)
+    assert float((d.double() - _true_min_distance(P, line)).abs().max()) < 1e-6
+
+
+def test_indexed_batch_equals_scanned_batch(golden):
+    """PointCloud's batches (far rows through the prebuilt index) against the brute-force scan of the same draws."""
+    from diffudf_b200.dataset import CloudIndex, sampleTrainingDataPC
+    g, X, N = _cloud(golden)
+    idx = CloudIndex(X)
+    a = sampleTrainingDataPC(X, N, 999, 1998, seed=11, batch_index=2, index=idx)
+    b = sampleTrainingDataPC(X[:2047], N[:2047], 999, 1998, seed=11, batch_index=2)          # < 2 048 points: the tiled scan
+    c = sampleTrainingDataPC(X[:2047], N[:2047], 999, 1998, seed=11, batch_index=2, index=CloudIndex(X[:2047]))
+    assert torch.equal(b[0], c[0]) and torch.equal(b[1], c[1])
+    assert float((b[2] ** 2 - c[2] ** 2).abs().max()) < 1e-6                               # the scan's expansion carries 2e-7 on d^2
+    far = a[0][0, 999:999 + 999]
+    assert float((a[2][0, 999:999 + 999, 0].double() - _true_min_distance(far, X)).abs().max()) < 1e-6
+
+
 def test_device_draws_are_valid_deterministic_and_distinct(golden):
     from diffudf_b200.dataset import sampleTrainingDataPC, shortestDistance
     g, X, N = _cloud(golden)
