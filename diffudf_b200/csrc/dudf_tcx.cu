@@ -259,7 +259,8 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   unsigned char* Aimg;
   int64_t ld, col0;
   int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
-                          //   8 no tile stores, 16 no collector reuse of the weight operand, 32 no accumulator loads
+                          //   8 no tile stores, 16 no collector reuse of the weight operand, 32 no accumulator loads,
+                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group
   unsigned long long* trace;
   const float* dirs;      // DIR3 queries: [P][9] = three unit directions (a, b, c) per point
 };
@@ -353,7 +354,7 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       }
       tc_trace(e.trace, e.tn, 10 + h, l);
       const uint32_t taddr = e.tmem_q + ((e.jg + (uint32_t)l - 1u) & 1u) * 256 + h * 128;
-      auto group = [&](int g) {
+      auto group = [&](int g, const TmemRegs<GC>* pre) {
         float u[GC];
         if (l == 0) {
           if constexpr (DIR) tcx_first_layer_dir<GC>(u, e.xs + g * (GC / NCH) * XS, w0, r0x, r0y, r0z, b0);
@@ -362,6 +363,8 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
           if (dbg & 32) {            // diagnostics: no accumulator loads
 #pragma unroll
             for (int j = 0; j < GC; ++j) u[j] = (float)(j + e.lane);
+          } else if (pre) {
+            tc_ld_take<GC>(*pre, u);
           } else {
             TmemRegs<GC> tr;
             tc_ld_issue<GC>(taddr + g * GC, tr);
@@ -406,8 +409,22 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
           }
         }
       };
+      // A TMEM load that competes with the accumulating MMAs of the other neuron half takes ~850 clk (tools/tcx_trace.py), three
+      // times the ~250 instructions of a group: with two groups per warp, both loads are issued up front so that their latencies
+      // overlap instead of adding up (two distinct register sets, no rotation: ptxas keeps them in place).  Half epilogue 2 250 -> 1 830
+      // clk, the MMA groups under it 2 020 -> 2 230 (TMEM reads and accumulation share the port), layer period 9 310 -> 8 820 clk:
+      // grid queries +3.5 % (profiles/r3_tcx_trace_ldtm_*.txt).  40-column groups (Hessian jet) do not gain: three register sets
+      // of 40 spill, and only one of the two warp sets has a second group.
+      if (GC == 32 && NG_PER == 2 && l > 0 && g_end - g_begin == 2 && !(dbg & (32 | 2048))) {
+        TmemRegs<GC> t0, t1;
+        tc_ld_issue<GC>(taddr + g_begin * GC, t0);
+        tc_ld_issue<GC>(taddr + (g_begin + 1) * GC, t1);
+        group(g_begin, &t0);
+        group(g_begin + 1, &t1);
+      } else {
 #pragma unroll 1
-      for (int g = g_begin; g < g_end; ++g) group(g);
+        for (int g = g_begin; g < g_end; ++g) group(g, nullptr);
+      }
       tc_trace(e.trace, e.tn, 12 + h, l);
       if (l < L - 1) {
         tc_fence_before();
@@ -502,10 +519,13 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
       const int64_t tile = blockIdx.x + rd * gridDim.x;
       const bool valid = tile < ntiles;
       const int64_t colt = tr.col0 + tile * 128;
+      // diagnostics: 256 / 512 / 1024 = the epilogue warps of lane quarter 1 / 0 / 2 (the SM partition of the MMA warp / of the
+      // producer warp / of an idle warp) do no loads, math or stores — does the MMA stream slow down through its own partition?
+      const int dbg = tr.dbg | ((((tr.dbg & 256) && e.q == 1) || ((tr.dbg & 512) && e.q == 0) || ((tr.dbg & 1024) && e.q == 2)) ? 41 : 0);
       if (!valid || tile < tiles_a) {
-        tcx_tile<NA, TRAIN, SC, EW, DIR>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, tr.dbg, tr.dirs);
+        tcx_tile<NA, TRAIN, SC, EW, DIR>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, dbg, tr.dirs);
       } else {
-        if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC, EW>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, tr.dbg);
+        if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC, EW>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, dbg);
       }
     }
   }
