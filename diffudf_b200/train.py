@@ -218,7 +218,7 @@ def _epoch_loop(dataset, model, device, config, stage_fn):
         misplaced = torch.zeros(1, device=device, dtype=torch.int64)      # rows that contradict the [on | off] layout (read per epoch)
         for x, n, d in feeder.feed((tuple(torch.as_tensor(t, dtype=torch.float32) for t in b) for b in iter(dataset))):
             n_on = getattr(dataset, "samplesOnSurface", None)
-            need_on = mode == "s1" and weights[2] != 0
+            need_on = (mode == "s1" and weights[2] != 0) or mode == "s2"      # s2 evaluates the leading on-surface rows only
             if n_on is None and need_on:
                 from .loss_functions import on_surface_prefix
                 n_on = on_surface_prefix(d)
@@ -242,7 +242,7 @@ def _epoch_loop(dataset, model, device, config, stage_fn):
         vals = running.cpu().numpy()                        # one read-back per epoch
         if int(misplaced.item()) != 0:
             raise RuntimeError(f"{int(misplaced.item())} rows of this epoch's batches contradict the [on-surface (d == 0) | off-surface] layout "
-                               "the fused loss_s1 step relies on (dataset.samplesOnSurface leading rows)")
+                               "the fused loss_s1 / loss_s2 steps rely on (dataset.samplesOnSurface leading rows)")
         epoch_loss = 0.0
         for i, k in enumerate(keys):
             losses.setdefault(k, [0.0] * epochs)[epoch] = float(vals[i])

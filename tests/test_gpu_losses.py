@@ -135,6 +135,36 @@ def test_fused_trainer_trajectory(golden, oracle, weights):
     assert all(torch.isfinite(v).all() for v in sd.values())
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tcx3"])
+def test_loss_s2_on_surface_prefix_equals_all_rows(prec, golden, weights):
+    """loss_s2 reads f only where d == 0 (src/loss_functions.py:106-121): with gt['n_on'] the network is evaluated on the
+    leading on-surface rows only — same terms and the same parameter gradient as evaluating every row."""
+    import diffudf_b200 as D
+    from diffudf_b200 import SIREN
+    Ld = golden("losses_trained.npz")
+    x, d = Ld["x"].reshape(-1, 3), Ld["d"].reshape(-1)
+    order = np.argsort(d != 0, kind="stable")                             # [on | off] layout
+    x, d = np.ascontiguousarray(x[order]), np.ascontiguousarray(d[order])
+    n_on = int((d == 0).sum())
+    assert 0 < n_on < len(d)
+    out = []
+    for extra in ({}, {"n_on": n_on}):
+        m = SIREN(3, 1, [256] * 8, w0=30, delay_init=True)
+        m.train_precision = prec
+        m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(v) for i, (W, b) in enumerate(weights["trained"])
+                           for k, v in (("weight", W), ("bias", b))})
+        m = m.cuda()
+        gt = {"sdf": torch.from_numpy(d).cuda(), **extra}
+        loss = D.loss_s2(m, torch.from_numpy(x).cuda(), gt, [1e5, 1e5], 100.0)
+        sum(loss.values()).backward()
+        out.append(({k: float(v) for k, v in loss.items()}, [p.grad.clone() for p in m.parameters()]))
+    (ta, ga), (tb, gb) = out
+    for k in ta:
+        assert abs(ta[k] - tb[k]) <= 1e-6 * max(abs(ta[k]), 1e-3), (k, ta[k], tb[k])
+    for a, b in zip(ga, gb):
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()) + 1e-12
+
+
 def test_adam_kernel_matches_torch():
     from diffudf_b200.engine import adam_step
     torch.manual_seed(0)
