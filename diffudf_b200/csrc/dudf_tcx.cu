@@ -417,8 +417,7 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       // of 40 spill, and only one of the two warp sets has a second group.
       if (GC == 32 && NG_PER == 2 && l > 0 && g_end - g_begin == 2 && !(dbg & (32 | 2048))) {
         TmemRegs<GC> t0, t1;
-        tc_ld_issue<GC>(taddr + g_begin * GC, t0);
-        tc_ld_issue<GC>(taddr + (g_begin + 1) * GC, t1);
+        tmem_ld_x64(taddr + g_begin * GC, t0.a, t1.a);       // one 64-column load (two x32 loads time the same)
         group(g_begin, &t0);
         group(g_begin + 1, &t1);
       } else {

@@ -141,6 +141,16 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
+// 64 consecutive columns in one instruction: columns 0-31 -> r0, 32-63 -> r1
+__device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t* r0, uint32_t* r1) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15]), "=r"(r0[16]), "=r"(r0[17]), "=r"(r0[18]), "=r"(r0[19]), "=r"(r0[20]), "=r"(r0[21]), "=r"(r0[22]), "=r"(r0[23]), "=r"(r0[24]), "=r"(r0[25]), "=r"(r0[26]), "=r"(r0[27]), "=r"(r0[28]), "=r"(r0[29]), "=r"(r0[30]), "=r"(r0[31]), "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15]), "=r"(r1[16]), "=r"(r1[17]), "=r"(r1[18]), "=r"(r1[19]), "=r"(r1[20]), "=r"(r1[21]), "=r"(r1[22]), "=r"(r1[23]), "=r"(r1[24]), "=r"(r1[25]), "=r"(r1[26]), "=r"(r1[27]), "=r"(r1[28]), "=r"(r1[29]), "=r"(r1[30]), "=r"(r1[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 // ---- descriptors ----
 // shared-memory matrix descriptor, 128-byte swizzle.  The tile is a stack of 8-row x 128-byte
 // swizzle atoms; `sbo` = byte distance between consecutive atoms along the strided (8-row group)
