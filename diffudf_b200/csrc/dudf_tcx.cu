@@ -413,8 +413,9 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
       // times the ~250 instructions of a group: with two groups per warp, both loads are issued up front so that their latencies
       // overlap instead of adding up (two distinct register sets, no rotation: ptxas keeps them in place).  Half epilogue 2 250 -> 1 830
       // clk, the MMA groups under it 2 020 -> 2 230 (TMEM reads and accumulation share the port), layer period 9 310 -> 8 820 clk:
-      // grid queries +3.5 % (profiles/r3_tcx_trace_ldtm_*.txt).  40-column groups (Hessian jet) do not gain: three register sets
-      // of 40 spill, and only one of the two warp sets has a second group.
+      // grid queries +4 % (profiles/r3_tcx_trace_ldtm_*.txt, r3_tcx_ab_ldtm.txt).  40-column groups (Hessian jet) LOSE 4-5 % with either
+      // form of look-ahead (both loads up front, or the second issued when the first has landed): only one of the two warp sets has a
+      // second group, and its earlier loads take TMEM cycles from the MMAs of the other neuron half.
       if (GC == 32 && NG_PER == 2 && l > 0 && g_end - g_begin == 2 && !(dbg & (32 | 2048))) {
         TmemRegs<GC> t0, t1;
         tmem_ld_x64(taddr + g_begin * GC, t0.a, t1.a);       // one 64-column load (two x32 loads time the same)
