@@ -14,6 +14,7 @@
 //     keeps its full significand over the observed 1e6 dynamic range of the adjoints;
 //   * the weight gradient of every hidden layer is one split-K GEMM over all columns (M = N = 256, K = columns).
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "dudf_common.cuh"
 #include "dudf_kernels.h"
 #include "dudf_device.cuh"
@@ -248,7 +249,7 @@ __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr,
 
 template <int NCH>
 __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const GradView& grad, const SegDev& sg, int64_t pair, int64_t colp,
-                                            const float* Ust, int64_t ld, float S, float wl) {
+                                            const float* Ust, int64_t ld, float S, float wl, bool prefetch_l2, bool first_pair, int64_t colp_next) {
   using C = TcCfg<NCH>;
   const int L = net.n_lin - 1;
   const float invS = 1.0f / S;
@@ -282,6 +283,19 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
   // one is being worked on — an HBM read takes 1 500-2 000 clk under this kernel's load, and a request issued only at the boundary was
   // fully exposed (0.372 -> 0.348 ms per launch).  Requesting TWO groups ahead costs more in register copies than it hides (0.362 ms).
   auto stash_of = [&](int l, int s) { return Ust + ((size_t)l * ld + colp + s * 128) * 256 + e.n * 4; };
+  // ... and the whole stash of a (layer, sub-tile) is asked into the L2 TWO units ahead (one thread, one bulk prefetch per column
+  // group: NRAW contiguous 4 KB rows), so that the register loads above find it there instead of in HBM
+  auto prefetch_unit = [&](int l, int s, int64_t col) {
+    if (e.tid == 0 && prefetch_l2) {
+      const float* base = Ust + ((size_t)l * ld + col + s * 128) * 256;
+#pragma unroll
+      for (int g = 0; g < C::NGRP; ++g) bulk_prefetch_l2(base + (size_t)g * C::GC * 256, NRAW * 4096);
+    }
+  };
+  if (first_pair) {                 // later pairs: requested by the previous pair of this CTA (below)
+    prefetch_unit(L - 1, 0, colp);
+    prefetch_unit(L - 1, 1, colp);
+  }
   uint4 nxt[NRAW];
   tt_stash_load<NCH, C::GC>(nxt, stash_of(L - 1, 0));
   for (int l = L - 1; l >= 0; --l) {
@@ -293,6 +307,9 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
       const bool more = (s == 0) || (l > 0);
       const float* ust_next = more ? ((s == 0) ? stash_of(l, 1) : stash_of(l - 1, 0)) : ust;
       tc_trace(e.trace, e.tn, 40 + s, l);
+      if (l > 0) prefetch_unit(l - 1, s, colp);
+      else if (colp_next >= 0) prefetch_unit(L - 1, s, colp_next);      // the top layer of this CTA's next pair (group geometry of THIS
+                                                                        // segment: a pair of the other jet order is covered approximately)
       if (!top) {
         mbar_wait(&e.acc_ready[s], (e.acc_phase >> s) & 1u, 0x400 + s);
         e.acc_phase ^= 1u << s;
@@ -339,7 +356,7 @@ template <int NA, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradView grad, SegDev sa, SegDev sb,
                    const float* __restrict__ seed_absmax, const float* __restrict__ Ust, unsigned char* __restrict__ Zimg, int64_t ld,
-                   int64_t col0, unsigned long long* trace) {
+                   int64_t col0, unsigned long long* trace, int prefetch_l2) {
   using C = TcCfg<NA>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -385,10 +402,12 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
     const float wl = net.W[L][e.n];
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t colp = col0 + pair * 256;
+      const bool first_pair = pair == (int64_t)blockIdx.x;
+      const int64_t colp_next = (pair + gridDim.x < npairs) ? col0 + (pair + gridDim.x) * 256 : -1;
       if (pair < sa.npairs) {
-        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl);
+        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next);
       } else {
-        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl);
+        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next);
       }
     }
   }
@@ -518,8 +537,9 @@ static int tt_launch_bwd(const void* packed, const NetView& net, const GradView&
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
   const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
   if (grid < 1) return 0;
+  static const int prefetch_l2 = [] { const char* e = getenv("DUDF_BWD_PREFETCH_L2"); return e ? atoi(e) : 1; }();   // A/B switch
   k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, seed_absmax, Ust, (unsigned char*)Zimg, ld, col0,
-                                               tc_get_trace());
+                                               tc_get_trace(), prefetch_l2);
   DUDF_LAUNCH_OK();
   return 0;
 }

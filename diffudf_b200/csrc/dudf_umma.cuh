@@ -64,6 +64,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(void* bar, uint32_t parity, un
   }
 }
 
+// asks the L2 for a contiguous global range (16-byte aligned, size a multiple of 16): no registers, no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
