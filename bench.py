@@ -210,9 +210,13 @@ def aux_other_losses(dev, batches, n_on, precision="tcx3"):
     from diffudf_b200 import SIREN
     from diffudf_b200.train import FusedTrainer
     out = {}
-    for mode, w, key in (("s2", [1e5, 1e5], "loss_s2"), ("siren", [3e3, 1e2, 1e2, 5e1], "loss_siren")):
+    # "_graph": the same step captured once as a CUDA graph and replayed (FusedTrainer(graph=True): learning rate and Adam's step
+    # count on the device) — loss_s2's dozen small kernels take ~0.1 ms of device time, less than the host needs to launch them;
+    # "loss_s1_graph" is the headline step through the same mechanism
+    for mode, w, key, graph in (("s2", [1e5, 1e5], "loss_s2", False), ("s2", [1e5, 1e5], "loss_s2_graph", True),
+                                ("siren", [3e3, 1e2, 1e2, 5e1], "loss_siren", False), ("s1", W_S1, "loss_s1_graph", True)):
         torch.manual_seed(123)
-        tr = FusedTrainer(SIREN(3, 1, [256] * 8, w0=30).to(dev), precision=precision)
+        tr = FusedTrainer(SIREN(3, 1, [256] * 8, w0=30).to(dev), precision=precision, graph=graph)
         for i in range(4):
             tr.step(mode, *batches[i % len(batches)], n_on, w, ALPHA, LR)
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -99,6 +99,7 @@ SIGNATURES = {
     "dudf_loss_s2_stats": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "dudf_loss_s2_finish": [c_void_p, c_float, c_float, c_void_p, c_void_p],
     "dudf_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64, c_void_p],
+    "dudf_adam_step_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_void_p],
     "dudf_adam_step_guarded": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64, c_void_p,
                                c_void_p, c_void_p],
     "dudf_scale_guard": [c_void_p, c_void_p, c_float, c_void_p, c_void_p],

@@ -689,6 +689,13 @@ int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream);
 }
 
+int dudf_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* state, float beta1, float beta2, float eps,
+                       void* stream) {
+  DUDF_REQUIRE(p && g && m && v && state, "dudf_adam_step_dev: null argument");
+  DUDF_REQUIRE(((uintptr_t)state & 7) == 0, "dudf_adam_step_dev: state must be 8-byte aligned");
+  return adam_step_dev(p, g, m, v, n, state, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
 int dudf_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                            int64_t t, const float* unsafe_flag, int64_t* skipped, void* stream) {
   DUDF_REQUIRE(p && g && m && v && unsafe_flag, "dudf_adam_step_guarded: null argument");

@@ -152,6 +152,7 @@ int s2_finish(const double* stats, float w0, float w1, double* terms, cudaStream
 int loss_s2_stats(const float* packed, const float* dist, int64_t P, double* stats, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
               cudaStream_t st, const float* unsafe = nullptr, long long* skipped = nullptr);
+int adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* state, float b1, float b2, float eps, cudaStream_t st);
 int adam_step_peers(float* p, const float* const* peer_grads, int world, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                     int64_t t, int guarded, long long* skipped, float* g_sum_out, cudaStream_t st);
 int dirs9(const float* n, const float* dirs6, int64_t P, float* d9, cudaStream_t st);

@@ -161,6 +161,43 @@ int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
   return 0;
 }
 
+// The same update with its step-dependent scalars read from DEVICE memory, for a training step replayed as a CUDA graph (kernel
+// arguments are frozen at capture): state[0] = learning rate (written by the host when the schedule changes it), the 64-bit step count
+// behind it (state + 2, 8-byte aligned) and a block ticket (state + 4).  Every block forms lr / (1 - b1^t) and sqrt(1 - b2^t) for
+// t = count + 1 in double, like adam_step does on the host; the last block to finish advances the count.
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, int64_t n, float* __restrict__ state, float b1, float b2,
+                                                       float eps) {
+  __shared__ float sh[2];
+  long long* count = reinterpret_cast<long long*>(state + 2);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(state + 4);
+  if (threadIdx.x == 0) {
+    const double t = (double)(*count + 1);
+    sh[0] = (float)((double)state[0] / (1.0 - pow((double)b1, t)));
+    sh[1] = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2_sqrt = sh[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    adam_update(p[i], m[i], v[i], g[i], step_size, bc2_sqrt, b1, b2, eps);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {          // every block has read the count before the last one finishes
+      *count += 1;
+      *ticket = 0u;
+    }
+  }
+}
+
+int adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* state, float b1, float b2, float eps, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  adam_dev_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, state, b1, b2, eps);
+  DUDF_LAUNCH_OK();
+  return 0;
+}
+
 // Data-parallel Adam with the gradient all-reduce FUSED IN: every rank owns a gradient buffer in peer-mapped (symmetric) memory;
 // after a cross-rank barrier each rank's kernel reads element i of ALL ranks' buffers over NVLink (fixed rank order 0..W-1, so
 // every rank forms the bit-identical sum and the replicated parameters stay in lock-step), and applies the update — one pass

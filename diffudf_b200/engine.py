@@ -298,6 +298,15 @@ def adam_step(p, g, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, unsafe_flag=N
                                                 _lib.current_stream()), "dudf_adam_step_guarded")
 
 
+def adam_step_dev(p, g, m, v, state, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Adam with the learning rate and the step count read from (and the count advanced in) the 6-float device array `state`
+    (dudf_adam_step_dev): the form a CUDA graph of the training step can replay."""
+    L = _lib.lib()
+    with torch.cuda.device(p.device):
+        _lib.check(L.dudf_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), state.data_ptr(), float(beta1),
+                                        float(beta2), float(eps), _lib.current_stream()), "dudf_adam_step_dev")
+
+
 def adam_step_peers(p, peer_ptrs, world, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, guarded=False, skipped=None, g_sum_out=None):
     """Adam with the gradient all-reduce fused in (dudf_adam_step_peers): peer_ptrs = ctypes array of `world` device pointers to
     the ranks' (n + 1)-float gradient buffers in peer-mapped memory; the caller has ordered a cross-rank barrier before."""

@@ -13,7 +13,7 @@ import time
 import numpy as np
 import torch
 
-from .engine import adam_step, adam_step_peers, scale_guard
+from .engine import adam_step, adam_step_dev, adam_step_peers, scale_guard
 from .loss_functions import S1_KEYS, S2_KEYS, SIREN_KEYS, TrainCore
 
 
@@ -30,9 +30,18 @@ class FusedTrainer:
     """Owns flat fp32 parameter / gradient / Adam-moment buffers; the module's parameters become views
     of the flat buffer so that state_dict()/load_state_dict() keep working."""
 
-    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None, precision=None, fused=True):
+    def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, dp=None, precision=None, fused=True, graph=False):
+        """graph=True (single GPU): a step's launches — weight re-pack, forward, loss, reverse sweep, weight gradient, Adam — are
+        captured once per (mode, batch shape, loss weights) into a CUDA graph and replayed; the scalars that change from step to step
+        (learning rate, Adam's step count) live on the device (dudf_adam_step_dev).  A step that is dominated by launch overhead
+        (loss_s2: a dozen small kernels in ~0.1 ms of device time) no longer waits for the host."""
         self.model = model
         self.fused = fused                  # tensor-core steps of loss_s1 / loss_siren go through the single fused launch
+        self.graph = bool(graph)
+        self._graphs = {}                   # key -> dict(graph, x, n, d, terms) | "warm" (one eager step taken with this key)
+        self._adam_state = None             # device [lr, -, count lo, count hi, ticket, -] of dudf_adam_step_dev
+        self._dev_t = -1                    # host's idea of the device step count (-1: stale)
+        self._dev_lr = None
         self.betas, self.eps, self.dp = betas, eps, dp
         ws, bs = model._weights_biases()
         dev = ws[0].device
@@ -94,10 +103,58 @@ class FusedTrainer:
         self.grad_all, self.gW, self.gB = self.sets[k]
         self.grad = self.grad_all[:self.n]
 
+    GRAPH_LIMIT = 8            # distinct step signatures captured before falling back to eager launches
+
+    def _graph_step(self, mode, x, normals, d, n_on, weights, alpha, lr):
+        """Replay (or, the second time a signature is seen, capture) the step as a CUDA graph.  Returns None when this step must be
+        launched eagerly (first occurrence of a signature: it also creates every cached workspace the capture will refer to)."""
+        key = (mode, tuple(x.shape), int(n_on), tuple(float(w) for w in weights), float(alpha), self.core._prec())
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self.GRAPH_LIMIT:
+                return None
+            self._graphs[key] = "warm"
+            return None
+        dev = x.device
+        if self._adam_state is None:
+            self._adam_state = torch.zeros(6, device=dev, dtype=torch.float32)
+        if self._dev_lr != float(lr):
+            self._adam_state[0:1].fill_(float(lr))
+            self._dev_lr = float(lr)
+        if self._dev_t != self.t:                              # eager steps were taken in between
+            self._adam_state[2:4].view(torch.int64).fill_(self.t)
+            self._dev_t = self.t
+        if g == "warm":
+            sx, sn, sd = torch.empty_like(x), torch.empty_like(normals), torch.empty_like(d)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(graph):
+                self.grad_all.zero_()
+                terms = self.core.forward(mode, sx, sn, sd, n_on, weights, alpha, None, None, eager_seeds=True)
+                self.core.backward(None, self.gW, self.gB)
+                adam_step_dev(self.flat, self.grad, self.m, self.v, self._adam_state, self.betas[0], self.betas[1], self.eps)
+            # the graph refers to the core's cached workspaces (stash, operand images, packed jets, seeds): keep them alive when a
+            # step of another shape evicts them from the cache
+            g = dict(graph=graph, x=sx, n=sn, d=sd, terms=terms, keep=list(self.core.ws.values()))
+            self._graphs[key] = g
+        g["x"].copy_(x)
+        g["n"].copy_(normals)
+        g["d"].copy_(d)
+        g["graph"].replay()
+        self.t += 1
+        self._dev_t = self.t
+        if self.model._engine is not None:                     # parameters changed in place: eager users re-pack on next use
+            self.model._engine._sig = None
+        return g["terms"].clone()
+
     def step(self, mode, x, normals, d, n_on, weights, alpha, lr):
         """One optimisation step on a device-resident batch (x (P,3), normals (P,3), d (P,), fp32).
         Returns the (4,) float64 device tensor of this rank's loss-term shares (no sync)."""
         dp = self.dp
+        if self.graph and dp is None and (mode == "s2" or self.core._prec() != "tc16" or not self.fused):
+            terms = self._graph_step(mode, x, normals, d, n_on, weights, alpha, lr)
+            if terms is not None:
+                return terms
         P_global = dp.global_rows(x.shape[0]) if dp is not None else None
         if self.peer is not None:
             self._use_set(self.t % 2)
@@ -207,7 +264,9 @@ def _epoch_loop(dataset, model, device, config, stage_fn):
     if isinstance(opt, dict) and str(opt.get("type", "adam")).lower() != "adam":
         raise NotImplementedError(f"optimizer {opt.get('type')!r}: the fused loop implements torch.optim.Adam (train.py:334-337)")
     dp = config.get("dp")
-    trainer = FusedTrainer(model.to(device), dp=dp, precision=config.get("precision"))
+    # single GPU: every step signature of the schedule (loss_s1, loss_s2) is captured once as a CUDA graph and replayed
+    # (config['cuda_graph'] = False launches eagerly)
+    trainer = FusedTrainer(model.to(device), dp=dp, precision=config.get("precision"), graph=bool(config.get("cuda_graph", dp is None)))
     feeder = BatchFeeder(device)
     losses, best_loss, best_weights = {}, np.inf, None
     torch.cuda.synchronize(device)

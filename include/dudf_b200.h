@@ -264,6 +264,12 @@ int dudf_mesh_sample_surface(const float* triangles, const float* cdf, int64_t n
  * t is the 1-based step count.  Flat fp32 arrays of n elements. */
 int dudf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int64_t t, void* stream);
+/* The same update for a step that is replayed as a CUDA graph (kernel arguments are frozen at capture, so the scalars that change
+ * from step to step live on the device): state = 6 device floats, 8-byte aligned: [0] learning rate (fp32, written by the caller when
+ * the schedule changes it), [2..3] the 64-bit count of steps taken so far (the kernel uses t = count + 1 and advances it), [4] an
+ * internal block ticket (zero-initialised).  Bias corrections are formed in double as dudf_adam_step forms them on the host. */
+int dudf_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* state, float beta1, float beta2, float eps,
+                       void* stream);
 /* Safety net of the fused tensor-core step (dudf_train_step_fused scales its fp16 adjoints with the PREVIOUS step's seed
  * magnitude): dudf_scale_guard adds 1 to *flag when S(amax_prev) * amax_next exceeds `limit` (nominal range (1024, 2048], fp16
  * saturates at 65504) or is not finite; the flag lives in the slot behind the flat gradient so that the data-parallel

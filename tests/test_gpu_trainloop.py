@@ -137,3 +137,41 @@ def test_adam_step_peers_with_one_rank_equals_adam_step():
     before = p2.clone()
     adam_step_peers(p2, ptrs, 1, m2, v2, 1e-3, 5, guarded=True, skipped=skipped)
     assert torch.equal(p2, before) and int(skipped) == 1
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tcx3"])
+def test_graph_replayed_steps_equal_eager_steps(prec, golden, weights):
+    """FusedTrainer(graph=True): the step captured as a CUDA graph (learning rate and Adam's step count on the device,
+    dudf_adam_step_dev) against the eager launches — same loss terms, same parameters after s1 and s2 steps with a changing
+    learning rate and an eager step in between (the device count is re-synchronised)."""
+    from diffudf_b200 import SIREN
+    from diffudf_b200.train import FusedTrainer
+    T = golden("trajectory_init.npz")
+    runs = []
+    for graph in (False, True):
+        m = SIREN(3, 1, [256] * 8, w0=30, delay_init=True)
+        m.load_state_dict({f"net.{i}.0.{k}": torch.from_numpy(v) for i, (W, b) in enumerate(weights["init"])
+                           for k, v in (("weight", W), ("bias", b))})
+        tr = FusedTrainer(m.cuda(), precision=prec, graph=graph)
+        out = []
+        sched = [("s1", 1e-5), ("s1", 1e-5), ("s1", 1e-5), ("s1", 2e-6), ("s2", 1e-7), ("s2", 1e-7), ("s2", 5e-8), ("s1", 2e-6), ("s2", 5e-8)]
+        for step, (mode, lr) in enumerate(sched):
+            b = step % 7
+            x = torch.from_numpy(T["x"][b][0]).cuda()
+            n = torch.from_numpy(T["normals"][b][0]).cuda()
+            d = torch.from_numpy(T["d"][b][0, :, 0]).cuda()
+            n_on = int((T["d"][b][0, :, 0] == 0).sum())
+            w = [1e4, 1e4, 1e4, 1e3] if mode == "s1" else [1e5, 1e5]
+            out.append(tr.step(mode, x, n, d, n_on, w, 100.0, lr).cpu().numpy())
+        runs.append((out, tr.flat.clone(), tr.t))
+        if graph:
+            assert sum(isinstance(g, dict) for g in tr._graphs.values()) == 2           # s1 and s2 were captured
+            assert int(tr._adam_state[2:4].view(torch.int64).item()) == tr.t == len(sched)
+    (ta, pa, _), (tb, pb, _) = runs
+    for a, b in zip(ta, tb):
+        assert np.allclose(a, b, rtol=2e-4, atol=1e-7), (a, b)
+    # Same arithmetic (bias corrections in double on the device instead of on the host).  Gradients are accumulated with atomics, so
+    # two runs differ in the last bits, and Adam's first updates are sign-like (lr * g / |g|): an element whose gradient is ~0 may
+    # move by 2 lr in either run.  A wrong step count or learning rate would shift EVERY element by O(lr) = 1e-5.
+    diff = (pa - pb).abs()
+    assert float(diff.max()) < 2.5e-5 and float(diff.mean()) < 2e-7, (float(diff.max()), float(diff.mean()))
