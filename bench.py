@@ -604,7 +604,7 @@ def run_ours(args, rank, local_rank, world):
     flops = {"jet_forward_multi": third, "jet_backward_multi": third, "jet_wgrad": third, "fused_fwd_loss_bwd": 2 * third}
     traffic = {}
     try:        # DRAM bytes per launch from the committed ncu --set full capture of the same kernels (tools/ncu_summary.py)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r3_ncu_traffic.json")))
     except Exception:
         pass
     dom = max((k for k in prof if k in flops), key=lambda k: prof[k]) if prof else None
