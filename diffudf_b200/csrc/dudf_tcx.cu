@@ -42,7 +42,7 @@ constexpr int TCX_OFF_LO = TC_ACT_BYTES;       // lo tile behind the hi tile
 constexpr int TCX_OFF_RING = 2 * TC_ACT_BYTES;
 constexpr int TCX_OFF_WL = TCX_OFF_RING + TCX_STAGES * TC_CHUNK_BYTES;
 constexpr int TCX_OFF_XS = TCX_OFF_WL + 256 * 4;
-constexpr int TCX_OFF_OS = TCX_OFF_XS + 128 * 3 * 4;
+constexpr int TCX_OFF_OS = TCX_OFF_XS + 2 * 128 * 3 * 4;   // two point buffers: the next tile's points are loaded a tile ahead
 constexpr int TCX_OFF_BAR = TCX_OFF_OS + 8 * 128 * 4;        // os: [8 = neuron half x lane quarter][128 columns] partial sums
 constexpr int TCX_SMEM = TCX_OFF_BAR + 256 + 1024;
 static_assert(TCX_SMEM <= 232448, "shared memory budget");
@@ -304,139 +304,161 @@ __device__ __forceinline__ void tcx_act_point_dir(float* u, float s, float c, fl
   u[0] = s;
 }
 
-// all layers of one 128-column tile.  x == null: grid points (first + p).  TRAIN: stash the pre-activations, write raw channels.
-template <int NCH, bool TRAIN, int SC, int EW, bool DIR = false>
-__device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const float* __restrict__ x, int64_t P, int gridN, int64_t grid_first,
-                                         float vs, int64_t tile, bool valid, const QueryOut& out, float* outp, float* Ust, int64_t ld, int64_t colt,
-                                         int dbg, const float* __restrict__ dirs = nullptr) {
-  static_assert(!DIR || (NCH == 10 && !TRAIN), "directional third-order jet: 10 channels, queries only");
-  constexpr int XS = DIR ? 12 : 3;             // floats per point in xs: the point (+ its three directions)
+// ---- one 128-column tile, in pieces ------------------------------------------------------------------------------------------
+// Per-tile inputs of the epilogue warps.  x == null: grid points (grid_first + p).
+struct TcxTileArgs {
+  const float* x;
+  const float* dirs;      // DIR3 queries
+  int64_t P, tile, colt, grid_first;
+  int gridN;
+  float vs;
+  bool valid;
+  float* outp;            // TRAIN: raw channels [P][NCH]
+};
+enum { TCX_FIRST = 0, TCX_HIDDEN = 1, TCX_LAST = 2 };
+
+// the tile's points (+ directions) -> xs; cooperative over the EW epilogue warps, the caller orders a tcx_epi_bar before they are read
+template <int NCH, int EW, bool DIR>
+__device__ __forceinline__ void tcx_load_points(const TcxEpi& e, const TcxTileArgs& t, float* xs) {
+  constexpr int XS = DIR ? 12 : 3;
   using C = TcxCfg<NCH>;
-  constexpr int GC = C::GC;
-  const int L = net.n_lin - 1;
-  const float w0 = net.w0, ww = net.ww;
-  tc_trace(e.trace, e.tn, 14, NCH);
-  tcx_epi_bar<EW>();
   for (int i = e.tid; i < C::PT; i += EW * 32) {
-    const int64_t p = tile * C::PT + i;
+    const int64_t p = t.tile * C::PT + i;
     float pt[3] = {0.f, 0.f, 0.f};
-    if (valid && p < P) {
-      if (x) { pt[0] = x[p * 3]; pt[1] = x[p * 3 + 1]; pt[2] = x[p * 3 + 2]; }
-      else grid_point(grid_first + p, gridN, vs, pt);
+    if (t.valid && p < t.P) {
+      if (t.x) { pt[0] = t.x[p * 3]; pt[1] = t.x[p * 3 + 1]; pt[2] = t.x[p * 3 + 2]; }
+      else grid_point(t.grid_first + p, t.gridN, t.vs, pt);
     }
-    e.xs[i * XS] = pt[0]; e.xs[i * XS + 1] = pt[1]; e.xs[i * XS + 2] = pt[2];
+    xs[i * XS] = pt[0]; xs[i * XS + 1] = pt[1]; xs[i * XS + 2] = pt[2];
     if constexpr (DIR) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) e.xs[i * XS + 3 + k] = (valid && p < P) ? dirs[p * 9 + k] : 0.f;
+      for (int k = 0; k < 9; ++k) xs[i * XS + 3 + k] = (t.valid && p < t.P) ? t.dirs[p * 9 + k] : 0.f;
     }
   }
-  if (C::NV < 128 && e.tid < 256) {       // idle columns of both tiles are zero for this tile's math (a launch may mix jet orders)
-    *reinterpret_cast<uint4*>(tc_tile_row(e.act, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(tc_tile_row(e.act + TCX_OFF_LO, e.tid) + tc_chunk_off(15, e.tid & 7)) = make_uint4(0, 0, 0, 0);
-  }
-  tcx_epi_bar<EW>();
+}
+
+// One neuron half h of one layer l of tile t.  KIND: TCX_FIRST (l = 0: from the points in xs, no accumulator), TCX_HIDDEN, TCX_LAST
+// (l = L - 1: output layer into e.os).  The caller has waited for the accumulator (l > 0).  FIRST / HIDDEN publish the half to the MMA warp.
+template <int NCH, bool TRAIN, int SC, int EW, bool DIR, int KIND>
+__device__ __forceinline__ void tcx_half(TcxEpi& e, const NetView& net, const TcxTileArgs& t, const float* xs, int l, int h, float* Ust,
+                                         int64_t ld, int dbg) {
+  constexpr int XS = DIR ? 12 : 3;
+  using C = TcxCfg<NCH>;
+  constexpr int GC = C::GC;
+  const float w0 = net.w0, ww = net.ww;
   constexpr int NG_PER = (C::NGRP + EW / 4 - 1) / (EW / 4);
   const int g_begin = min(e.cw * NG_PER, C::NGRP), g_end = min(g_begin + NG_PER, C::NGRP);
-  for (int l = 0; l < L; ++l) {
-    for (int h = 0; h < 2; ++h) {
-      const int n = h * 128 + e.q * 32 + e.lane;               // this thread's neuron in this half = its row of the B operand
-      const uint32_t r7 = n & 7;
-      const uint32_t row_hi = smem_u32(tc_tile_row(e.act, n));
-      float r0x = 0.f, r0y = 0.f, r0z = 0.f, b0 = 0.f, bias = 0.f;
-      if (l == 0) { r0x = net.W[0][n * 3]; r0y = net.W[0][n * 3 + 1]; r0z = net.W[0][n * 3 + 2]; b0 = net.b[0][n]; }
-      else bias = ww * net.b[l][n];
-      const float wl = (l == L - 1) ? e.wl_s[n] : 0.f;
-      tc_trace(e.trace, e.tn, 40 + h, l);
-      if (l > 0) {
-        mbar_wait(&e.acc_ready[h], (e.acc_phase >> h) & 1u, 0x1400 + h);
-        e.acc_phase ^= 1u << h;
-        tc_fence_after();
-      }
-      tc_trace(e.trace, e.tn, 10 + h, l);
-      const uint32_t taddr = e.tmem_q + ((e.jg + (uint32_t)l - 1u) & 1u) * 256 + h * 128;
-      auto group = [&](int g, const TmemRegs<GC>* pre) {
-        float u[GC];
-        if (l == 0) {
-          if constexpr (DIR) tcx_first_layer_dir<GC>(u, e.xs + g * (GC / NCH) * XS, w0, r0x, r0y, r0z, b0);
-          else tc_first_layer_group<NCH, GC>(u, e.xs + g * (GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
-        } else {
-          if (dbg & 32) {            // diagnostics: no accumulator loads
-#pragma unroll
-            for (int j = 0; j < GC; ++j) u[j] = (float)(j + e.lane);
-          } else if (pre) {
-            tc_ld_take<GC>(*pre, u);
-          } else {
-            TmemRegs<GC> tr;
-            tc_ld_issue<GC>(taddr + g * GC, tr);
-            tc_ld_take<GC>(tr, u);
-          }
-          if constexpr (TRAIN) {       // the stash holds the unscaled pre-activations of every channel
-#pragma unroll
-            for (int j = 0; j < GC; ++j) u[j] *= TCX_WSCALE_INV;
-#pragma unroll
-            for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
-          } else {                     // queries: only the sine argument is unscaled, the derivative channels keep the 64 (below)
-#pragma unroll
-            for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] = fmaf(u[pp * NCH], TCX_WSCALE_INV, bias);
-          }
-        }
-        if constexpr (TRAIN) {
-          if (valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + colt) * 256 + n * 4 + (size_t)g * GC * 256);
-        }
-        if (!(dbg & 1)) {
-#pragma unroll
-          for (int pp = 0; pp < GC / NCH; ++pp) {
-            float sn, cs;
-            if constexpr (SC == 1) sincos_poly(u[pp * NCH], sn, cs);
-            else sincos_fast(u[pp * NCH], sn, cs);
-            if constexpr (TRAIN) tc_act_point<NCH>(u + pp * NCH, sn, cs);
-            else if constexpr (DIR) tcx_act_point_dir(u + pp * NCH, sn, cs, l == 0 ? 1.f : TCX_WSCALE_INV);
-            else tc_act_point_scaled<NCH>(u + pp * NCH, sn, cs, l == 0 ? 1.f : TCX_WSCALE_INV);
-          }
-        }
-        if (l < L - 1) {
-          if (!(dbg & 8)) tcx_store_group<GC>(u, row_hi, g * (GC / 8), r7);
-        } else {
-          // output layer (256 -> 1 per channel) on the fp32 activations: this warp's 32 neurons, reduced over its lanes
-#pragma unroll
-          for (int j = 0; j < GC; ++j) u[j] *= wl;
-          float* dst = e.os + (h * 4 + e.q) * 128 + g * GC;
-          tcx_colsum<32>(u, e.lane);
-          dst[e.lane] = u[0];
-          if constexpr (GC == 40) {
-            tcx_colsum<8>(u + 32, e.lane);
-            if (e.lane < 8) dst[32 + e.lane] = u[32];
-          }
-        }
-      };
-      // A TMEM load that competes with the accumulating MMAs of the other neuron half takes ~850 clk (tools/tcx_trace.py), three
-      // times the ~250 instructions of a group: with two groups per warp, both loads are issued up front so that their latencies
-      // overlap instead of adding up (two distinct register sets, no rotation: ptxas keeps them in place).  Half epilogue 2 250 -> 1 830
-      // clk, the MMA groups under it 2 020 -> 2 230 (TMEM reads and accumulation share the port), layer period 9 310 -> 8 820 clk:
-      // grid queries +4 % (profiles/r3_tcx_trace_ldtm_*.txt, r3_tcx_ab_ldtm.txt).  40-column groups (Hessian jet) LOSE 4-5 % with either
-      // form of look-ahead (both loads up front, or the second issued when the first has landed): only one of the two warp sets has a
-      // second group, and its earlier loads take TMEM cycles from the MMAs of the other neuron half.
-      if (GC == 32 && NG_PER == 2 && l > 0 && g_end - g_begin == 2 && !(dbg & (32 | 2048))) {
-        TmemRegs<GC> t0, t1;
-        tmem_ld_x64(taddr + g_begin * GC, t0.a, t1.a);       // one 64-column load (two x32 loads time the same)
-        group(g_begin, &t0);
-        group(g_begin + 1, &t1);
-      } else {
-#pragma unroll 1
-        for (int g = g_begin; g < g_end; ++g) group(g, nullptr);
-      }
-      tc_trace(e.trace, e.tn, 12 + h, l);
-      if (l < L - 1) {
-        tc_fence_before();
-        fence_proxy_async();
-        __syncwarp();
-        if (e.lane == 0) mbar_arrive(&e.act_ready[h]);
-      }
-      tc_trace(e.trace, e.tn, 30 + h, l);
+  const int n = h * 128 + e.q * 32 + e.lane;               // this thread's neuron in this half = its row of the B operand
+  const uint32_t r7 = n & 7;
+  const uint32_t row_hi = smem_u32(tc_tile_row(e.act, n));
+  float r0x = 0.f, r0y = 0.f, r0z = 0.f, b0 = 0.f, bias = 0.f;
+  if constexpr (KIND == TCX_FIRST) {
+    r0x = net.W[0][n * 3]; r0y = net.W[0][n * 3 + 1]; r0z = net.W[0][n * 3 + 2]; b0 = net.b[0][n];
+    // the idle columns of a tile narrower than 128 are zero for its MMAs (a launch may mix jet orders): every thread clears its own row
+    if (C::NV < 128 && e.cw == 0) {
+      tc_sts128(row_hi + tc_chunk_off(15, r7), 0u, 0u, 0u, 0u);
+      tc_sts128(row_hi + TCX_OFF_LO + tc_chunk_off(15, r7), 0u, 0u, 0u, 0u);
     }
+  } else {
+    bias = ww * net.b[l][n];
   }
+  const float wl = (KIND == TCX_LAST) ? e.wl_s[n] : 0.f;
+  tc_trace(e.trace, e.tn, 10 + h, l);
+  const uint32_t taddr = e.tmem_q + ((e.jg + (uint32_t)l - 1u) & 1u) * 256 + h * 128;
+  auto group = [&](int g, const TmemRegs<GC>* pre) {
+    float u[GC];
+    if constexpr (KIND == TCX_FIRST) {
+      if constexpr (DIR) tcx_first_layer_dir<GC>(u, xs + g * (GC / NCH) * XS, w0, r0x, r0y, r0z, b0);
+      else tc_first_layer_group<NCH, GC>(u, xs + g * (GC / NCH) * 3, w0, r0x, r0y, r0z, b0);
+    } else {
+      if (dbg & 32) {            // diagnostics: no accumulator loads
+#pragma unroll
+        for (int j = 0; j < GC; ++j) u[j] = (float)(j + e.lane);
+      } else if (pre) {
+        tc_ld_take<GC>(*pre, u);
+      } else {
+        TmemRegs<GC> tr;
+        tc_ld_issue<GC>(taddr + g * GC, tr);
+        tc_ld_take<GC>(tr, u);
+      }
+      if constexpr (TRAIN) {       // the stash holds the unscaled pre-activations of every channel
+#pragma unroll
+        for (int j = 0; j < GC; ++j) u[j] *= TCX_WSCALE_INV;
+#pragma unroll
+        for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] += bias;
+      } else {                     // queries: only the sine argument is unscaled, the derivative channels keep the 64 (below)
+#pragma unroll
+        for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] = fmaf(u[pp * NCH], TCX_WSCALE_INV, bias);
+      }
+    }
+    if constexpr (TRAIN) {
+      if (t.valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
+    }
+    if (!(dbg & 1)) {
+#pragma unroll
+      for (int pp = 0; pp < GC / NCH; ++pp) {
+        float sn, cs;
+        if constexpr (SC == 1) sincos_poly(u[pp * NCH], sn, cs);
+        else sincos_fast(u[pp * NCH], sn, cs);
+        if constexpr (TRAIN) tc_act_point<NCH>(u + pp * NCH, sn, cs);
+        else if constexpr (DIR) tcx_act_point_dir(u + pp * NCH, sn, cs, KIND == TCX_FIRST ? 1.f : TCX_WSCALE_INV);
+        else tc_act_point_scaled<NCH>(u + pp * NCH, sn, cs, KIND == TCX_FIRST ? 1.f : TCX_WSCALE_INV);
+      }
+    }
+    if constexpr (KIND != TCX_LAST) {
+      if (!(dbg & 8)) tcx_store_group<GC>(u, row_hi, g * (GC / 8), r7);
+    } else {
+      // output layer (256 -> 1 per channel) on the fp32 activations: this warp's 32 neurons, reduced over its lanes
+#pragma unroll
+      for (int j = 0; j < GC; ++j) u[j] *= wl;
+      float* dst = e.os + (h * 4 + e.q) * 128 + g * GC;
+      tcx_colsum<32>(u, e.lane);
+      dst[e.lane] = u[0];
+      if constexpr (GC == 40) {
+        tcx_colsum<8>(u + 32, e.lane);
+        if (e.lane < 8) dst[32 + e.lane] = u[32];
+      }
+    }
+  };
+  // A TMEM load that competes with the accumulating MMAs of the other neuron half takes ~850 clk (tools/tcx_trace.py), three
+  // times the ~250 instructions of a group: with two groups per warp, both loads are issued up front so that their latencies
+  // overlap instead of adding up (two distinct register sets, no rotation: ptxas keeps them in place).  Half epilogue 2 250 -> 1 830
+  // clk, the MMA groups under it 2 020 -> 2 230 (TMEM reads and accumulation share the port), layer period 9 310 -> 8 820 clk:
+  // grid queries +4 % (profiles/r3_tcx_trace_ldtm_*.txt, r3_tcx_ab_ldtm.txt).  40-column groups (Hessian jet) LOSE 4-5 % with either
+  // form of look-ahead (both loads up front, or the second issued when the first has landed): only one of the two warp sets has a
+  // second group, and its earlier loads take TMEM cycles from the MMAs of the other neuron half.
+  if (KIND != TCX_FIRST && GC == 32 && NG_PER == 2 && g_end - g_begin == 2 && !(dbg & (32 | 2048))) {
+    TmemRegs<GC> t0, t1;
+    tmem_ld_x64(taddr + g_begin * GC, t0.a, t1.a);       // one 64-column load (two x32 loads time the same)
+    group(g_begin, &t0);
+    group(g_begin + 1, &t1);
+  } else {
+#pragma unroll 1
+    for (int g = g_begin; g < g_end; ++g) group(g, nullptr);
+  }
+  tc_trace(e.trace, e.tn, 12 + h, l);
+  if constexpr (KIND != TCX_LAST) {
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (e.lane == 0) mbar_arrive(&e.act_ready[h]);
+  }
+  tc_trace(e.trace, e.tn, 30 + h, l);
+}
+
+__device__ __forceinline__ void tcx_wait_acc(TcxEpi& e, int l, int h) {
+  tc_trace(e.trace, e.tn, 40 + h, l);
+  mbar_wait(&e.acc_ready[h], (e.acc_phase >> h) & 1u, 0x1400 + h);
+  e.acc_phase ^= 1u << h;
+  tc_fence_after();
+}
+
+// partial sums of the output layer -> channels -> outputs of the tile's points
+template <int NCH, bool TRAIN, int EW, bool DIR>
+__device__ __forceinline__ void tcx_finish_tile(TcxEpi& e, const NetView& net, const TcxTileArgs& t, const QueryOut& out) {
+  using C = TcxCfg<NCH>;
+  const int L = net.n_lin - 1;
   tc_trace(e.trace, e.tn, 20, 0);
-  e.jg += (uint32_t)(L - 1);
   tcx_epi_bar<EW>();
   if (e.tid < C::NV) {
     float v = 0.f;
@@ -448,11 +470,11 @@ __device__ __forceinline__ void tcx_tile(TcxEpi& e, const NetView& net, const fl
   }
   tcx_epi_bar<EW>();
   if (e.tid < C::PT) {
-    const int64_t p = tile * C::PT + e.tid;
-    if (valid && p < P) {
+    const int64_t p = t.tile * C::PT + e.tid;
+    if (t.valid && p < t.P) {
       if constexpr (TRAIN) {
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) outp[p * NCH + ch] = e.os[e.tid * NCH + ch];
+        for (int ch = 0; ch < NCH; ++ch) t.outp[p * NCH + ch] = e.os[e.tid * NCH + ch];
       } else {
         finalize_point<NCH>(out, p, e.os + e.tid * NCH);
       }
@@ -507,7 +529,7 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
   } else {
     setmaxnreg_inc<TcxRegs<EW>::EPI>();
     TcxEpi e;
-    e.act = act; e.xs = (float*)(smem + TCX_OFF_XS); e.os = (float*)(smem + TCX_OFF_OS); e.wl_s = wl_s;
+    e.act = act; e.xs = nullptr; e.os = (float*)(smem + TCX_OFF_OS); e.wl_s = wl_s;
     e.act_ready = act_ready; e.acc_ready = acc_ready;
     e.q = warp & 3; e.cw = warp >> 2; e.lane = lane; e.tid = tid;
     e.tmem_q = tmem_base + ((uint32_t)(e.q * 32) << 16);
@@ -515,18 +537,66 @@ tcx_forward_kernel(const unsigned char* __restrict__ packed, NetView net, SegDev
     e.trace = (tr.trace && blockIdx.x == 0 && warp == 0) ? tr.trace + TC_TRACE_REGION : nullptr;
     e.tn = 0;
     const float vs = gridN > 1 ? 2.0f / (float)(gridN - 1) : 0.f;
-    for (int64_t rd = 0; rd < rounds; ++rd) {
+    float* xs2[2] = {(float*)(smem + TCX_OFF_XS), (float*)(smem + TCX_OFF_XS) + 128 * 3};
+    auto args_of = [&](int64_t rd) {
+      TcxTileArgs t;
       const int64_t tile = blockIdx.x + rd * gridDim.x;
-      const bool valid = tile < ntiles;
-      const int64_t colt = tr.col0 + tile * 128;
-      // diagnostics: 256 / 512 / 1024 = the epilogue warps of lane quarter 1 / 0 / 2 (the SM partition of the MMA warp / of the
-      // producer warp / of an idle warp) do no loads, math or stores — does the MMA stream slow down through its own partition?
-      const int dbg = tr.dbg | ((((tr.dbg & 256) && e.q == 1) || ((tr.dbg & 512) && e.q == 0) || ((tr.dbg & 1024) && e.q == 2)) ? 41 : 0);
-      if (!valid || tile < tiles_a) {
-        tcx_tile<NA, TRAIN, SC, EW, DIR>(e, net, sa.x, sa.P, gridN, grid_first, vs, tile, valid, out, sa.outp, tr.Ust, tr.ld, colt, dbg, tr.dirs);
-      } else {
-        if constexpr (NB > 0) tcx_tile<NB, TRAIN, SC, EW>(e, net, sb.x, sb.P, gridN, grid_first, vs, tile - tiles_a, valid, out, sb.outp, tr.Ust, tr.ld, colt, dbg);
+      t.valid = tile < ntiles;
+      const bool in_a = !t.valid || tile < tiles_a;          // a round past the end works on a fully masked tile of segment a
+      const SegDev& sg = in_a ? sa : sb;
+      t.x = sg.x; t.P = sg.P; t.outp = sg.outp; t.dirs = tr.dirs;
+      t.tile = in_a ? tile : tile - tiles_a;
+      t.colt = tr.col0 + tile * 128;
+      t.gridN = gridN; t.grid_first = grid_first; t.vs = vs;
+      return t;
+    };
+    auto is_a = [&](int64_t rd) { const int64_t tile = blockIdx.x + rd * gridDim.x; return NB == 0 || tile >= ntiles || tile < tiles_a; };
+    // diagnostics: 256 / 512 / 1024 = the epilogue warps of lane quarter 1 / 0 / 2 (the SM partition of the MMA warp / of the
+    // producer warp / of an idle warp) do no loads, math or stores — does the MMA stream slow down through its own partition?
+    const int dbg = tr.dbg | ((((tr.dbg & 256) && e.q == 1) || ((tr.dbg & 512) && e.q == 0) || ((tr.dbg & 1024) && e.q == 2)) ? 41 : 0);
+    constexpr int NBX = NB > 0 ? NB : NA;
+    auto load_points = [&](int64_t rd, float* xs) {
+      const TcxTileArgs t = args_of(rd);
+      if (is_a(rd)) tcx_load_points<NA, EW, DIR>(e, t, xs);
+      else tcx_load_points<NBX, EW, false>(e, t, xs);
+    };
+    auto first_half = [&](int64_t rd, int h) {
+      const TcxTileArgs t = args_of(rd);
+      if (is_a(rd)) tcx_half<NA, TRAIN, SC, EW, DIR, TCX_FIRST>(e, net, t, xs2[rd & 1], 0, h, tr.Ust, tr.ld, dbg);
+      else tcx_half<NBX, TRAIN, SC, EW, false, TCX_FIRST>(e, net, t, xs2[rd & 1], 0, h, tr.Ust, tr.ld, dbg);
+    };
+    // Tiles are software-pipelined across their boundary: the single in-place tile leaves the tensor pipe idle from the last MMA of a
+    // tile until the first layer of the next one is written, and the output layer + finalisation + point loads + first layer used to
+    // sit in that gap (7 500 of 69 000 clk per tile, tools/tcx_trace.py).  Now the next tile's points are loaded a tile ahead, and its
+    // first layer is written as soon as the last accumulator half of the current tile is complete (then the rows of that k-half are
+    // dead) — BEFORE the current tile's output layer is evaluated, which then runs under the next tile's MMAs.
+    if (rounds > 0) {
+      load_points(0, xs2[0]);
+      tcx_epi_bar<EW>();
+      first_half(0, 0);
+      first_half(0, 1);
+    }
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+      const TcxTileArgs t = args_of(rd);
+      const bool a = is_a(rd), more = rd + 1 < rounds;
+      tc_trace(e.trace, e.tn, 14, a ? NA : NBX);
+      if (more) load_points(rd + 1, xs2[(rd + 1) & 1]);
+      for (int l = 1; l < L - 1; ++l)
+        for (int h = 0; h < 2; ++h) {
+          tcx_wait_acc(e, l, h);
+          if (a) tcx_half<NA, TRAIN, SC, EW, DIR, TCX_HIDDEN>(e, net, t, nullptr, l, h, tr.Ust, tr.ld, dbg);
+          else tcx_half<NBX, TRAIN, SC, EW, false, TCX_HIDDEN>(e, net, t, nullptr, l, h, tr.Ust, tr.ld, dbg);
+        }
+      tcx_epi_bar<EW>();                                      // the next tile's points are visible to every warp; the previous tile's outputs have been read
+      for (int h = 0; h < 2; ++h) {
+        tcx_wait_acc(e, L - 1, h);                            // every MMA that read the rows of k-half h has completed
+        if (more) first_half(rd + 1, h);
+        if (a) tcx_half<NA, TRAIN, SC, EW, DIR, TCX_LAST>(e, net, t, nullptr, L - 1, h, tr.Ust, tr.ld, dbg);
+        else tcx_half<NBX, TRAIN, SC, EW, false, TCX_LAST>(e, net, t, nullptr, L - 1, h, tr.Ust, tr.ld, dbg);
       }
+      e.jg += (uint32_t)(L - 1);
+      if (a) tcx_finish_tile<NA, TRAIN, EW, DIR>(e, net, t, out);
+      else tcx_finish_tile<NBX, TRAIN, EW, false>(e, net, t, out);
     }
   }
   tc_fence_before();
@@ -639,6 +709,7 @@ int tcx_forward(const void* packed, const NetView& net, int nch, const float* x,
   a.P = P;
   TcxTrain tr;
   memset(&tr, 0, sizeof(tr));
+  DUDF_REQUIRE(net.n_lin >= 3, "split tensor-core path: at least two hidden layers");
   switch (nch) {
     case 1: return tcx_launch_cl<1, 0, false>(packed, net, a, b, (P + TcxCfg<1>::PT - 1) / TcxCfg<1>::PT, 0, gridN, grid_first, out, tr, sms, st);
     case 4: return tcx_launch_cl<4, 0, false>(packed, net, a, b, (P + TcxCfg<4>::PT - 1) / TcxCfg<4>::PT, 0, gridN, grid_first, out, tr, sms, st);
@@ -662,6 +733,7 @@ int tcx_forward_dir3(const void* packed, const NetView& net, const float* x, con
   QueryOut out;
   memset(&out, 0, sizeof(out));
   out.packed = out_packed;
+  DUDF_REQUIRE(net.n_lin >= 3, "split tensor-core path: at least two hidden layers");
   const int64_t tiles = (P + TcxCfg<10>::PT - 1) / TcxCfg<10>::PT;
   int cl = tcx_cluster_size();
   while (cl > 1 && tiles < 2 * cl) cl >>= 1;
@@ -678,6 +750,7 @@ int tcx_train_forward(const void* packed, const NetView& net, const TcSegment* s
                       int sms, cudaStream_t st) {
   DUDF_REQUIRE(ld % 64 == 0 && col0 % 128 == 0, "tensor-core stash: ld must be a multiple of 64 and col0 of 128");
   DUDF_REQUIRE(nseg == 1 || nseg == 2, "tensor-core training: 1 or 2 segments per launch");
+  DUDF_REQUIRE(net.n_lin >= 3, "split tensor-core path: at least two hidden layers");
   SegDev a, b;
   memset(&a, 0, sizeof(a));
   memset(&b, 0, sizeof(b));

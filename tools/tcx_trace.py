@@ -9,6 +9,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diffudf_b200 import SIREN, _lib  # noqa: E402
 
+train = len(sys.argv) > 1 and sys.argv[1] == "train"        # python tools/tcx_trace.py train [first tile] [tiles]: the training forward
+if train:
+    sys.argv[1] = "2"
 order = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 p0 = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ntiles = int(sys.argv[3]) if len(sys.argv) > 3 else 1
@@ -17,10 +20,22 @@ m = SIREN(3, 1, [256] * 8, w0=30).cuda()
 eng = m._engine_synced(2)
 x = torch.rand(1 << 19, 3, device="cuda") * 2 - 1
 buf = torch.zeros(2 * 8192, dtype=torch.int64, device="cuda")
-eng.query(x, order, "tcx3")
 L = _lib.lib()
-L.dudf_debug_set_trace(buf.data_ptr())
-eng.query(x, order, "tcx3")
+if train:
+    import numpy as np
+    from bench import ALPHA, W_S1, make_batches
+    from diffudf_b200.train import FusedTrainer
+    tr = FusedTrainer(m, precision="tcx3")
+    bx, bn, bd = make_batches(1, 0)[0]
+    bx, bn, bd = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (bx[0], bn[0], bd[0, :, 0]))
+    tr.core.forward("s1", bx, bn, bd, 9990, W_S1, ALPHA, None, None)
+    torch.cuda.synchronize()
+    L.dudf_debug_set_trace(buf.data_ptr())
+    tr.core.forward("s1", bx, bn, bd, 9990, W_S1, ALPHA, None, None)
+else:
+    eng.query(x, order, "tcx3")
+    L.dudf_debug_set_trace(buf.data_ptr())
+    eng.query(x, order, "tcx3")
 torch.cuda.synchronize()
 L.dudf_debug_set_trace(None)
 raw = buf.cpu().numpy().astype("uint64")
