@@ -96,8 +96,7 @@ __device__ __forceinline__ void tt_fwd_pair(EpiCtx& e, const NetView& net, const
         for (int g = 0; g < C::NGRP; ++g) {
           float u[C::GC];
           tc_first_layer_group<NCH, C::GC>(u, e.xs + (s * C::PT + g * (C::GC / NCH)) * 3, w0, r0x, r0y, r0z, b0);
-          tt_stash_group<NCH, C::GC>(u, ust + (size_t)g * C::GC * 256);
-          tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), e.r7);
+          tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), e.r7);      // no stash: the reverse sweep recomputes this layer from the points
         }
       } else {
         TmemRegs<C::GC> nxt;
@@ -249,7 +248,8 @@ __device__ __forceinline__ void tt_bwd_group(const uint4* raw, TmemRegs<GC>& tr,
 
 template <int NCH>
 __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const GradView& grad, const SegDev& sg, int64_t pair, int64_t colp,
-                                            const float* Ust, int64_t ld, float S, float wl, bool prefetch_l2, bool first_pair, int64_t colp_next) {
+                                            const float* Ust, int64_t ld, float S, float wl, bool prefetch_l2, bool first_pair, int64_t colp_next,
+                                            const FirstRow& fr) {
   using C = TcCfg<NCH>;
   const int L = net.n_lin - 1;
   const float invS = 1.0f / S;
@@ -296,18 +296,19 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
     prefetch_unit(L - 1, 0, colp);
     prefetch_unit(L - 1, 1, colp);
   }
+  // the first layer's pre-activations are recomputed from the points (RECOMP0): no stash is written or read for layer 0
   uint4 nxt[NRAW];
-  tt_stash_load<NCH, C::GC>(nxt, stash_of(L - 1, 0));
+  if (L > 1) tt_stash_load<NCH, C::GC>(nxt, stash_of(L - 1, 0));
   for (int l = L - 1; l >= 0; --l) {
     const float wl_cur = (l == 0) ? net.w0 : net.ww;
     const bool top = (l == L - 1), first = (l == 0);
     for (int s = 0; s < 2; ++s) {
       unsigned char* trow = tc_tile_row(e.act + s * TC_ACT_BYTES, e.n);
       const float* ust = stash_of(l, s);
-      const bool more = (s == 0) || (l > 0);
+      const bool more = (s == 0) ? (l > 0) : (l > 1);           // the next (layer, sub-tile) reads a stash
       const float* ust_next = more ? ((s == 0) ? stash_of(l, 1) : stash_of(l - 1, 0)) : ust;
       tc_trace(e.trace, e.tn, 40 + s, l);
-      if (l > 0) prefetch_unit(l - 1, s, colp);
+      if (l > 1) prefetch_unit(l - 1, s, colp);
       else if (colp_next >= 0) prefetch_unit(L - 1, s, colp_next);      // the top layer of this CTA's next pair (group geometry of THIS
                                                                         // segment: a pair of the other jet order is covered approximately)
       if (!top) {
@@ -321,19 +322,21 @@ __device__ __forceinline__ void tt_bwd_pair(EpiCtx& e, const NetView& net, const
 #pragma unroll 1
       for (int g = 0; g < C::NGRP; ++g) {
         uint4 ug[NRAW];
+        if (!first) {
 #pragma unroll
-        for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
-        if (g + 1 < C::NGRP) tt_stash_load<NCH, C::GC>(nxt, ust + (size_t)(g + 1) * C::GC * 256);
-        else if (more) tt_stash_load<NCH, C::GC>(nxt, ust_next);
+          for (int j = 0; j < NRAW; ++j) ug[j] = nxt[j];
+          if (g + 1 < C::NGRP) tt_stash_load<NCH, C::GC>(nxt, ust + (size_t)(g + 1) * C::GC * 256);
+          else if (more) tt_stash_load<NCH, C::GC>(nxt, ust_next);
+        }
         // the group's own accumulators are loaded inside the group and used in place (NOW): the TMEM load hides behind the stash
         // conversion, and ptxas no longer copies the 32 / 40 staging registers of a prefetched group out and back
         const uint32_t tcur = e.tmem_lane + s * 256 + g * C::GC;
         const float* sdg = sd + s * 256 + g * C::GC;
         const float* pts = e.xs + (s * C::PT + g * (C::GC / NCH)) * 3;
         const int c0 = g * (C::GC / 8);
-        if (top && first) tt_bwd_group<NCH, C::GC, true, true, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        if (top && first) tt_bwd_group<NCH, C::GC, true, true, true, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s, &fr);
         else if (top)     tt_bwd_group<NCH, C::GC, true, false, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
-        else if (first)   tt_bwd_group<NCH, C::GC, false, true, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
+        else if (first)   tt_bwd_group<NCH, C::GC, false, true, true, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s, &fr);
         else              tt_bwd_group<NCH, C::GC, false, false, false, true>(ug, tr, tcur, wl, sdg, pts, trow, c0, e.r7, bsum, wlsum, w0s);
       }
       tc_trace(e.trace, e.tn, 32 + s, l);
@@ -400,14 +403,16 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
     e.acc_phase = 0;
     const float S = loss_scale_from(seed_absmax);
     const float wl = net.W[L][e.n];
+    FirstRow fr;
+    fr.w0 = net.w0; fr.rx = net.W[0][e.n * 3]; fr.ry = net.W[0][e.n * 3 + 1]; fr.rz = net.W[0][e.n * 3 + 2]; fr.b = net.b[0][e.n];
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t colp = col0 + pair * 256;
       const bool first_pair = pair == (int64_t)blockIdx.x;
       const int64_t colp_next = (pair + gridDim.x < npairs) ? col0 + (pair + gridDim.x) * 256 : -1;
       if (pair < sa.npairs) {
-        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next);
+        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next, fr);
       } else {
-        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next);
+        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next, fr);
       }
     }
   }

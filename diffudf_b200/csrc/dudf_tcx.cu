@@ -391,7 +391,7 @@ __device__ __forceinline__ void tcx_half(TcxEpi& e, const NetView& net, const Tc
         for (int pp = 0; pp < GC / NCH; ++pp) u[pp * NCH] = fmaf(u[pp * NCH], TCX_WSCALE_INV, bias);
       }
     }
-    if constexpr (TRAIN) {
+    if constexpr (TRAIN && KIND != TCX_FIRST) {      // (the reverse sweep recomputes the first layer from the points: no stash for it)
       if (t.valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
     }
     if (!(dbg & 1)) {
