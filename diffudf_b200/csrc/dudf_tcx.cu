@@ -135,7 +135,7 @@ __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* 
   };
   for (int64_t r = 0; r < rounds; ++r) {
     const int64_t tile = blockIdx.x + r * gridDim.x;
-    const bool copy = img != nullptr && tile < ntiles;
+    const bool copy = img != nullptr && tile < ntiles && !(dbg & 16384);
     for (int j = 0; j < n_phase; ++j, ++jg) {
       const uint32_t acc = tmem_base + (jg & 1u) * 256;
       for (int kh = 0; kh < 2; ++kh) {
@@ -260,7 +260,7 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   int64_t ld, col0;
   int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
                           //   8 no tile stores, 16 no collector reuse of the weight operand, 32 no accumulator loads,
-                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group
+                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group, 8192 no stash stores, 16384 no operand-image copies
   unsigned long long* trace;
   const float* dirs;      // DIR3 queries: [P][9] = three unit directions (a, b, c) per point
 };
@@ -392,7 +392,7 @@ __device__ __forceinline__ void tcx_half(TcxEpi& e, const NetView& net, const Tc
       }
     }
     if constexpr (TRAIN && KIND != TCX_FIRST) {      // (the reverse sweep recomputes the first layer from the points: no stash for it)
-      if (t.valid) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
+      if (t.valid && !(dbg & 8192)) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
     }
     if (!(dbg & 1)) {
 #pragma unroll
