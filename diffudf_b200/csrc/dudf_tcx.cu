@@ -164,7 +164,10 @@ __device__ __forceinline__ void tcx_mma_role(unsigned char* act, unsigned char* 
             mbar_wait(&full[stage], phase, 0x1300 + stage);                    // hi chunk: against the hi and the lo tile
             const uint64_t a_hi = desc_advance(a_desc0, stage * TC_CHUNK_BYTES);
             if (!skip) {
-              if (dbg & 16) {       // diagnostics: no collector reuse (A re-read from shared memory by every MMA)
+              // Wh x (Ah, Al): pairwise per K = 16 step with the weight slice latched in the collector, or as two runs of four steps
+              // that re-read it.  Measured (profiles/r3_tcx_ab_ldtm.txt): queries are 2 % (f, grad) to 10 % (value only) FASTER
+              // without the reuse, the training forward 0.8 % slower — so each mode takes its own; DUDF_TCX_DBG bit 16 swaps them
+              if (((dbg & 16) != 0) == (img != nullptr)) {
                 mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bh_desc0, koff), idesc, (kh | kb) != 0);
                 mma_f16_ss_k64_warp(d_tmem, a_hi, desc_advance(bl_desc0, koff), idesc, 1);
               } else {
@@ -259,8 +262,8 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   unsigned char* Aimg;
   int64_t ld, col0;
   int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
-                          //   8 no tile stores, 16 no collector reuse of the weight operand, 32 no accumulator loads,
-                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group, 8192 no stash stores, 16384 no operand-image copies
+                          //   8 no tile stores, 16 swap the collector-reuse choice (training: reuse, queries: none), 32 no accumulator loads,
+                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group, 8192 no stash stores, 16384 no operand-image copies, 32768 stash into one 128 KB region per CTA (stays in the L2)
   unsigned long long* trace;
   const float* dirs;      // DIR3 queries: [P][9] = three unit directions (a, b, c) per point
 };
@@ -392,7 +395,8 @@ __device__ __forceinline__ void tcx_half(TcxEpi& e, const NetView& net, const Tc
       }
     }
     if constexpr (TRAIN && KIND != TCX_FIRST) {      // (the reverse sweep recomputes the first layer from the points: no stash for it)
-      if (t.valid && !(dbg & 8192)) tt_stash_group<NCH, GC>(u, Ust + ((size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
+      if (t.valid && !(dbg & 8192))
+        tt_stash_group<NCH, GC>(u, Ust + ((dbg & 32768) ? (size_t)blockIdx.x * 128 : (size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
     }
     if (!(dbg & 1)) {
 #pragma unroll
