@@ -426,18 +426,22 @@ struct Stash {
   static constexpr int CHUNKS = (NCH == 1) ? GC / 4 : NF4 + NH8;
 };
 
+// `hint`: 0 plain stores, 1 st.global.cs (streaming), 2 st.global.wt (write-through)
+__device__ __forceinline__ void tt_st16(float* dst, float4 v, int hint) {
+  if (hint == 1) __stcs(reinterpret_cast<float4*>(dst), v);
+  else if (hint == 2) __stwt(reinterpret_cast<float4*>(dst), v);
+  else *reinterpret_cast<float4*>(dst) = v;
+}
 template <int NCH, int GC>
-__device__ __forceinline__ void tt_stash_group(const float* u, float* dst) {
+__device__ __forceinline__ void tt_stash_group(const float* u, float* dst, int hint = 0) {
   using S = Stash<NCH, GC>;
   if constexpr (NCH == 1) {
 #pragma unroll
-    for (int j4 = 0; j4 < GC / 4; ++j4)
-      *reinterpret_cast<float4*>(dst + j4 * 1024) = make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]);
+    for (int j4 = 0; j4 < GC / 4; ++j4) tt_st16(dst + j4 * 1024, make_float4(u[j4 * 4], u[j4 * 4 + 1], u[j4 * 4 + 2], u[j4 * 4 + 3]), hint);
   } else {
 #pragma unroll
     for (int j4 = 0; j4 < S::NF4; ++j4)
-      *reinterpret_cast<float4*>(dst + j4 * 1024) =
-          make_float4(u[(j4 * 4) * NCH], u[(j4 * 4 + 1) * NCH], u[(j4 * 4 + 2) * NCH], u[(j4 * 4 + 3) * NCH]);
+      tt_st16(dst + j4 * 1024, make_float4(u[(j4 * 4) * NCH], u[(j4 * 4 + 1) * NCH], u[(j4 * 4 + 2) * NCH], u[(j4 * 4 + 3) * NCH]), hint);
     float d[S::NH8 * 8];
 #pragma unroll
     for (int pp = 0; pp < S::NP; ++pp)
@@ -447,9 +451,10 @@ __device__ __forceinline__ void tt_stash_group(const float* u, float* dst) {
     for (int j = S::ND; j < S::NH8 * 8; ++j) d[j] = 0.f;
 #pragma unroll
     for (int c8 = 0; c8 < S::NH8; ++c8)
-      *reinterpret_cast<uint4*>(dst + (S::NF4 + c8) * 1024) =
-          make_uint4(tc_pack_h2(d[8 * c8], d[8 * c8 + 1]), tc_pack_h2(d[8 * c8 + 2], d[8 * c8 + 3]),
-                     tc_pack_h2(d[8 * c8 + 4], d[8 * c8 + 5]), tc_pack_h2(d[8 * c8 + 6], d[8 * c8 + 7]));
+      tt_st16(dst + (S::NF4 + c8) * 1024,
+              make_float4(__uint_as_float(tc_pack_h2(d[8 * c8], d[8 * c8 + 1])), __uint_as_float(tc_pack_h2(d[8 * c8 + 2], d[8 * c8 + 3])),
+                          __uint_as_float(tc_pack_h2(d[8 * c8 + 4], d[8 * c8 + 5])), __uint_as_float(tc_pack_h2(d[8 * c8 + 6], d[8 * c8 + 7]))),
+              hint);
   }
 }
 

@@ -108,7 +108,7 @@ __device__ __forceinline__ void tt_fwd_pair(EpiCtx& e, const NetView& net, const
           if (g + 1 < C::NGRP) tc_ld_issue<C::GC>(e.tmem_lane + s * 256 + (g + 1) * C::GC, nxt);
 #pragma unroll
           for (int pp = 0; pp < C::GC / NCH; ++pp) u[pp * NCH] += bias;
-          tt_stash_group<NCH, C::GC>(u, ust + (size_t)g * C::GC * 256);
+          tt_stash_group<NCH, C::GC>(u, ust + (size_t)g * C::GC * 256, 1);
           tc_emit_group<NCH, C::GC, true>(u, trow, g * (C::GC / 8), e.r7);
         }
       }

@@ -263,7 +263,7 @@ struct TcxTrain {         // training forward: stash + operand images (null for 
   int64_t ld, col0;
   int dbg;                // diagnostics (DUDF_TCX_DBG; results are meaningless): 1 no epilogue math, 2 no MMAs, 4 no weight traffic,
                           //   8 no tile stores, 16 swap the collector-reuse choice (training: reuse, queries: none), 32 no accumulator loads,
-                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group, 8192 no stash stores, 16384 no operand-image copies, 32768 stash into one 128 KB region per CTA (stays in the L2)
+                          //   256 / 512 / 1024 lane quarter 1 / 0 / 2 idle (see tcx_forward_kernel), 2048 accumulator loads group by group, 8192 no stash stores, 16384 no operand-image copies, 32768 stash into one 128 KB region per CTA (stays in the L2), 65536 plain instead of streaming stash stores
   unsigned long long* trace;
   const float* dirs;      // DIR3 queries: [P][9] = three unit directions (a, b, c) per point
 };
@@ -396,7 +396,8 @@ __device__ __forceinline__ void tcx_half(TcxEpi& e, const NetView& net, const Tc
     }
     if constexpr (TRAIN && KIND != TCX_FIRST) {      // (the reverse sweep recomputes the first layer from the points: no stash for it)
       if (t.valid && !(dbg & 8192))
-        tt_stash_group<NCH, GC>(u, Ust + ((dbg & 32768) ? (size_t)blockIdx.x * 128 : (size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256);
+        tt_stash_group<NCH, GC>(u, Ust + ((dbg & 32768) ? (size_t)blockIdx.x * 128 : (size_t)l * ld + t.colt) * 256 + n * 4 + (size_t)g * GC * 256,
+                                (dbg & 65536) ? 0 : 1);      // streaming stores (st.global.cs): -2.6 % on the launch against plain ones (bit 65536)
     }
     if (!(dbg & 1)) {
 #pragma unroll
