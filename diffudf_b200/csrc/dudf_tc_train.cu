@@ -388,8 +388,8 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
     if (warp == 8) {
       if (lane == 0) tc_producer<1>(packed, ring, full, empty, rounds, L - 1, TC_DIR_BWD);
     } else if (warp == 9) {
-      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD, 0, 0ull,
-                     (trace && blockIdx.x == 0) ? trace : nullptr);
+      tc_mma_role<1>(act, ring, full, empty, act_ready, acc_ready, tmem_base, rounds, L - 1, nullptr, Zimg, ld >> 6, col0 >> 6, TC_DIR_BWD, 0,
+                     (prefetch_l2 & 2) ? l2_policy_evict_first() : 0ull, (trace && blockIdx.x == 0) ? trace : nullptr);
     }
   } else {
     setmaxnreg_inc<TC_REGS_EPI>();
@@ -410,9 +410,9 @@ tt_backward_kernel(const unsigned char* __restrict__ packed, NetView net, GradVi
       const bool first_pair = pair == (int64_t)blockIdx.x;
       const int64_t colp_next = (pair + gridDim.x < npairs) ? col0 + (pair + gridDim.x) * 256 : -1;
       if (pair < sa.npairs) {
-        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next, fr);
+        tt_bwd_pair<NA>(e, net, grad, sa, pair, colp, Ust, ld, S, wl, (prefetch_l2 & 1) != 0, first_pair, colp_next, fr);
       } else {
-        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl, prefetch_l2, first_pair, colp_next, fr);
+        if constexpr (NB > 0) tt_bwd_pair<NB>(e, net, grad, sb, pair - sa.npairs, colp, Ust, ld, S, wl, (prefetch_l2 & 1) != 0, first_pair, colp_next, fr);
       }
     }
   }
@@ -543,7 +543,7 @@ static int tt_launch_bwd(const void* packed, const NetView& net, const GradView&
   DUDF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NA>::SMEM));
   const int grid = (int)std::min<int64_t>(a.npairs + b.npairs, sms);
   if (grid < 1) return 0;
-  static const int prefetch_l2 = [] { const char* e = getenv("DUDF_BWD_PREFETCH_L2"); return e ? atoi(e) : 1; }();   // A/B switch
+  static const int prefetch_l2 = [] { const char* e = getenv("DUDF_BWD_PREFETCH_L2"); return e ? atoi(e) : 3; }();   // A/B switch: bit 0 stash prefetch, bit 1 evict-first adjoint images
   k<<<grid, TC_THREADS, TcCfg<NA>::SMEM, st>>>((const unsigned char*)packed, net, grad, a, b, seed_absmax, Ust, (unsigned char*)Zimg, ld, col0,
                                                tc_get_trace(), prefetch_l2);
   DUDF_LAUNCH_OK();
