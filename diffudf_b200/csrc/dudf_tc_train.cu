@@ -430,7 +430,7 @@ constexpr int TW_SMEM = TW_STAGES * 2 * TC_IMG_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(192, 1)
 tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const unsigned char* __restrict__ Aimg, int64_t ncb, int splits,
-                float ww, const float* __restrict__ seed_absmax, int layer0) {
+                float ww, const float* __restrict__ seed_absmax, int layer0, int evict_first) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + TW_STAGES * 2 * TC_IMG_BYTES);
@@ -456,12 +456,18 @@ tt_wgrad_kernel(GradView grad, const unsigned char* __restrict__ Zimg, const uns
   if (warp == 4) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t policy = evict_first ? l2_policy_evict_first() : 0ull;
       // (asking the blocks behind the ring into the L2 with bulk prefetches makes this HBM-bound kernel 30-45 % SLOWER: measured, removed)
       for (int64_t cb = cb0; cb < cb1; ++cb) {
         mbar_wait(&empty[stage], phase ^ 1, 0x500 + stage);
         mbar_arrive_expect_tx(&full[stage], 2 * TC_IMG_BYTES);
-        bulk_g2s(smem + stage * 2 * TC_IMG_BYTES, zsrc + (size_t)cb * TC_IMG_BYTES, TC_IMG_BYTES, &full[stage]);
-        bulk_g2s(smem + stage * 2 * TC_IMG_BYTES + TC_IMG_BYTES, asrc + (size_t)cb * TC_IMG_BYTES, TC_IMG_BYTES, &full[stage]);
+        if (policy) {             // the images are read exactly once: keep them from displacing what the next step's kernels find in the L2
+          bulk_g2s_hint(smem + stage * 2 * TC_IMG_BYTES, zsrc + (size_t)cb * TC_IMG_BYTES, TC_IMG_BYTES, &full[stage], policy);
+          bulk_g2s_hint(smem + stage * 2 * TC_IMG_BYTES + TC_IMG_BYTES, asrc + (size_t)cb * TC_IMG_BYTES, TC_IMG_BYTES, &full[stage], policy);
+        } else {
+          bulk_g2s(smem + stage * 2 * TC_IMG_BYTES, zsrc + (size_t)cb * TC_IMG_BYTES, TC_IMG_BYTES, &full[stage]);
+          bulk_g2s(smem + stage * 2 * TC_IMG_BYTES + TC_IMG_BYTES, asrc + (size_t)cb * TC_IMG_BYTES, TC_IMG_BYTES, &full[stage]);
+        }
         if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -605,9 +611,10 @@ int tc_train_wgrad(const NetView& net, const GradView& grad, const void* Zimg, c
   const int nl = layer_hi - layer_lo;
   int splits = std::max(1, sms / nl);
   splits = (int)std::min<int64_t>(splits, ncb);
+  static const int wgrad_evict_first = [] { const char* e = getenv("DUDF_WGRAD_EVICT_FIRST"); return e ? atoi(e) : 1; }();   // A/B switch
   DUDF_CUDA_OK(cudaFuncSetAttribute(tt_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
   tt_wgrad_kernel<<<nl * splits, 192, TW_SMEM, st>>>(grad, (const unsigned char*)Zimg, (const unsigned char*)Aimg, ncb, splits, net.ww,
-                                                    seed_absmax, layer_lo);
+                                                    seed_absmax, layer_lo, wgrad_evict_first);
   DUDF_LAUNCH_OK();
   return 0;
 }

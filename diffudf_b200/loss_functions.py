@@ -93,15 +93,17 @@ class TrainCore:
         segs, ld, nout = self.plan(mode, P, n_on, w, prec)
         Z, A, Zb = self._stashes(m.n_hidden, ld, prec)
         packed = self._buf("packed", (nout,))
-        terms = torch.zeros(4, device=x.device, dtype=torch.float64)
-        stats = torch.zeros(3, device=x.device, dtype=torch.float64) if mode == "s2" else None
+        # one fill for the step's small accumulators: 4 loss terms, 3 loss_s2 statistics (float64) and the seed magnitude (float32)
+        small = torch.zeros(8, device=x.device, dtype=torch.float64)
+        terms = small[:4]
+        stats = small[4:7] if mode == "s2" else None
         eng.jet_forward_multi([dict(x=x[s["row0"]:s["row0"] + s["rows"]], order=s["order"], col0=s["col0"],
                                     packed=packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]) for s in segs], Z, A, ld, prec)
         seeds = None
         if eager_seeds and mode != "s2":
             seeds = self._buf("seeds", (nout,))
             if absmax is None and prec in TC_PRECISIONS:
-                absmax = torch.zeros(1, device=x.device, dtype=torch.float32)
+                absmax = small[7:].view(torch.float32)[:1]
         for s in segs:
             pk = packed[s["off"]:s["off"] + s["rows"] * NCH[s["order"]]]
             ds = d[s["row0"]:s["row0"] + s["rows"]]
