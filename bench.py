@@ -277,9 +277,13 @@ def aux_full_size_queries(dev):
     # evaluate(): host numpy in, float64 host arrays out (value + gradient), 2 M points
     xs = np.random.default_rng(0).uniform(-1, 1, (2_000_000, 3)).astype(np.float32)
     grads = np.zeros((xs.shape[0], 3))
-    t0 = time.perf_counter()
-    evaluate(m, xs, device=dev, gradients=grads, max_batch=1 << 20)
-    out["evaluate_host_2M_value_grad_queries_per_s"] = xs.shape[0] / (time.perf_counter() - t0)
+    evaluate(m, xs, device=dev, gradients=grads, max_batch=1 << 20)          # warm-up: pinned staging, page faults of the result arrays
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        evaluate(m, xs, device=dev, gradients=grads, max_batch=1 << 20)
+        times.append(time.perf_counter() - t0)
+    out["evaluate_host_2M_value_grad_queries_per_s"] = xs.shape[0] / sorted(times)[1]
     # NDF projection (config 5): 2 M seeds, 3 steps (2 gradient queries + 1 Hessian query per point)
     smp = Sampler(decoder=m, device=dev)
     seeds = torch.from_numpy(xs.astype(np.float64)).to(dev)

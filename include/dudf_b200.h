@@ -134,8 +134,10 @@ int dudf_shade_hits(const long long* rows, int64_t H, const double* samples, con
 int dudf_cap_mesh(dudf_ctx* ctx, const float* df, const float* vecs, int N, float threshold, double* tris, int64_t capacity,
                   int64_t* n_tris_host, void* stream);
 
-/* evaluate() of src/evaluate.py:5-37 with HOST buffers: chunks of max_batch points, fp32 compute, results
- * widened to float64 on the device and copied into the caller's arrays (any of them may be NULL). */
+/* evaluate() of src/evaluate.py:5-37 with HOST buffers: chunks of at most max_batch points, fp32 compute, results
+ * widened to float64 on the device and copied into the caller's arrays (any of them may be NULL).  The chunks run through a
+ * two-slot pipeline (kernels on `stream`, device -> pinned staging on a copy stream, staging -> the caller's pageable arrays on
+ * the host); the call returns when every result is in place. */
 int dudf_evaluate_host(dudf_ctx* ctx, const float* x_host, int64_t N, int order, double* f_host, double* g_host,
                        double* H_host, int64_t max_batch, int precision, void* stream);
 
