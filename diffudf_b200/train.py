@@ -115,6 +115,8 @@ class FusedTrainer:
                 return None
             self._graphs[key] = "warm"
             return None
+        if g == "eager":                                       # a capture of this signature failed before
+            return None
         dev = x.device
         if self._adam_state is None:
             self._adam_state = torch.zeros(6, device=dev, dtype=torch.float32)
@@ -128,11 +130,19 @@ class FusedTrainer:
             sx, sn, sd = torch.empty_like(x), torch.empty_like(normals), torch.empty_like(d)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(dev)
-            with torch.cuda.graph(graph):
-                self.grad_all.zero_()
-                terms = self.core.forward(mode, sx, sn, sd, n_on, weights, alpha, None, None, eager_seeds=True)
-                self.core.backward(None, self.gW, self.gB)
-                adam_step_dev(self.flat, self.grad, self.m, self.v, self._adam_state, self.betas[0], self.betas[1], self.eps)
+            try:
+                with torch.cuda.graph(graph):
+                    self.grad_all.zero_()
+                    terms = self.core.forward(mode, sx, sn, sd, n_on, weights, alpha, None, None, eager_seeds=True)
+                    self.core.backward(None, self.gW, self.gB)
+                    adam_step_dev(self.flat, self.grad, self.m, self.v, self._adam_state, self.betas[0], self.betas[1], self.eps)
+            except Exception as exc:                           # nothing was executed: launch this signature eagerly from now on
+                import warnings
+                warnings.warn(f"diffudf_b200: CUDA-graph capture of the {mode} step failed ({exc!r}); launching it eagerly")
+                self._graphs[key] = "eager"
+                self.core.pending = None
+                self._dev_t = -1
+                return None
             # the graph refers to the core's cached workspaces (stash, operand images, packed jets, seeds): keep them alive when a
             # step of another shape evicts them from the cache
             g = dict(graph=graph, x=sx, n=sn, d=sd, terms=terms, keep=list(self.core.ws.values()))
