@@ -133,3 +133,25 @@ def test_triangle_soup_export_roundtrip(tmp_path):
             vs = np.array([[float(t) for t in l.split()] for l in txt[h + 1:h + 1 + len(v)]])
             fs = np.array([[int(t) for t in l.split()[1:]] for l in txt[h + 1 + len(v):]])
         assert np.array_equal(vs, v) and np.array_equal(fs, f)          # repr() round-trips float64 exactly
+
+
+def test_cloud_index_buffer_sizes():
+    """dudf_cloud_index_bytes (host arithmetic only): header + points padded to whole 32-leaf blocks + one box pair per node of every
+    level up to the first level with at most 32 boxes; out-of-range sizes answer -1."""
+    from diffudf_b200 import _lib
+    L = _lib.lib()
+    assert L.dudf_cloud_index_bytes(0) == -1 and L.dudf_cloud_index_bytes(-5) == -1 and L.dudf_cloud_index_bytes((1 << 30) + 1) == -1
+    def expect(n):
+        pts = ((n + 31) // 32 + 31) // 32 * 1024
+        total, count = 64 + pts * 16, n
+        while True:
+            count = (count + 31) // 32
+            total += (count + 31) // 32 * 32 * 32
+            if count <= 32:
+                return total
+    prev = 0
+    for n in (1, 31, 32, 33, 1024, 1025, 32768, 32769, 200000, 1 << 20, (1 << 20) + 1, 1 << 30):
+        b = L.dudf_cloud_index_bytes(n)
+        assert b == expect(n), (n, b, expect(n))
+        assert b >= prev and b % 16 == 0
+        prev = b
