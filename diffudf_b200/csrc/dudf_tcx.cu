@@ -80,7 +80,7 @@ struct TcxCfg {
 // TMEM-load / conversion / store latencies of each other, and a neuron half is turned around in ~half the time — the half
 // epilogue sits on the critical path of the in-place schedule (tools/tcx_trace.py).
 template <int EW> __device__ __forceinline__ void tcx_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); }
-template <int EW> struct TcxRegs { static constexpr int EPI = (EW == 8) ? TC_REGS_EPI : 104, AUX = TC_REGS_AUX; };   // 20 warps launch at 96: (640 * 96 - 128 * 56) / 512 = 106
+template <int EW> struct TcxRegs { static constexpr int EPI = (EW == 8) ? TC_REGS_EPI : (EW == 12 ? 152 : 104), AUX = TC_REGS_AUX; };   // 16 warps launch at 128: (512 * 128 - 128 * 56) / 384 = 152   // 20 warps launch at 96: (640 * 96 - 128 * 56) / 512 = 106
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -701,6 +701,8 @@ static int tcx_launch_cl(const void* packed, const NetView& net, const SegDev& a
     return tcx_launch_ew<NA, NB, TRAIN, 1, 16>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
   }
 #endif
+  // (12 epilogue warps — three sets, one 40-column group per warp and neuron half, 152 registers — were tried for the training forward:
+  //  parity green, 0.553-0.556 ms against 0.541: like the 16-warp variant, a shorter half epilogue only crowds the TMEM port)
   if (tcx_sincos_mode() == 0) return tcx_launch_ew<NA, NB, TRAIN, 0, 8>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
   return tcx_launch_ew<NA, NB, TRAIN, 1, 8>(cl, packed, net, a, b, ta, tb, gridN, first, out, tr, sms, st);
 }
