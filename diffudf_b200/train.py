@@ -128,6 +128,14 @@ class FusedTrainer:
             self._dev_t = self.t
         if g == "warm":
             sx, sn, sd = torch.empty_like(x), torch.empty_like(normals), torch.empty_like(d)
+            # the core's cached workspaces of THIS signature exist before the capture starts (a step of another shape may have evicted
+            # them since the warm-up step): an allocation inside the capture would put its zero-fill — 1.3 GB of operand images — into
+            # the graph and repeat it on every replay
+            prec = self.core._prec()
+            _, ld, nout = self.core.plan(mode, x.shape[0], n_on, weights, prec)
+            self.core._stashes(self.model.n_hidden, ld, prec)
+            self.core._buf("packed", (nout,))
+            self.core._buf("seeds", (nout,))
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(dev)
             try:
