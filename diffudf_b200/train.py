@@ -295,13 +295,13 @@ def _epoch_loop(dataset, model, device, config, stage_fn):
         misplaced = torch.zeros(1, device=device, dtype=torch.int64)      # rows that contradict the [on | off] layout (read per epoch)
         for x, n, d in feeder.feed((tuple(torch.as_tensor(t, dtype=torch.float32) for t in b) for b in iter(dataset))):
             n_on = getattr(dataset, "samplesOnSurface", None)
-            need_on = (mode == "s1" and weights[2] != 0) or mode == "s2"      # s2 evaluates the leading on-surface rows only
+            need_on = mode == "s1" and weights[2] != 0
             if n_on is None and need_on:
                 from .loss_functions import on_surface_prefix
                 n_on = on_surface_prefix(d)
                 if n_on is None:
                     raise RuntimeError("batches must be ordered [on-surface | off-surface] for the fused step")
-            elif need_on:
+            elif n_on is not None and (need_on or mode == "s2"):      # (s2 evaluates the leading on-surface rows only when it knows them)
                 # the reference masks the alignment term on d == 0 (loss_functions.py:45-53); the fused step takes the first n_on
                 # rows: count disagreements on the device, raise at the epoch's read-back
                 misplaced += (d[:n_on] != 0).sum() + (d[n_on:] == 0).sum()
